@@ -1,0 +1,101 @@
+"""ctypes binding of lib3dgp_b200.so -- the C ABI declared in include/gp3d_b200.h.
+
+There is deliberately NO fallback: if the shared library is missing and cannot be built (no nvcc), every op
+raises.  Nothing here imports oracle/.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib3dgp_b200.so')
+_lock = threading.Lock()
+_lib = None
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+
+class RaymarchOpts(ctypes.Structure):
+    """gp3d_raymarch_opts (include/gp3d_b200.h)."""
+    _fields_ = [
+        ('B', c_int), ('R', c_int), ('N', c_int), ('P', c_int), ('C', c_int), ('H', c_int),
+        ('ray_start', c_float), ('ray_end', c_float), ('box_half', c_float), ('noise_std', c_float),
+        ('use_inf_depth', c_int), ('last_back', c_int), ('white_back_end_idx', c_int), ('clamp_mode', c_int),
+        ('mlp_mode', c_int), ('seed', ctypes.c_uint64), ('offset', ctypes.c_uint64),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY symbol of include/gp3d_b200.h (tests/test_abi.py checks this).
+PROTOTYPES = {
+    'gp3d_last_error': (ctypes.c_char_p, []),
+    'gp3d_version': (c_int, []),
+    'gp3d_built_arch': (c_int, []),
+    'gp3d_bias_act': (c_int, [c_void_p] * 6 + [c_int, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    'gp3d_upfirdn2d_out_size': (c_int, [c_int] * 6),
+    'gp3d_upfirdn2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 4 + [c_int64] * 4 + [c_int] * 11 + [c_float]
+                       + [c_int] * 2 + [c_int64] * 4 + [c_void_p]),
+    'gp3d_filtered_lrelu_act': (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 4 + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p]),
+    'gp3d_raymarch_forward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 14 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
+    'gp3d_raymarch_backward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 19 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
+    'gp3d_modulate': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    'gp3d_demod_act': (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 6 + [c_float] * 3 + [c_void_p]),
+    'gp3d_grad_epilogue': (c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
+    'gp3d_gemm_bf16_tn': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
+    'gp3d_conv2d_nhwc_bf16': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+}
+
+
+def lib():
+    """Returns the loaded CDLL, building it first if the .so is absent and nvcc is available."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)       # AttributeError => header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        assert L.gp3d_built_arch() == 100, 'lib3dgp_b200.so was not built for sm_100a'
+        _lib = L
+    return _lib
+
+
+class Gp3dError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().gp3d_last_error().decode(errors='replace')
+        raise Gp3dError(f'{what} failed (code {rc}): {msg}')
+
+
+DTYPE_CODE = {'torch.float32': 0, 'torch.float16': 1, 'torch.bfloat16': 2}
+
+
+def dtype_code(t):
+    try:
+        return DTYPE_CODE[str(t.dtype)]
+    except KeyError:
+        raise Gp3dError(f'unsupported dtype {t.dtype}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name='tensor'):
+    if t.device.type != 'cuda':
+        raise Gp3dError(f'{name} must be a CUDA tensor: 3dgp_b200 has no CPU path (device={t.device})')

@@ -1,0 +1,246 @@
+// Error plumbing + small streaming kernels of lib3dgp_b200:
+//   modulate / demod_act  : the elementwise halves of modulated_conv2d (networks_stylegan2.py:67-76,142-144)
+//   filtered_lrelu_act    : sign-coded leaky-ReLU used by filtered_lrelu's generic path (filtered_lrelu.cu:1105-1211)
+//   grad_epilogue         : /world + nan_to_num of the flattened gradient (training_loop.py:340-341)
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void gp3d_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gp3d_last_error(void) { return g_err; }
+extern "C" int gp3d_version(void) { return 1; }
+extern "C" int gp3d_built_arch(void) {
+#ifdef GP3D_ARCH
+    return GP3D_ARCH;
+#else
+    return 100;
+#endif
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// y[n,c,hw] = x[n,c,hw] * s[n,c]   (cl: element index = (n*HW + hw)*C + c)
+template <class T, bool CL>
+__global__ void __launch_bounds__(256) modulate_kernel(const T* __restrict__ x, const T* __restrict__ s, T* __restrict__ y,
+                                                       int N, int C, int HW) {
+    constexpr int VEC = vec16<T>::N;
+    const int64_t nvec = (int64_t)N * C * HW / VEC;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = v * VEC;
+        vec16<T> vx; float f[VEC];
+        vx.load(x + i0); vx.unpack(f);
+        if (CL) {
+            const int c0 = (int)(i0 % C);
+            const int n = (int)(i0 / ((int64_t)C * HW));
+#pragma unroll
+            for (int k = 0; k < VEC; k++) f[k] *= io_traits<T>::ld(s + (int64_t)n * C + c0 + k);
+        } else {
+            const float sv = io_traits<T>::ld(s + i0 / HW);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) f[k] *= sv;
+        }
+        vx.pack(f); vx.store(y + i0);
+    }
+}
+
+// y = clamp(act(x * d[n,c] + noise[(n),hw] + b[c]) * gain), act in {linear(1), lrelu(3)}
+template <class T, bool CL, int ACT>
+__global__ void __launch_bounds__(256) demod_act_kernel(const T* __restrict__ x, const T* __restrict__ d,
+                                                        const T* __restrict__ noise, int noise_per_sample,
+                                                        const T* __restrict__ b, T* __restrict__ y,
+                                                        int N, int C, int HW, float alpha, float gain, float clamp) {
+    constexpr int VEC = vec16<T>::N;
+    const int64_t nvec = (int64_t)N * C * HW / VEC;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = v * VEC;
+        vec16<T> vx; float f[VEC];
+        vx.load(x + i0); vx.unpack(f);
+        if (CL) {
+            const int c0 = (int)(i0 % C);
+            const int64_t pix = i0 / C;                  // n*HW + hw
+            const int n = (int)(pix / HW);
+            const int hw = (int)(pix - (int64_t)n * HW);
+            const float nz = noise ? io_traits<T>::ld(noise + (noise_per_sample ? (int64_t)n * HW : 0) + hw) : 0.f;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const float dv = d ? io_traits<T>::ld(d + (int64_t)n * C + c0 + k) : 1.f;
+                const float bv = b ? io_traits<T>::ld(b + c0 + k) : 0.f;
+                f[k] = fmaf(f[k], dv, nz) + bv;
+            }
+        } else {
+            const int64_t nc = i0 / HW;
+            const int hw0 = (int)(i0 - nc * HW);
+            const int n = (int)(nc / C), c = (int)(nc - (int64_t)n * C);
+            const float dv = d ? io_traits<T>::ld(d + nc) : 1.f;
+            const float bv = b ? io_traits<T>::ld(b + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const float nz = noise ? io_traits<T>::ld(noise + (noise_per_sample ? (int64_t)n * HW : 0) + hw0 + k) : 0.f;
+                f[k] = fmaf(f[k], dv, nz) + bv;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            float t = f[k];
+            if (ACT == 3) t = (t > 0.f) ? t : t * alpha;
+            t *= gain;
+            if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
+            f[k] = t;
+        }
+        vx.pack(f); vx.store(y + i0);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) flrelu_act_kernel(T* x, uint8_t* si, int N, int C, int H, int W, int sH, int sW4,
+                                                         int sx, int sy, float gain, float slope, float clamp, int write_signs) {
+    // one thread per group of 4 consecutive x (one sign byte); grid (ceil(W/4/128), H, N*C)
+    const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    for (int nc = blockIdx.z; nc < N * C; nc += gridDim.z) {
+        if (xq * 4 >= W) continue;
+        T* row = x + ((int64_t)nc * H + yy) * W;
+        const int sxq = (xq * 4 + sx);       // sign x coordinate of element 0 (must be a multiple of 4 for byte packing)
+        const int syy = yy + sy;
+        const bool sign_ok = si && syy >= 0 && syy < sH;
+        uint8_t* sp = si ? si + ((int64_t)nc * sH + (sign_ok ? syy : 0)) * sW4 : nullptr;
+        uint32_t code = 0;
+        if (si && !write_signs) {
+            // read 4 codes starting at sign-x = sxq (may straddle two bytes when sx % 4 != 0)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int sxx = sxq + k;
+                uint32_t c = 0;
+                if (sign_ok && sxx >= 0 && (sxx >> 2) < sW4) c = (sp[sxx >> 2] >> ((sxx & 3) * 2)) & 3u;
+                code |= c << (2 * k);
+            }
+        }
+        uint32_t wcode = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int xx = xq * 4 + k;
+            if (xx >= W) break;
+            float v = io_traits<T>::ld(row + xx);
+            if (si && !write_signs) {
+                const uint32_t c = (code >> (2 * k)) & 3u;
+                v *= (c == 0) ? gain : (c == 1) ? gain * slope : 0.f;
+            } else {
+                uint32_t c = 0;
+                if (v < 0.f) { v *= slope; c = 1; }
+                v *= gain;
+                if (clamp >= 0.f && fabsf(v) > clamp) { v = copysignf(clamp, v); c = 2; }   // clamped => code 2 (zero gradient)
+                wcode |= c << (2 * k);
+            }
+            io_traits<T>::st(row + xx, v);
+        }
+        if (si && write_signs && sign_ok && (sxq & 3) == 0 && sxq >= 0 && (sxq >> 2) < sW4) sp[sxq >> 2] = (uint8_t)wcode;
+    }
+}
+
+__global__ void __launch_bounds__(256) grad_epilogue_kernel(float* g, int64_t numel, float inv_world, float posinf, float neginf) {
+    const int64_t nvec = numel / 4;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        float4 t = reinterpret_cast<float4*>(g)[v];
+        float f[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float a = f[k] * inv_world;
+            a = (a != a) ? 0.f : a;
+            a = fminf(fmaxf(a, neginf), posinf);       // maps +-inf to posinf / neginf (torch.nan_to_num semantics) and clamps
+            f[k] = a;
+        }
+        reinterpret_cast<float4*>(g)[v] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    if (blockIdx.x == 0) {
+        const int64_t i = nvec * 4 + threadIdx.x;
+        if (i < numel) {
+            float a = g[i] * inv_world;
+            a = (a != a) ? 0.f : a;
+            g[i] = fminf(fmaxf(a, neginf), posinf);
+        }
+    }
+}
+
+template <class T>
+int launch_modulate(const void* x, const void* s, void* y, int N, int C, int HW, int cl, cudaStream_t st) {
+    constexpr int VEC = vec16<T>::N;
+    const int64_t total = (int64_t)N * C * HW;
+    if (total % VEC || (!cl && HW % VEC) || (cl && C % VEC) || !gp3d_aligned16(x) || !gp3d_aligned16(y)) return GP3D_E_UNSUPPORTED;
+    const int grid = gp3d_grid_for(total / VEC, 256, 8);
+    if (cl) modulate_kernel<T, true><<<grid, 256, 0, st>>>((const T*)x, (const T*)s, (T*)y, N, C, HW);
+    else modulate_kernel<T, false><<<grid, 256, 0, st>>>((const T*)x, (const T*)s, (T*)y, N, C, HW);
+    return 0;
+}
+
+template <class T>
+int launch_demod(const void* x, const void* d, const void* noise, int nps, const void* b, void* y, int N, int C, int HW,
+                 int cl, int act, float alpha, float gain, float clamp, cudaStream_t st) {
+    constexpr int VEC = vec16<T>::N;
+    const int64_t total = (int64_t)N * C * HW;
+    if (total % VEC || (!cl && HW % VEC) || (cl && C % VEC) || !gp3d_aligned16(x) || !gp3d_aligned16(y)) return GP3D_E_UNSUPPORTED;
+    const int grid = gp3d_grid_for(total / VEC, 256, 8);
+#define GP3D_DEMOD(CLV, ACTV) demod_act_kernel<T, CLV, ACTV><<<grid, 256, 0, st>>>((const T*)x, (const T*)d, (const T*)noise, nps, (const T*)b, (T*)y, N, C, HW, alpha, gain, clamp)
+    if (cl) { if (act == 3) GP3D_DEMOD(true, 3); else GP3D_DEMOD(true, 1); }
+    else    { if (act == 3) GP3D_DEMOD(false, 3); else GP3D_DEMOD(false, 1); }
+#undef GP3D_DEMOD
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gp3d_modulate(const void* x, const void* s, void* y, int dtype, int N, int C, int HW, int cl, void* stream) {
+    GP3D_CHECK_ARG(x && s && y && N >= 1 && C >= 1 && HW >= 1, "modulate: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = dtype == GP3D_F32 ? launch_modulate<float>(x, s, y, N, C, HW, cl, st)
+          : dtype == GP3D_F16 ? launch_modulate<__half>(x, s, y, N, C, HW, cl, st)
+          : dtype == GP3D_BF16 ? launch_modulate<__nv_bfloat16>(x, s, y, N, C, HW, cl, st) : GP3D_E_BADARG;
+    if (r != 0) { gp3d_set_error("modulate: unsupported shape/alignment (N=%d C=%d HW=%d cl=%d)", N, C, HW, cl); return r; }
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_demod_act(const void* x, const void* d, const void* noise, int noise_per_sample, const void* b,
+                              void* y, int dtype, int N, int C, int HW, int cl,
+                              int act, float alpha, float gain, float clamp, void* stream) {
+    GP3D_CHECK_ARG(x && y && N >= 1 && C >= 1 && HW >= 1, "demod_act: bad arguments");
+    GP3D_CHECK_ARG(act == 1 || act == 3, "demod_act: only linear (1) and lrelu (3) are fused, got %d", act);
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = dtype == GP3D_F32 ? launch_demod<float>(x, d, noise, noise_per_sample, b, y, N, C, HW, cl, act, alpha, gain, clamp, st)
+          : dtype == GP3D_F16 ? launch_demod<__half>(x, d, noise, noise_per_sample, b, y, N, C, HW, cl, act, alpha, gain, clamp, st)
+          : dtype == GP3D_BF16 ? launch_demod<__nv_bfloat16>(x, d, noise, noise_per_sample, b, y, N, C, HW, cl, act, alpha, gain, clamp, st)
+                               : GP3D_E_BADARG;
+    if (r != 0) { gp3d_set_error("demod_act: unsupported shape/alignment (N=%d C=%d HW=%d cl=%d)", N, C, HW, cl); return r; }
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_filtered_lrelu_act(void* x, uint8_t* si, int dtype, int N, int C, int H, int W,
+                                       int sH, int sW4, int sx, int sy, float gain, float slope, float clamp,
+                                       int write_signs, void* stream) {
+    GP3D_CHECK_ARG(x && N >= 1 && C >= 1 && H >= 1 && W >= 1, "filtered_lrelu_act: bad arguments");
+    GP3D_CHECK_ARG(!si || (sH >= 1 && sW4 >= 1), "filtered_lrelu_act: bad sign tensor geometry");
+    GP3D_CHECK_ARG(!(si && write_signs) || (sx & 3) == 0, "filtered_lrelu_act: sign x-offset must be a multiple of 4 when writing");
+    GP3D_CHECK_ARG(H <= 65535, "filtered_lrelu_act: H too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((W + 4 * 128 - 1) / (4 * 128), H, (unsigned)min((int64_t)N * C, (int64_t)65535));
+    if (dtype == GP3D_F32) flrelu_act_kernel<float><<<grid, 128, 0, st>>>((float*)x, si, N, C, H, W, sH, sW4, sx, sy, gain, slope, clamp, write_signs);
+    else if (dtype == GP3D_F16) flrelu_act_kernel<__half><<<grid, 128, 0, st>>>((__half*)x, si, N, C, H, W, sH, sW4, sx, sy, gain, slope, clamp, write_signs);
+    else if (dtype == GP3D_BF16) flrelu_act_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((__nv_bfloat16*)x, si, N, C, H, W, sH, sW4, sx, sy, gain, slope, clamp, write_signs);
+    else { gp3d_set_error("filtered_lrelu_act: unsupported dtype %d", dtype); return GP3D_E_BADARG; }
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, float posinf, float neginf, void* stream) {
+    GP3D_CHECK_ARG(g && numel >= 0, "grad_epilogue: bad arguments");
+    GP3D_CHECK_ARG(gp3d_aligned16(g), "grad_epilogue: buffer must be 16-byte aligned");
+    if (numel == 0) return GP3D_OK;
+    grad_epilogue_kernel<<<gp3d_grid_for(numel / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, numel, inv_world, posinf, neginf);
+    GP3D_RETURN_LAUNCH();
+}

@@ -1,0 +1,109 @@
+"""conv2d / conv_transpose2d with arbitrarily high order gradients and the `no_weight_gradients()` switch the loss
+uses for R1 / path-length regularisation (reference src/torch_utils/ops/conv2d_gradfix.py:24-172).
+
+Engine selection: shapes covered by the tcgen05 implicit-GEMM kernels of lib3dgp_b200 (csrc/conv_tc.cu) are routed
+there by `..ops.modconv`; everything else (tiny 4x4..16x16 layers, 5x5 depth-adaptor convs, strided / transposed
+forms) goes through ATen's convolution, exactly the library call the reference makes (conv2d_gradfix.py:113-115).
+"""
+import contextlib
+
+import torch
+
+enabled = False                     # kept for training_loop.py:78 (`conv2d_gradfix.enabled = True`)
+weight_gradients_disabled = False   # toggled by no_weight_gradients()
+
+
+@contextlib.contextmanager
+def no_weight_gradients(disable=True):
+    global weight_gradients_disabled
+    old = weight_gradients_disabled
+    if disable:
+        weight_gradients_disabled = True
+    yield
+    weight_gradients_disabled = old
+
+
+def _tuple2(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    if input.device.type != 'cuda':
+        raise RuntimeError('3dgp_b200.conv2d_gradfix: CUDA tensors only (no CPU path)')
+    return _conv(False, weight.shape, _tuple2(stride), _tuple2(padding), (0, 0), _tuple2(dilation), groups).apply(input, weight, bias)
+
+
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    if input.device.type != 'cuda':
+        raise RuntimeError('3dgp_b200.conv2d_gradfix: CUDA tensors only (no CPU path)')
+    return _conv(True, weight.shape, _tuple2(stride), _tuple2(padding), _tuple2(output_padding), _tuple2(dilation), groups).apply(input, weight, bias)
+
+
+_cache = dict()
+
+
+def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
+    weight_shape = tuple(weight_shape)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
+    if key in _cache:
+        return _cache[key]
+    ndim = 2
+    kw = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+
+    def out_pad_for(input_shape, output_shape):
+        # output_padding of the adjoint operator (conv2d_gradfix.py:95-105)
+        if transpose:
+            return (0, 0)
+        return tuple(input_shape[i + 2] - (output_shape[i + 2] - 1) * stride[i] - (1 - 2 * padding[i])
+                     - dilation[i] * (weight_shape[i + 2] - 1) for i in range(ndim))
+
+    class Conv2d(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, weight, bias):
+            assert tuple(weight.shape) == weight_shape
+            if not transpose:
+                out = torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, **kw)
+            else:
+                out = torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, output_padding=output_padding, **kw)
+            ctx.save_for_backward(input, weight, bias)
+            return out
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            input, weight, bias = ctx.saved_tensors
+            gi = gw = gb = None
+            if ctx.needs_input_grad[0]:
+                p = out_pad_for(input.shape, grad_output.shape)
+                gi = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups).apply(grad_output, weight, None)
+                assert gi.shape == input.shape
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                gw = Conv2dGradWeight.apply(grad_output, input, bias)
+                assert tuple(gw.shape) == weight_shape
+            if ctx.needs_input_grad[2]:
+                gb = grad_output.sum([0, 2, 3])
+            return gi, gw, gb
+
+    class Conv2dGradWeight(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, grad_output, input, bias):
+            bias_shape = bias.shape if bias is not None else None
+            empty_w = torch.empty(weight_shape, dtype=input.dtype, layout=input.layout, device=input.device)
+            gw = torch.ops.aten.convolution_backward(
+                grad_output, input, empty_w, bias_sizes=bias_shape, stride=stride, padding=padding, dilation=dilation,
+                transposed=transpose, output_padding=output_padding, groups=groups, output_mask=[False, True, False])[1]
+            ctx.save_for_backward(grad_output, input)
+            return gw
+
+        @staticmethod
+        def backward(ctx, g2_gw):
+            grad_output, input = ctx.saved_tensors
+            g2_go = g2_in = None
+            if ctx.needs_input_grad[0]:
+                g2_go = Conv2d.apply(input, g2_gw, None)
+            if ctx.needs_input_grad[1]:
+                p = out_pad_for(input.shape, grad_output.shape)
+                g2_in = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups).apply(grad_output, g2_gw, None)
+            return g2_go, g2_in, None
+
+    _cache[key] = Conv2d
+    return Conv2d

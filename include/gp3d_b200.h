@@ -1,0 +1,180 @@
+/*
+ * gp3d_b200.h -- C ABI of lib3dgp_b200.so, the sm_100a implementation of 3DGP's per-image hot path.
+ *
+ * Every entry point replaces one function of the reference's native plugin layer
+ * (pybind11 modules built by src/torch_utils/custom_ops.py::get_plugin) or one
+ * library call site on the hot path.  The reference's boundary passes torch::Tensor; this ABI is
+ * the layer directly below it: plain device pointers, sizes, strides and a cudaStream_t.  The Python
+ * shim in 3dgp_b200/torch_utils/custom_ops.py re-creates the reference's plugin objects
+ * (`bias_act_plugin.bias_act(...)`, `upfirdn2d_plugin.upfirdn2d(...)`, ...) on top of these calls.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name starts with h_;
+ *   - `stream` is a cudaStream_t (pass 0 for the legacy default stream); launches are asynchronous;
+ *   - return value: 0 = ok, <0 = invalid argument (GP3D_E_*), >0 = cudaError_t of the failed launch;
+ *     gp3d_last_error() returns a static human-readable string for the last failure on this thread;
+ *   - dtype codes: 0 = float32, 1 = float16, 2 = bfloat16;
+ *   - strides are in ELEMENTS.
+ *   - callee never allocates: outputs are caller-allocated (the reference's callee-allocates contract,
+ *     bias_act.cpp:55 / upfirdn2d.cpp:38, is restored by the Python shim with torch.empty).
+ */
+#ifndef GP3D_B200_H_
+#define GP3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP3D_OK            0
+#define GP3D_E_BADARG     -1
+#define GP3D_E_UNSUPPORTED -2
+#define GP3D_E_TOOLARGE   -3
+
+#define GP3D_F32  0
+#define GP3D_F16  1
+#define GP3D_BF16 2
+
+const char* gp3d_last_error(void);
+int         gp3d_version(void);            /* ABI version, currently 1 */
+int         gp3d_built_arch(void);         /* 100 => sm_100a */
+
+/* ------------------------------------------------------------------------------------------------
+ * bias_act  -- replaces bias_act_plugin.bias_act (reference src/torch_utils/ops/bias_act.cpp:32-90,
+ * kernel bias_act.cu:23-147).  y = clamp(act(x + b[(i / stepB) % sizeB]) * gain) for grad == 0;
+ * grad == 1 / 2: first / second derivative forms (x := dy resp. d_dx; xref, yref, dy as in
+ * bias_act.py:179,198).  b / xref / yref / dy may be NULL ("absent", the reference's empty tensor).
+ * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish (bias_act.py:22-30).
+ * clamp < 0 disables clamping.  numel <= INT32_MAX (bias_act.cpp:50).
+ */
+int gp3d_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy,
+                  void* y, int dtype, int64_t numel, int64_t sizeB, int64_t stepB,
+                  int grad, int act, float alpha, float gain, float clamp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * upfirdn2d -- replaces upfirdn2d_plugin.upfirdn2d (reference upfirdn2d.cpp:16-100, kernels
+ * upfirdn2d.cu:29-200).  Per channel: zero-insert upsample (upx,upy) -> pad/crop (pad*) -> FIR with the
+ * float32 filter f[fh][fw] (true convolution unless flip != 0) -> keep every (downx,downy)-th sample.
+ * Output extent is computed by the CALLER with gp3d_upfirdn2d_out_size() (integer formula of
+ * upfirdn2d.cpp:35-36) and must be >= 1.
+ * x: [N,C,inH,inW] addressed through strides (NCHW or channels-last); y likewise.
+ */
+int gp3d_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int fsize);
+int gp3d_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                   int N, int C, int inH, int inW,
+                   int64_t xsN, int64_t xsC, int64_t xsH, int64_t xsW,
+                   int fh, int fw, int upx, int upy, int downx, int downy,
+                   int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                   int outH, int outW,
+                   int64_t ysN, int64_t ysC, int64_t ysH, int64_t ysW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * filtered_lrelu_act_ -- replaces filtered_lrelu_plugin.filtered_lrelu_act_ (filtered_lrelu.cpp:213-298,
+ * kernel filtered_lrelu.cu:1105-1211).  In place on x [N,C,H,W] (NCHW contiguous):
+ *   write_signs=1: s = sign/clamp code of x (bit0: x<0, bit1: |gain*lrelu(x)|>clamp), 2 bits per element
+ *                  packed 4 per byte along W into si[N,C,sH,sW4] at offset (sx,sy); x = clamp(lrelu(x)*gain)
+ *   write_signs=0, si != NULL: x *= (code==0 ? gain : code==1 ? gain*slope : 0) using stored codes
+ *   si == NULL: plain x = clamp(lrelu(x)*gain).
+ */
+int gp3d_filtered_lrelu_act(void* x, uint8_t* si, int dtype, int N, int C, int H, int W,
+                            int sH, int sW4, int sx, int sy, float gain, float slope, float clamp,
+                            int write_signs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused tri-plane ray-march (forward).  Replaces the ~25 torch ops of ImportanceRenderer.forward
+ * (reference src/training/tri_plane_renderer.py:126-170) together with simple_tri_plane_renderer
+ * (:560-588, ATen grid_sampler_2d), TriPlaneMLP.forward (networks_epigraf.py:46-68),
+ * sample_stratified (:208-235), sample_importance/sample_pdf (:237-295), unify_samples (:196-206) and
+ * ClassicalRayMarcher.forward (:353-405).  No per-sample tensor is written to HBM.
+ *
+ * planes   : [B][3 planes][C=32 ch][P][P] addressed by element strides (psB, psP, psC, psY, psX).
+ *            Fast path: psC == 1 (channel-minor / channels-last storage).  dtype f32 or f16.
+ * ray_o/d  : [B][R][3] float32 contiguous.
+ * w1,b1    : first FC layer raw parameters [H=64][32], [64]; w2,b2: [4][64],[4] (float32, row-major);
+ *            the reference's runtime weight gains 1/sqrt(fan_in) (layers.py:39,47) are applied inside.
+ * u_coarse : [B][R][N] uniform(0,1) stratification jitter (tri_plane_renderer.py:225), or NULL => Philox.
+ * u_fine   : [B][R][N] uniform(0,1) inverse-CDF variates (:279), or NULL => Philox.
+ * sn_coarse/sn_fine : optional [B][R][N] standard-normal density noise (:185-186), scaled by noise_std.
+ * outputs  : rgb [B][R][3], depth [B][R], wsum [B][R], tfinal [B][R]  (float32).
+ */
+typedef struct gp3d_raymarch_opts {
+    int   B, R, N;            /* batch, rays per image, samples per pass (coarse == fine == N, N <= 64) */
+    int   P;                  /* plane resolution */
+    int   C;                  /* feature channels per plane (32) */
+    int   H;                  /* MLP hidden width (64) */
+    float ray_start, ray_end; /* cfg.camera.ray.{start,end} */
+    float box_half;           /* box_size / 2 = cfg.camera.cube_scale; coords are divided by it (tri_plane_renderer.py:576) */
+    float noise_std;          /* rendering_options['density_noise'] */
+    int   use_inf_depth;      /* last delta 1e10 (1) or 1e-3 (0), tri_plane_renderer.py:356 */
+    int   last_back;          /* :386-387 */
+    int   white_back_end_idx; /* :392-395 */
+    int   clamp_mode;         /* 0 softplus, 1 relu (:359-364) */
+    int   mlp_mode;           /* 0 = fp32 SIMT, 1 = TF32 mma.sync, 2 = 3xTF32 error-compensated mma.sync */
+    uint64_t seed, offset;    /* Philox stream when u_* are NULL */
+} gp3d_raymarch_opts;
+
+int gp3d_raymarch_forward(const void* planes, int planes_dtype,
+                          int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
+                          const float* ray_o, const float* ray_d,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* u_coarse, const float* u_fine,
+                          const float* sn_coarse, const float* sn_fine,
+                          float* rgb, float* depth, float* wsum, float* tfinal,
+                          const gp3d_raymarch_opts* opts, void* stream);
+
+/* Backward of the above.  Recomputes the forward per ray block (nothing was saved), then back-propagates
+ * g_rgb [B][R][3] and g_depth [B][R] into
+ *   g_planes (same strides as planes, float32, ACCUMULATED with red.global.add -- caller zero-fills),
+ *   g_w1,g_b1,g_w2,g_b2 (accumulated, caller zero-fills), g_ray_o / g_ray_d [B][R][3] (overwritten; may be NULL).
+ * The importance-sampled depths are constants (tri_plane_renderer.py:241,254 no_grad + detach).
+ * Requires the SAME u_* / sn_* inputs (or the same Philox seed/offset) as the forward call.
+ */
+int gp3d_raymarch_backward(const void* planes, int planes_dtype,
+                           int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
+                           const float* ray_o, const float* ray_d,
+                           const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* u_coarse, const float* u_fine,
+                           const float* sn_coarse, const float* sn_fine,
+                           const float* g_rgb, const float* g_depth,
+                           float* g_planes, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                           float* g_ray_o, float* g_ray_d,
+                           const gp3d_raymarch_opts* opts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise fusions around the modulated convolution (reference networks_stylegan2.py:67-76, 142-144):
+ *   gp3d_modulate   : y[n,c,h,w] = x[n,c,h,w] * s[n,c]                         (x * styles, :68)
+ *   gp3d_demod_act  : y = clamp(lrelu(x * d[n,c] + noise[n?,h,w] * nstr + b[c]) * gain)
+ *                     == fma.fma (:71) followed by bias_act.bias_act (:144) in one pass.
+ * NCHW-contiguous or channels-last (cl != 0), float32/16/bf16.
+ */
+int gp3d_modulate(const void* x, const void* s, void* y, int dtype, int N, int C, int HW, int cl, void* stream);
+int gp3d_demod_act(const void* x, const void* d, const void* noise, int noise_per_sample, const void* b,
+                   void* y, int dtype, int N, int C, int HW, int cl,
+                   int act, float alpha, float gain, float clamp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gradient all-reduce epilogue (reference training_loop.py:340-341): in place
+ *   g = nan_to_num(g / world, nan=0, posinf=1e5, neginf=-1e5)    over a flat float32 buffer.
+ */
+int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, float posinf, float neginf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 / TMEM (sm_100a):  D[M][N] (+)= A[M][K] * B[N][K]^T, bf16 operands,
+ * fp32 accumulate in TMEM, TMA-fed 128B-swizzled smem tiles.  This is the engine under the modulated /
+ * discriminator convolutions (implicit GEMM: the conv front-end lays the im2col tiles out through TMA).
+ * M % 128 == 0, N % 128 == 0, K % 64 == 0.  A,B row-major bf16 (K contiguous); D row-major float32.
+ */
+int gp3d_gemm_bf16_tn(const void* A, const void* B, float* D, int M, int N, int K, int accumulate, void* stream);
+
+/* 3x3 / 1x1 stride-1 "same" convolution as an implicit GEMM on tcgen05 (NHWC bf16 activations,
+ * weights [Cout][kh][kw][Cin] bf16, fp32 NHWC output).  Replaces the cuDNN call of
+ * conv2d_gradfix.py:113 for the hot shapes.  Cin % 64 == 0, Cout % 128 == 0, W % 8 == 0.
+ */
+int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
+                          int ksize, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GP3D_B200_H_ */
