@@ -1,0 +1,39 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def gp():
+    """The product package (directory name starts with a digit -> importlib)."""
+    return importlib.import_module('3dgp_b200')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    import numpy as np
+    d = os.path.join(ROOT, 'tests', 'golden')
+
+    def load(name):
+        return np.load(os.path.join(d, name + '.npz'))
+    return load

@@ -1,0 +1,144 @@
+"""GPU parity suite for the plugin ops: sm_100a kernels (through the reference-shaped plugin objects and the C ABI)
+vs the golden vectors produced by the unmodified reference, and vs the CPU oracle on fresh seeds."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, restated as R
+from util import maxrel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # fp32 ops: only summation order / fma contraction / fast-math intrinsics differ
+
+
+def _ops():
+    return (importlib.import_module('3dgp_b200.torch_utils.ops.bias_act'),
+            importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d'),
+            importlib.import_module('3dgp_b200.torch_utils.ops.filtered_lrelu'))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('name,kw', cases.upfirdn2d_cases(), ids=[c[0] for c in cases.upfirdn2d_cases()])
+def test_upfirdn2d_vs_golden(golden, name, kw):
+    _, up, _ = _ops()
+    x, f = cases.upfirdn2d_inputs(name, kw)
+    g = golden('upfirdn2d')[name]
+    ft = None if f is None else cu(f)
+    y = up.upfirdn2d(cu(x), ft, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain'])
+    assert tuple(y.shape) == g.shape                       # integer index formula
+    if kw.get('integer', False):
+        assert np.array_equal(y.cpu().numpy(), g)          # bit-exact
+    else:
+        assert maxrel(y.cpu().numpy(), g) < TOL
+    # channels-last storage goes through the C-minor kernel and must give the same numbers
+    if x.shape[1] % 4 == 0 and f is not None and f.ndim == 2:
+        ycl = up.upfirdn2d(cu(x).contiguous(memory_format=torch.channels_last), ft, up=kw['up'], down=kw['down'], padding=kw['padding'],
+                           flip_filter=kw['flip_filter'], gain=kw['gain'])
+        assert ycl.stride(1) == 1
+        assert torch.equal(ycl.contiguous(), y)
+
+
+def test_upfirdn2d_gradient_is_adjoint():
+    _, up, _ = _ops()
+    rs = np.random.RandomState(3)
+    x = cu(rs.standard_normal((2, 3, 9, 11)).astype(np.float32)).requires_grad_(True)
+    f = cu(cases._f2d(cases.F1331))
+    y = up.upfirdn2d(x, f, up=2, down=1, padding=[2, 1, 2, 1], gain=4)
+    dy = cu(rs.standard_normal(tuple(y.shape)).astype(np.float32))
+    (dx,) = torch.autograd.grad(y, x, dy)
+    # <A x, dy> == <x, A^T dy>
+    lhs = (y * dy).sum().item(); rhs = (x * dx).sum().item()
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
+    xo = x.detach().cpu().numpy()
+    yo = R.upfirdn2d(xo, f.cpu().numpy(), up=2, padding=[2, 1, 2, 1], gain=4)
+    assert maxrel(y.detach().cpu().numpy(), yo) < TOL
+
+
+def test_upfirdn2d_fp16_and_large_shape_properties():
+    _, up, _ = _ops()
+    f = cu(cases._f2d(cases.F1331))
+    # BASELINE-size layer: [B,128,256,256] -> up 2 (skip path).  Linearity + DC gain (filter sums to 1, gain 4 = up^2).
+    x = torch.ones([2, 128, 256, 256], device='cuda')
+    y = up.upsample2d(x, f)
+    assert tuple(y.shape) == (2, 128, 512, 512)
+    inner = y[:, :, 4:-4, 4:-4]
+    assert torch.allclose(inner, torch.ones_like(inner), atol=1e-6)
+    a = torch.randn([1, 64, 128, 128], device='cuda'); b = torch.randn_like(a)
+    assert torch.allclose(up.upsample2d(a + 2 * b, f), up.upsample2d(a, f) + 2 * up.upsample2d(b, f), atol=1e-4)
+    xh = torch.randn([2, 8, 32, 32], device='cuda', dtype=torch.float16)
+    yh = up.downsample2d(xh, f)
+    yo = R.downsample2d(xh.float().cpu().numpy(), f.cpu().numpy())
+    assert yh.dtype == torch.float16 and maxrel(yh.float().cpu().numpy(), yo) < 2e-3
+
+
+def test_upfirdn2d_errors():
+    _, up, _ = _ops()
+    with pytest.raises(RuntimeError):
+        up.upfirdn2d(torch.zeros([1, 1, 2, 2], device='cuda'), cu(cases._f2d([1, 4, 6, 4, 1])))   # output < 1x1
+    with pytest.raises(RuntimeError):
+        up._plugin.upfirdn2d(torch.zeros([1, 1, 4, 4], device='cuda'), torch.ones([2, 2], device='cuda', dtype=torch.float16), 1, 1, 1, 1, 0, 0, 0, 0, False, 1.0)
+
+
+@pytest.mark.parametrize('name,kw', cases.bias_act_cases(), ids=[c[0] for c in cases.bias_act_cases()])
+def test_bias_act_vs_golden(golden, name, kw):
+    ba, _, _ = _ops()
+    x, b = cases.bias_act_inputs(name, kw)
+    g = golden('bias_act')
+    xt = cu(x).requires_grad_(True)
+    bt = cu(b).requires_grad_(True) if b is not None else None
+    y = ba.bias_act(xt, bt, dim=kw['dim'], act=kw['act'], alpha=kw.get('alpha'), gain=kw.get('gain'), clamp=kw.get('clamp'))
+    assert maxrel(y.detach().cpu().numpy(), g[name + '/y']) < TOL
+    dy = cu(cases.cotangent(y.shape, 11))
+    gr = torch.autograd.grad(y, [xt] + ([bt] if bt is not None else []), dy, create_graph=True)
+    assert maxrel(gr[0].detach().cpu().numpy(), g[name + '/dx']) < 5e-5
+    if bt is not None:
+        assert maxrel(gr[1].detach().cpu().numpy(), g[name + '/db']) < 5e-5
+    if (name + '/d2x') in g.files and gr[0].requires_grad:
+        v = cu(cases.cotangent(y.shape, 12))
+        g2 = torch.autograd.grad(gr[0], xt, v, allow_unused=True)[0]
+        g2 = torch.zeros_like(xt) if g2 is None else g2
+        ref2 = g[name + '/d2x']
+        assert np.abs(g2.cpu().numpy() - ref2).max() < 5e-5 * max(1.0, np.abs(ref2).max())
+
+
+def test_bias_act_half_and_channels_last():
+    ba, _, _ = _ops()
+    x = torch.randn([4, 16, 8, 8], device='cuda')
+    b = torch.randn([16], device='cuda')
+    y = ba.bias_act(x, b, act='lrelu')
+    ycl = ba.bias_act(x.contiguous(memory_format=torch.channels_last), b, act='lrelu')
+    assert torch.equal(ycl.contiguous(), y)
+    yh = ba.bias_act(x.half(), b.half(), act='lrelu', clamp=256)
+    assert maxrel(yh.float().cpu().numpy(), y.cpu().numpy()) < 3e-3
+    yb = ba.bias_act(x.bfloat16(), b.bfloat16(), act='lrelu')
+    assert maxrel(yb.float().cpu().numpy(), y.cpu().numpy()) < 2e-2
+
+
+def test_bias_act_full_size_roundtrip():
+    """BASELINE-size tensor (one 512^2 x 128 layer of one image): grad of lrelu through saved y is +-gain mask."""
+    ba, _, _ = _ops()
+    x = torch.randn([1, 128, 512, 512], device='cuda', requires_grad=True)
+    y = ba.bias_act(x, None, act='lrelu')
+    (dx,) = torch.autograd.grad(y.sum(), x)
+    g = float(np.sqrt(2))
+    expect = torch.where(x > 0, torch.full_like(x, g), torch.full_like(x, 0.2 * g))
+    assert torch.allclose(dx, expect, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('name,kw', cases.filtered_lrelu_cases(), ids=[c[0] for c in cases.filtered_lrelu_cases()])
+def test_filtered_lrelu_vs_golden(golden, name, kw):
+    _, _, fl = _ops()
+    x, fu, fd, b = cases.filtered_lrelu_inputs(name, kw)
+    g = golden('filtered_lrelu')
+    xt = cu(x).requires_grad_(True); bt = cu(b).requires_grad_(True)
+    y = fl.filtered_lrelu(xt, cu(fu), cu(fd), bt, up=kw['up'], down=kw['down'], padding=kw['padding'], gain=kw['gain'], slope=kw['slope'], clamp=kw['clamp'])
+    assert maxrel(y.detach().cpu().numpy(), g[name + '/y']) < TOL
+    dy = cu(cases.cotangent(y.shape, 13))
+    gx, gb = torch.autograd.grad(y, [xt, bt], dy)
+    assert maxrel(gx.cpu().numpy(), g[name + '/dx']) < 5e-5
+    assert maxrel(gb.cpu().numpy(), g[name + '/db']) < 5e-5
