@@ -70,7 +70,12 @@ class Gp3dError(RuntimeError):
     pass
 
 
+launch_count = 0   # number of successful kernel-launching C-ABI calls in this process (bench.py: gpu_launches)
+
+
 def check(rc, what=''):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = lib().gp3d_last_error().decode(errors='replace')
         raise Gp3dError(f'{what} failed (code {rc}): {msg}')

@@ -30,6 +30,7 @@ struct Block {
     float* s_fi;   // [TR][NP]   fine depths, s-space, ascending
     float4* out_co;  // [TR][N+1] (r,g,b,sigma) of coarse samples
     float4* out_fi;  // [TR][N+1]
+    unsigned char* fperm;   // [TR][N]  fperm[k] = index (in u_fine order) of the k-th smallest fine sample
     int N, NP;
 
     static __host__ __device__ int np(int N) { return N | 1; }
@@ -37,7 +38,9 @@ struct Block {
         size_t f = kC * kH + kH + kH * 4 + 4 + kWarps * kC * 33 + TR * 3 * 2 + 3 * TR * np(N);
         return (f + 3) & ~(size_t)3;
     }
-    static __host__ __device__ size_t bytes(int N) { return floats_before_out(N) * 4 + 2 * (size_t)TR * (N + 1) * 16; }
+    static __host__ __device__ size_t bytes(int N) {
+        return floats_before_out(N) * 4 + 2 * (size_t)TR * (N + 1) * 16 + (((size_t)TR * N + 15) & ~(size_t)15);
+    }
 
     __device__ void carve(unsigned char* raw, int N_) {
         N = N_; NP = np(N_);
@@ -53,6 +56,7 @@ struct Block {
         s_fi = cdf + TR * NP;
         out_co = reinterpret_cast<float4*>(w1s + floats_before_out(N_));
         out_fi = out_co + TR * (N + 1);
+        fperm = reinterpret_cast<unsigned char*>(out_fi + TR * (N + 1));
     }
 };
 
@@ -183,8 +187,11 @@ __device__ __forceinline__ void forward_passes(const Block<TR>& s, const Params&
             __syncwarp();
             if (valid) {
                 if (p.o.noise_std > 0.f) {
+                    // the reference draws the noise in sample-generation order (tri_plane_renderer.py:186); fine samples were
+                    // sorted afterwards here, so map back through fperm
                     const float* sn = pass ? p.sn_fine : p.sn_coarse;
-                    const float z = sn ? sn[(ray_base + rl) * N + i] : rng_normal(p.o, (uint64_t)(ray_base + rl), i, 2 + pass);
+                    const int ni = pass ? (int)s.fperm[rl * N + i] : i;
+                    const float z = sn ? sn[(ray_base + rl) * N + ni] : rng_normal(p.o, (uint64_t)(ray_base + rl), ni, 2 + pass);
                     o.w += z * p.o.noise_std;
                 }
                 outp[rl * (N + 1) + i] = o;
@@ -199,6 +206,7 @@ __device__ __forceinline__ void forward_passes(const Block<TR>& s, const Params&
                 const float* sc = s.s_co + rl * NP;
                 float* cd = s.cdf + rl * NP;
                 float* sf = s.s_fi + rl * NP;
+                unsigned char* pm = s.fperm + rl * N;
                 float T = 1.f;
                 for (int i = 0; i < N; i++) {
                     const float sig = density_act(s.out_co[rl * (N + 1) + i].w, p.o.clamp_mode);
@@ -226,8 +234,8 @@ __device__ __forceinline__ void forward_passes(const Block<TR>& s, const Params&
                     const float b1v = 0.5f * (sc[above] + sc[above + 1]);
                     const float v = b0 + (u - c0) / den * (b1v - b0);
                     int j = k;                         // insertion into the sorted prefix sf[0..k)
-                    while (j > 0 && sf[j - 1] > v) { sf[j] = sf[j - 1]; j--; }
-                    sf[j] = v;
+                    while (j > 0 && sf[j - 1] > v) { sf[j] = sf[j - 1]; pm[j] = pm[j - 1]; j--; }
+                    sf[j] = v; pm[j] = (unsigned char)k;
                 }
             }
             __syncthreads();

@@ -16,6 +16,9 @@ import torch
 from ... import _lib
 
 
+TIMING = None   # set to a list to collect (start_event, end_event) pairs around the forward kernel (bench.py roofline)
+
+
 def planes_channel_minor(planes):
     """[B,3,C,P,P] -> same logical tensor stored as [B, P, P, 3*C] (channel-minor).  No copy if already so."""
     B, K, C, P, P2 = planes.shape
@@ -67,12 +70,19 @@ class _RayMarch(torch.autograd.Function):
         wsum = torch.empty([B, R, 1], dtype=torch.float32, device=pl.device)
         tfin = torch.empty([B, R], dtype=torch.float32, device=pl.device)
         opts = _opts(B, R, N, P, C, H, o)
+        ev = None
+        if TIMING is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         with torch.cuda.device(pl.device):
             rc = L.gp3d_raymarch_forward(
                 pl.data_ptr(), _lib.dtype_code(pl), pl.stride(0), pl.stride(1), pl.stride(2), pl.stride(3), pl.stride(4),
                 ro.data_ptr(), rd.data_ptr(), w1c.data_ptr(), b1c.data_ptr(), w2c.data_ptr(), b2c.data_ptr(),
                 _lib.ptr(uc), _lib.ptr(uf), _lib.ptr(sc), _lib.ptr(sf),
                 rgb.data_ptr(), depth.data_ptr(), wsum.data_ptr(), tfin.data_ptr(), ctypes.byref(opts), _lib.stream_ptr())
+        if ev is not None:
+            ev[1].record()
+            TIMING.append(ev + (B, R, N, P, C, pl.element_size()))
         _lib.check(rc, 'raymarch_forward')
         ctx.save_for_backward(pl, w1c, b1c, w2c, b2c, ro, rd,
                               *(t if t is not None else torch.empty(0, device=pl.device) for t in (uc, uf, sc, sf)))

@@ -1,0 +1,115 @@
+"""Non-saturating GAN loss with R1, patch-wise training and discriminator knowledge distillation
+(reference src/training/loss.py:33-339), for the configuration on the hot path: `training.learn_camera_dist=false`
+(the camera adaptor and its POT/EMD regulariser are outside the scope table), `pl_weight=0` (3dgp.yaml / base.yaml:77).
+Phases: Gmain, Dmain, Dreg (lazy R1) exactly as training_loop.py:321-331 drives them."""
+import numpy as np
+import torch
+
+from ..dnnlib import EasyDict
+from ..torch_utils.ops import conv2d_gradfix, upfirdn2d
+from .training_utils import extract_patches, linear_schedule, sample_patch_params
+
+
+def maybe_blur(img, blur_sigma):
+    """Gaussian blur with exp2 taps over +-3 sigma (loss.py:331-337)."""
+    blur_size = np.floor(blur_sigma * 3)
+    if blur_size > 0:
+        f = torch.arange(-blur_size, blur_size + 1, device=img.device).div(blur_sigma).square().neg().exp2()
+        img = upfirdn2d.filter2d(img, f / f.sum())
+    return img
+
+
+class StyleGAN2Loss:
+    def __init__(self, cfg, device, G, D, r1_gamma=10):
+        self.cfg, self.device, self.G, self.D, self.r1_gamma = cfg, device, G, D, r1_gamma
+        lk = cfg.model.loss_kwargs
+        self.blur_init_sigma = lk.get('blur_init_sigma', 0)
+        self.blur_fade_kimg = lk.get('blur_fade_kimg', 0)
+        self.patch_cfg = EasyDict.init_recursively(cfg.training.patch)
+        self.progressive_update(0)
+
+    def progressive_update(self, cur_kimg):
+        pc = self.patch_cfg
+        if pc.enabled:
+            if pc.distribution == 'beta':
+                pc.beta = linear_schedule(cur_kimg, pc.beta_val_start, pc.beta_val_end, pc.anneal_kimg)
+                pc.min_scale = pc.min_scale_trg
+            else:
+                pc.min_scale = linear_schedule(cur_kimg, pc.max_scale, pc.min_scale_trg, pc.anneal_kimg)
+        kd = self.cfg.model.loss_kwargs.kd.discr
+        self.D_kd_weight = linear_schedule(cur_kimg, kd.weight, 0.0, period=kd.anneal_kimg, start_step=0)
+
+    def run_G(self, z, c, camera_params, update_emas=False, patch_params=None, render_opts=None):
+        ws = self.G.mapping(z=z, c=c, update_emas=update_emas)
+        if patch_params is None:
+            patch_params = sample_patch_params(len(z), self.patch_cfg, device=z.device) if self.patch_cfg.enabled else {}
+        kw = dict(patch_params=patch_params) if self.patch_cfg.enabled else {}
+        ro = dict(concat_depth=self.cfg.training.use_depth, return_depth=True)
+        ro.update(render_opts or {})
+        out = self.G.synthesis(ws, camera_params, update_emas=update_emas, render_opts=ro, **kw)
+        out.ws = ws
+        return out, patch_params
+
+    def run_D(self, img, c, blur_sigma=0, update_emas=False, **kwargs):
+        img = maybe_blur(img, blur_sigma)
+        if self.cfg.training.use_depth:
+            bs = np.floor(blur_sigma * 3)
+            f = torch.arange(-bs, bs + 1, device=img.device).div(30.0).square().neg().exp2()   # loss.py:93-94
+            img = torch.cat([img[:, :3], upfirdn2d.filter2d(img[:, [3]], f / f.sum()), img[:, 4:]], dim=1)
+        return self.D(img, c, update_emas=update_emas, **kwargs)
+
+    def compute_sample_weights(self, patch_params, scale_pow=1):
+        s = patch_params['scales'].mean(dim=1) ** scale_pow
+        return s / (s.mean(dim=0) + 1e-8)
+
+    def accumulate_gradients(self, phase, real_data, gen_data, gain, cur_nimg, render_opts=None):
+        """real_data: {img [B,3,H,W], depth [B,1,H,W], c, embs, camera_angles}; gen_data: {z, c, camera_params}."""
+        assert phase in ['Gmain', 'Dmain', 'Dreg', 'Dall']
+        if self.r1_gamma == 0:
+            phase = {'Dreg': 'none', 'Dall': 'Dmain'}.get(phase, phase)
+        blur_sigma = max(1 - cur_nimg / (self.blur_fade_kimg * 1e3), 0) * self.blur_init_sigma if self.blur_fade_kimg > 0 else 0
+        lk = self.cfg.model
+        stats = {}
+        real_img = torch.cat([real_data.img, real_data.depth], dim=1) if self.cfg.training.use_depth else real_data.img
+
+        if phase == 'Gmain':
+            gen_out, pp = self.run_G(gen_data.z, gen_data.c, gen_data.camera_params, render_opts=render_opts)
+            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=gen_data.camera_params.angles)
+            loss = torch.nn.functional.softplus(-logits)
+            loss.mean().mul(gain).backward()
+            stats['Loss/G/loss'] = loss.detach().mean()
+
+        loss_Dgen = 0
+        if phase in ['Dmain', 'Dall']:
+            with torch.no_grad():
+                gen_out, pp = self.run_G(gen_data.z, gen_data.c, gen_data.camera_params, update_emas=True, render_opts=render_opts)
+            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, update_emas=True, patch_params=pp, camera_angles=gen_data.camera_params.angles)
+            loss_Dgen = torch.nn.functional.softplus(logits.clamp(min=-lk.discriminator.logits_clamp_val))
+            loss_Dgen = loss_Dgen + 0.0 * logits.max()
+            loss_Dgen.mean().mul(gain).backward()
+            stats['Loss/scores/fake'] = logits.detach().mean()
+
+        if phase in ['Dmain', 'Dreg', 'Dall']:
+            do_kd = self.D_kd_weight > 0 and phase in ['Dmain', 'Dall'] and self.D.b4.feat_out is not None
+            if self.patch_cfg.enabled:
+                pp = sample_patch_params(len(real_img), self.patch_cfg, device=real_img.device)
+                real_patch = extract_patches(real_img, pp, resolution=self.patch_cfg.resolution)
+            else:
+                pp, real_patch = None, real_img
+            tmp = real_patch.detach().requires_grad_(phase in ['Dreg', 'Dall'])
+            logits, feats = self.run_D(tmp, real_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=real_data.get('camera_angles'), predict_feat=do_kd)
+            loss_Dreal = loss_Dkd = loss_Dr1 = 0
+            if phase in ['Dmain', 'Dall']:
+                loss_Dreal = torch.nn.functional.softplus(-logits.clamp(max=lk.discriminator.logits_clamp_val)) + 0.0 * logits.max()
+                stats['Loss/scores/real'] = logits.detach().mean()
+            if do_kd:
+                dist = (feats - real_data.embs).norm(dim=1) * self.compute_sample_weights(pp)
+                loss_Dkd = dist * self.D_kd_weight
+            if phase in ['Dreg', 'Dall']:
+                with conv2d_gradfix.no_weight_gradients():
+                    r1_grads = torch.autograd.grad(outputs=[logits.sum()], inputs=[tmp], create_graph=True, only_inputs=True)[0]
+                r1_penalty = r1_grads.square().sum([1, 2, 3])
+                loss_Dr1 = r1_penalty * (self.r1_gamma / 2)
+                stats['Loss/D/r1_penalty'] = r1_penalty.detach().mean()
+            (loss_Dreal + loss_Dr1 + loss_Dkd).mean().mul(gain).backward()
+        return stats

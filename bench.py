@@ -192,7 +192,7 @@ def run_raymarch(args, rank, world, local):
     return res
 
 
-def cpu_raymarch(sample_rays=1024, repeats=1):
+def cpu_raymarch(sample_rays=4096, repeats=2):
     """Reference algorithm on the host cores (oracle port), bounded sample: one image, `sample_rays` rays."""
     from oracle import restated as R
     torch.set_num_threads(os.cpu_count())
@@ -213,27 +213,230 @@ def cpu_raymarch(sample_rays=1024, repeats=1):
 
 
 # ----------------------------------------------------------------------------------------------
+# workload: G+D training step (BASELINE configs[1])
+def synthetic_batch(cfg, B, device, seed):
+    """Synthetic data of the ImageNet-256 shape: uint8-like images, 16-bit-like depths, one-hot labels,
+    ResNet50-like 2048-d embeddings, latents, cameras from the uniform prior.  Returned on the HOST (pinned)."""
+    g = torch.Generator().manual_seed(seed)
+    res = cfg.dataset.resolution
+    img = torch.randint(0, 256, (B, 3, res, res), generator=g).float() / 127.5 - 1
+    depth = torch.randint(0, 65536, (B, 1, res, res), generator=g).float() / 65536 * 2 - 1
+    c = torch.zeros(B, cfg.dataset.c_dim); c[torch.arange(B), torch.arange(B) % cfg.dataset.c_dim] = 1
+    embs = torch.randn(B, cfg.dataset.embedding_dim, generator=g)
+    z = torch.randn(B, cfg.model.generator.z_dim, generator=g)
+    yaw = torch.rand(B, generator=g) * 3.14 - 1.57
+    pitch = torch.rand(B, generator=g) * (2.35619449 - 0.785398163) + 0.785398163
+    angles = torch.stack([yaw, pitch, torch.zeros(B)], 1)
+    fov = torch.rand(B, generator=g) * 35 + 10
+    look = torch.stack([torch.rand(B, generator=g) * 6.28 - 3.14, torch.acos(1 - 2 * torch.rand(B, generator=g).clamp(1e-5, 1 - 1e-5)), torch.rand(B, generator=g) * 0.2], 1)
+    host = dict(img=img, depth=depth, c=c, embs=embs, z=z, angles=angles, fov=fov, radius=torch.ones(B), look_at=look)
+    return {k: v.pin_memory() for k, v in host.items()}
+
+
+def to_step_inputs(host, device, dn):
+    d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+    real = dn.EasyDict(img=d['img'], depth=d['depth'], c=d['c'], embs=d['embs'], camera_angles=d['angles'])
+    gen = dn.EasyDict(z=d['z'], c=d['c'], camera_params=dn.TensorGroup(angles=d['angles'], fov=d['fov'], radius=d['radius'], look_at=d['look_at']))
+    return real, gen
+
+
+def conv_flops_per_image(cfg):
+    """Dense-contraction FLOPs of one image through G (decoder) and D, forward (492.0 / 209.8 GFLOP at the BASELINE config)."""
+    g = cfg.model.generator
+    res_list = [2 ** i for i in range(2, int(np.log2(g.tri_plane.res)) + 1)]
+    ch = {r: min(int(g.cbase * g.fmaps) // r, g.cmax) for r in res_list}
+    oc = 3 * g.tri_plane.feat_dim
+    fl = 0
+    for r in res_list:
+        if r > 4:
+            fl += 2 * ch[r // 2] * ch[r] * 9 * (r // 2) ** 2       # conv0, transpose-conv formulation (what runs)
+        fl += 2 * ch[r] * ch[r] * 9 * r * r                         # conv1
+        fl += 2 * ch[r] * oc * r * r                                # torgb
+    d = cfg.model.discriminator
+    pr = cfg.training.patch.resolution
+    top = pr * 2 ** d.num_additional_start_blocks
+    dres = [2 ** i for i in range(int(np.log2(top)), 2, -1)]
+    dch = {r: min(int(d.cbase * d.fmaps) // r, d.cmax) for r in dres + [4]}
+    fd = 0
+    hw = pr
+    for i, r in enumerate(dres):
+        down = 1 if i < d.num_additional_start_blocks else 2
+        if i == 0:
+            fd += 2 * 4 * dch[r] * hw * hw
+        fd += 2 * dch[r] * dch[r] * 9 * hw * hw                     # conv0
+        out_hw = hw // down
+        fd += 2 * dch[r] * dch[r // 2] * 9 * out_hw * out_hw        # conv1 (stride `down`)
+        fd += 2 * dch[r] * dch[r // 2] * out_hw * out_hw            # skip 1x1
+        hw = out_hw
+    fd += 2 * (dch[4] + 1) * dch[4] * 9 * 16 + 2 * dch[4] * 16 * dch[4] * 2 + 2 * dch[4] * dch[4]
+    return fl, fd
+
+
+def run_train_step(args, rank, world, local):
+    gp = importlib.import_module('3dgp_b200')
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    rmod = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
+    dev = torch.device('cuda', local)
+    B = args.batch_gpu or 32
+    mb = args.micro_batch or min(B, 8)
+    assert B % mb == 0 and mb % 4 == 0, 'micro-batch must divide batch-gpu and be a multiple of the minibatch-std group (4)'
+    small = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if args.small else {}
+    cfg = cfgm.make_config(batch_size=B * world, **small)
+    torch.manual_seed(1234 + rank); np.random.seed(1234 + rank)
+    G, D = cfgm.build_networks(cfg, dev)
+    with torch.no_grad():   # benchmark init: exercise the noise path (SURVEY.md 8d)
+        for n, p_ in G.named_parameters():
+            if n.endswith('noise_strength'):
+                p_.fill_(0.1)
+    G.train(); D.train()
+    G.synthesis.nerf_noise_std = 0.5
+    r1_gamma = 0.0002 * (cfg.dataset.resolution ** 2) / (B * world)      # train.py:173 'auto'
+    loss = lossm.StyleGAN2Loss(cfg, dev, G, D, r1_gamma=r1_gamma)
+    tr = stepm.Trainer(G, D, loss, cfg, rank=rank, world_size=world, D_reg_interval=16, batch_size=B * world, micro_batch=mb)
+    host = synthetic_batch(cfg, B, dev, seed=rank)
+    real, gen = to_step_inputs(host, dev, dn)
+    torch.cuda.synchronize()
+
+    def step():
+        tr.step(real, gen)
+
+    rmod.TIMING = None
+    ms, clocks = timed_region(step, args.steps, args.warmup, world)
+    # same steps, collecting the fused ray-march forward kernel's duration with events on the launching stream
+    c0 = gp._lib.launch_count
+    rmod.TIMING = []
+    ms2, _ = timed_region(step, args.steps, 0, world)
+    launches = (gp._lib.launch_count - c0) // max(args.steps + 3, 1)
+    ev = rmod.TIMING; rmod.TIMING = None
+    torch.cuda.synchronize()
+    kms = [a.elapsed_time(b) for (a, b, *_rest) in ev]
+    _, _, Bk, Rk, Nk, Pk, Ck, esz = ev[0]
+    alg = raymarch_algorithmic_bytes(Bk, Rk, Nk, Pk, Ck, plane_bytes=esz)
+    peaks = measured_peaks()
+    ach = alg / (float(np.mean(kms)) * 1e-3) / 1e9
+
+    # end-to-end through the public API: every step copies its inputs from pinned host memory and reads the losses back
+    stats_h = torch.empty(4, pin_memory=True)
+
+    def step_e2e():
+        r, g_ = to_step_inputs(host, dev, dn)
+        st = tr.step(r, g_)
+        vals = torch.stack([st.get('Loss/G/loss', torch.zeros((), device=dev)), st.get('Loss/scores/fake', torch.zeros((), device=dev)),
+                            st.get('Loss/scores/real', torch.zeros((), device=dev)), st.get('Loss/D/r1_penalty', torch.zeros((), device=dev))])
+        stats_h.copy_(vals, non_blocking=True)
+
+    ms_e2e, _ = timed_region(step_e2e, args.steps, 1, world)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    fg, fd = conv_flops_per_image(cfg)
+    # per iteration: Gmain = G fwd+bwd (3x) + D fwd + dgrad (2x); Dmain = G fwd (1x) + D fwd+bwd on fakes and reals (2 x 3x); Dreg/16 ~ D 2nd order
+    flops_step = B * (4 * fg + 8 * fd + (1.0 / 16) * 6 * fd)
+    res = dict(
+        metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
+        dtype='G fp32 (TF32 off) / D fp16+fp32, as the reference (configs/model/3dgp.yaml:8)',
+        config=dict(workload='train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64)' if not args.small else 'train_step SMALL (debug)',
+                    batch_per_gpu=B, micro_batch=mb, global_batch=B * world, phases='Gmain + Dmain every iteration, Dreg (R1) every 16th',
+                    l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
+                    parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)', conv_engine=args.conv_engine,
+                    conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9)),
+        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
+                      kernel='raymarch_fwd_kernel (inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
+                      launches_timed=len(kms), mean_ms=float(np.mean(kms))),
+        roofline_step_tensor=dict(bound='tensor', achieved=flops_step / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
+                                  frac=flops_step / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
+                                  note='dense-contraction FLOPs of the whole step / step time, against the measured sustained bf16 GEMM peak'),
+        e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=16),
+        gpu_launches=int(launches * args.steps), clocks=clocks)
+    return res
+
+
+def cpu_train_step(small=False, budget_s=25.0):
+    """Reference algorithm on the host cores (oracle port, torch-CPU / numpy, all threads) for the training-step metric.
+    Bounded sample: ONE image through the generator forward (mapping + tri-plane decoder + ray-march at the training patch
+    resolution + depth adaptor) and FOUR images (one minibatch-std group) through the discriminator forward, both at the
+    BASELINE widths.  Step cost is assembled with the same pass counts the GPU arm executes per iteration
+    (G: 1 differentiated pass = 3 forward-equivalents + 1 plain forward; D: 1 fwd + input-gradient pass (2) + 2 differentiated
+    passes (6)), i.e. images/s = 1 / (4 * tG + 8 * tD) -- an optimistic bound for the CPU since backward passes are costed at
+    forward speed x2."""
+    from oracle import ref_harness as rh, restated as R, shapes, cases
+    torch.set_num_threads(os.cpu_count())
+    kw = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if small else {}
+    Gc, Dc, m = rh.make_cfg(**kw)
+    gs, num_ws = shapes.generator_shapes(Gc)
+    ds, dres = shapes.discriminator_shapes(Dc, m['patch_res'], 4, m['embedding_dim'])
+    filt = torch.from_numpy(R.setup_filter([1, 3, 3, 1]))
+
+    def fill(shp_table, seed):
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for k, shp in shp_table.items():
+            if k.endswith('resample_filter'):
+                sd[k] = filt.clone()
+            elif k.endswith('fourier_coefs'):
+                sd[k] = (2.0 ** torch.arange(shp[0]).float() / (2 ** shp[0])) * np.pi
+            elif k.endswith('.bias') or k.endswith('progress_coef') or k.endswith('w_avg'):
+                sd[k] = torch.zeros(shp) + (1.0 if (k.endswith('affine.bias') and 'synthesis' in k) else 0.0)
+            elif k.endswith('noise_strength'):
+                sd[k] = torch.tensor(0.1)
+            elif k.endswith('near_plane_offset_raw'):
+                sd[k] = torch.tensor([-3.0])
+            else:
+                sd[k] = torch.randn(shp, generator=g)
+        return sd
+    sdG, sdD = fill(gs, 0), fill(ds, 1)
+    g = torch.Generator().manual_seed(2)
+    pr, N = m['patch_res'], Gc['num_ray_steps']
+    z = torch.randn(1, Gc['z_dim'], generator=g); c = torch.zeros(1, Gc['c_dim']); c[0, 0] = 1
+    t0 = time.perf_counter()
+    ws = R.mapping_network(sdG, 'mapping.', z, c, num_ws)
+    R.generator_synthesis(sdG, Gc, ws, torch.tensor([[0.3, 1.4, 0.0]]), torch.tensor([25.0]), torch.ones(1), torch.tensor([[0.1, 1.5, 0.1]]), pr,
+                          torch.full((1, 2), 0.5), torch.full((1, 2), 0.25), torch.rand(1, pr * pr, N, generator=g), torch.rand(1, pr * pr, N, generator=g),
+                          noise_mode='const', fused_modconv=False)
+    tG = time.perf_counter() - t0
+    img = torch.rand(4, 4, pr, pr, generator=g) * 2 - 1
+    c4 = torch.zeros(4, Dc['c_dim']); c4[:, 0] = 1
+    t0 = time.perf_counter()
+    R.discriminator(sdD, img, c4, torch.full((4, 2), 0.5), torch.full((4, 2), 0.25), dres, Dc['num_additional_start_blocks'], predict_feat=False)
+    tD = (time.perf_counter() - t0) / 4
+    val = 1.0 / (4 * tG + 8 * tD)
+    return dict(value=val, unit='images/s', cores=os.cpu_count(), kind='port',
+                sample=f'G forward 1 image {tG:.2f} s + D forward 4 patches {4 * tD:.2f} s at the BASELINE widths; step = 4 G-forward-equivalents + 8 D-forward-equivalents per image')
+
+
+# ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default=os.environ.get('GP3D_BENCH_WORKLOAD', 'raymarch'), choices=['train_step', 'raymarch', 'ginfer'])
+    ap.add_argument('--workload', default=os.environ.get('GP3D_BENCH_WORKLOAD', 'train_step'), choices=['train_step', 'raymarch', 'ginfer'])
     ap.add_argument('--batch-gpu', type=int, default=0)
     ap.add_argument('--mlp-mode', type=int, default=0)
     ap.add_argument('--planes-fp16', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--micro-batch', type=int, default=0)
+    ap.add_argument('--small', action='store_true')
+    ap.add_argument('--conv-engine', default='aten')
     args = ap.parse_args()
     rank, world, local = dist_info()
 
     if args.impl == 'reference':
         if rank != 0:
             return
-        cb = cpu_raymarch(sample_rays=2048, repeats=max(1, min(args.steps, 3)))
-        line = dict(impl='reference', metric='ray-march images/s (64x64 rays, 48+48 samples/ray, 32-ch 512^2 tri-planes)', value=cb['value'], unit='images/s',
+        if args.workload == 'train_step':
+            cb = cpu_train_step(small=args.small)
+            metric = 'G+D training-step images/s at 256x256'
+            wl = 'train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64)'
+        else:
+            cb = cpu_raymarch(sample_rays=4096, repeats=2)
+            metric = 'ray-march images/s (64x64 rays, 48+48 samples/ray, 32-ch 512^2 tri-planes)'
+            wl = 'raymarch (BASELINE configs[2])'
+        line = dict(impl='reference', metric=metric, value=cb['value'], unit='images/s',
                     n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 / cb['value'], higher_is_better=True, scaling='weak',
-                    vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload='raymarch (BASELINE configs[2])'),
+                    vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload=wl),
                     cpu_baseline=cb, e2e=dict(value=cb['value'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -244,13 +447,15 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl')
-    res = run_raymarch(args, rank, world, local)
+    res = run_train_step(args, rank, world, local) if args.workload == 'train_step' else run_raymarch(args, rank, world, local)
     if rank == 0:
         line = dict(metric=res['metric'], value=res['value'], unit=res['unit'], n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
                     config=res['config'], roofline=res['roofline'], e2e=res['e2e'], gpu_launches=res['gpu_launches'], clocks=res['clocks'])
+        if 'roofline_step_tensor' in res:
+            line['roofline_step_tensor'] = res['roofline_step_tensor']
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_raymarch()
+            line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -393,11 +393,13 @@ def bilinear_planes(planes, coords):
     B, _, C, P, _ = planes.shape
     out = []
     pairs = [(0, 1), (0, 2), (1, 2)]     # (width-coordinate, height-coordinate) of planes xy, xz, yz
+    M = coords.shape[1]
     for k, (iu, iv) in enumerate(pairs):
         ix = (coords[..., iu] + 1) / 2 * (P - 1)
         iy = (coords[..., iv] + 1) / 2 * (P - 1)
         x0 = torch.floor(ix); y0 = torch.floor(iy)
-        acc = torch.zeros(B, coords.shape[1], C)
+        acc = torch.zeros(B, M, C)
+        texels = planes[:, k].permute(0, 2, 3, 1).reshape(B, P * P, C)        # row = texel, col = channel
         for dy in (0, 1):
             for dx in (0, 1):
                 xx = x0 + dx; yy = y0 + dy
@@ -405,9 +407,8 @@ def bilinear_planes(planes, coords):
                 wy = (y0 + 1 - iy) if dy == 0 else (iy - y0)
                 valid = (xx >= 0) & (xx <= P - 1) & (yy >= 0) & (yy <= P - 1)
                 xi = xx.clamp(0, P - 1).long(); yi = yy.clamp(0, P - 1).long()
-                flat = planes[:, k].reshape(B, C, P * P)
-                idx = (yi * P + xi).unsqueeze(1).expand(B, C, -1)
-                v = torch.gather(flat, 2, idx).permute(0, 2, 1)           # [B, M, C]
+                idx = yi * P + xi                                              # [B, M]
+                v = torch.stack([texels[b].index_select(0, idx[b]) for b in range(B)])   # [B, M, C]
                 acc = acc + v * (wx * wy * valid.float()).unsqueeze(-1)
         out.append(acc)
     return torch.stack(out, dim=1)

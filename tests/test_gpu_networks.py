@@ -1,0 +1,121 @@
+"""GPU parity suite for the module surface (Generator / Discriminator / loss step) against goldens produced by the
+unmodified reference on the reduced-width 3DGP config (oracle/cases.py:small_net_kwargs): identical weights (seeded
+state dicts), latents, cameras, patch params and INJECTED layer / renderer noise."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import cases
+from util import maxrel, l2rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _build():
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0)
+    G, D = cfgm.build_networks(cfg, 'cuda', fp32_D=True)
+    sdG = cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, G.state_dict(), seed=100)
+    sdD = cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, D.state_dict(), seed=200)
+    G.load_state_dict(sdG); D.load_state_dict(sdD)
+    inp = cases.net_inputs(meta['net_kwargs'])
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    pp = dict(scales=t['patch_scales'], offsets=t['patch_offsets'])
+    return cfg, G, D, t, cam, pp, meta['net_kwargs']
+
+
+def _train_forward(G, t, cam, pp, kw):
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n).cuda() for n in cases.layer_noises(kw, B)]
+    G.train()
+    G.synthesis.nerf_noise_std = 0.0
+    ws = G.mapping(t['z'], t['c'])
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)))
+    out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
+    return ws, out, noises
+
+
+def test_generator_train_and_eval_vs_golden(golden):
+    cfg, G, D, t, cam, pp, kw = _build()
+    g = golden('networks')
+    ws, out, noises = _train_forward(G, t, cam, pp, kw)
+    assert maxrel(ws.detach().cpu().numpy(), g['G/ws']) < 1e-5
+    planes = G.synthesis.tri_plane_decoder(ws, noise_mode='random', layer_noises=noises, fused_modconv=False)
+    assert maxrel(planes.detach().contiguous().flatten()[::31].cpu().numpy(), g['G/train/planes_probe']) < TOL
+    assert maxrel(out.img.detach().cpu().numpy(), g['G/train/img']) < TOL
+    assert maxrel(out.depth.detach().cpu().numpy(), g['G/train/depth']) < TOL
+    # eval: fused modconv (grouped conv), const noise, full-frame render at img_resolution
+    G.eval()
+    B = t['z'].shape[0]
+    ue = cases.eval_variates(kw, B)
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=torch.from_numpy(ue['u_coarse']).cuda(), u_fine=torch.from_numpy(ue['u_fine']).cuda())
+    with torch.no_grad():
+        oe = G.synthesis(ws, cam, render_opts=ro, noise_mode='const')
+    assert maxrel(oe.img.cpu().numpy(), g['G/eval/img']) < TOL
+    assert maxrel(oe.depth.cpu().numpy(), g['G/eval/depth']) < TOL
+
+
+def test_discriminator_and_r1_double_backward_vs_golden(golden):
+    cfg, G, D, t, cam, pp, kw = _build()
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    g = golden('networks')
+    D.train()
+    img = torch.from_numpy(g['G/train/img']).cuda().requires_grad_(True)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    assert maxrel(logits.detach().cpu().numpy(), g['D/logits']) < TOL
+    assert maxrel(feats.detach().cpu().numpy(), g['D/feats']) < TOL
+    with cg.no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    assert l2rel(r1.detach().cpu().numpy(), g['D/r1_grads']) < TOL
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    names = cases.probe_params('D')
+    pars = dict(D.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    for n, gr in zip(names, gs):
+        assert l2rel(gr.cpu().numpy(), g['D/grad/' + n]) < 2e-3, n
+
+
+def test_generator_loss_gradients_vs_golden(golden):
+    cfg, G, D, t, cam, pp, kw = _build()
+    g = golden('networks')
+    D.train()
+    ws, out, _ = _train_forward(G, t, cam, pp, kw)
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    assert abs(loss.item() - float(g['G/loss'][0])) < 1e-3 * max(1.0, abs(float(g['G/loss'][0])))
+    names = cases.probe_params('G')
+    pars = dict(G.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    for n, gr in zip(names, gs):
+        assert l2rel(gr.cpu().numpy(), g['G/grad/' + n]) < 3e-3, n
+
+
+def test_training_step_runs_and_updates():
+    """One full Gmain + Dmain + Dreg iteration on the small config: finite stats, parameters move, G_ema tracks G."""
+    cfg, G, D, t, cam, pp, kw = _build()
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    B = t['z'].shape[0]
+    loss = lossm.StyleGAN2Loss(cfg, 'cuda', G, D, r1_gamma=1.0)
+    tr = stepm.Trainer(G, D, loss, cfg, D_reg_interval=16)
+    torch.manual_seed(0); np.random.seed(0)
+    real = dn.EasyDict(img=torch.rand(B, 3, 64, 64, device='cuda') * 2 - 1, depth=torch.rand(B, 1, 64, 64, device='cuda') * 2 - 1, c=t['c'],
+                       embs=torch.randn(B, kw['embedding_dim'], device='cuda'), camera_angles=t['angles'])
+    gen = dn.EasyDict(z=t['z'], c=t['c'], camera_params=cam)
+    w0 = G.synthesis.tri_plane_decoder.b8.conv0.weight.detach().clone(); d0 = D.b16.conv0.weight.detach().clone()
+    stats = tr.step(real, gen)
+    assert all(torch.isfinite(v).all() for v in stats.values()) and 'Loss/D/r1_penalty' in stats
+    assert not torch.equal(w0, G.synthesis.tri_plane_decoder.b8.conv0.weight) and not torch.equal(d0, D.b16.conv0.weight)
+    stats = tr.step(real, gen)
+    assert 'Loss/D/r1_penalty' not in stats     # lazy regularisation: Dreg only every 16th iteration
