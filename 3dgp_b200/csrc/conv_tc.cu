@@ -13,7 +13,7 @@
 
 namespace tc {
 
-constexpr int CBM = 128, CBK = 64, CSTAGES = 4;
+constexpr int CBM = 128, CBK = 64;
 constexpr int kConvThreads = 256;
 
 struct ConvGeom {
@@ -22,11 +22,16 @@ struct ConvGeom {
     int tiles_x, tiles_y, tiles_n, tiles_co;
 };
 
-template <int BN>
+// TERMS == 1: y += xh * wh.   TERMS == 3 (error-compensated "bf16x3", ~2^-16 relative): y += xh*wh + xh*wl + xl*wh with
+// x = xh + xl, w = wh + wl split into bf16 pairs; all three products accumulate into the same TMEM tile.
+template <int BN, int TERMS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                      const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmWl,
                       float* __restrict__ Y, ConvGeom g, int accumulate) {
-    constexpr uint32_t kStage = (CBM + BN) * CBK * 2;
+    constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
+    constexpr uint32_t kOperand = (CBM + BN) * CBK * 2;
+    constexpr uint32_t kStage = kOperand * (TERMS == 3 ? 2 : 1);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // keep every stage 1024-byte aligned: A tile is 16 KB, B tile BN*128 B (multiple of 1024 for BN % 8 == 0)
@@ -72,6 +77,10 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_expect_tx(&full_bar[st], kStage);
                 tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, x0 + kx - pad, y0 + ky - pad, n0);
                 tma_load_2d(sb, &tmW, &full_bar[st], tap * g.Cin + cb * CBK, co0);
+                if (TERMS == 3) {
+                    tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, x0 + kx - pad, y0 + ky - pad, n0);
+                    tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], tap * g.Cin + cb * CBK, co0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -84,8 +93,14 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const uint32_t sa = smem_u32(tiles + (size_t)st * kStage);
                 const uint32_t sb = sa + CBM * CBK * 2;
 #pragma unroll
-                for (int k = 0; k < CBK / 16; k++)
-                    umma_bf16(tmem_base, make_desc_k_sw128(sa + k * 32), make_desc_k_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < CBK / 16; k++) {
+                    const uint64_t dah = make_desc_k_sw128(sa + k * 32), dbh = make_desc_k_sw128(sb + k * 32);
+                    umma_bf16(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    if (TERMS == 3) {
+                        umma_bf16(tmem_base, dah, make_desc_k_sw128(sb + kOperand + k * 32), idesc, 1u);
+                        umma_bf16(tmem_base, make_desc_k_sw128(sa + kOperand + k * 32), dbh, idesc, 1u);
+                    }
+                }
                 umma_commit(&empty_bar[st]);
             }
             umma_commit(accum_bar);
@@ -116,23 +131,26 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     if (warp == 2) tmem_dealloc(tmem_base, 128);
 }
 
-template <int BN>
-int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, float* y, const ConvGeom& g, int accumulate, cudaStream_t s) {
-    constexpr uint32_t kStage = (CBM + BN) * CBK * 2;
+template <int BN, int TERMS>
+int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXl, const CUtensorMap& tmWl, float* y, const ConvGeom& g,
+                int accumulate, cudaStream_t s) {
+    constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
+    constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1);
     const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256;
-    auto kern = conv_nhwc_bf16_kernel<BN>;
+    auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { gp3d_set_error("conv2d_nhwc_bf16: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
     const int64_t grid = (int64_t)g.tiles_n * g.tiles_y * g.tiles_x * g.tiles_co;
-    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, y, g, accumulate);
+    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, tmXl, tmWl, y, g, accumulate);
     return 0;
 }
 
 }  // namespace tc
 
-extern "C" int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
-                                     int ksize, int accumulate, void* stream) {
+static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
+                     int ksize, int accumulate, void* stream) {
     GP3D_CHECK_ARG(x && w && y, "conv2d_nhwc_bf16: null pointer");
+    GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "conv2d_nhwc_bf16x3: both low-order operands are required");
     GP3D_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_nhwc_bf16: kernel size must be 1 or 3 (got %d)", ksize);
     GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0, "conv2d_nhwc_bf16: empty tensor");
     if (Cin % 64 != 0 || !(Cout % 128 == 0 || Cout == 96 || Cout == 64)) {
@@ -152,30 +170,53 @@ extern "C" int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int
     g.tiles_x = W / g.TW; g.tiles_y = H / g.TH; g.tiles_n = N / g.TN; g.tiles_co = Cout / BN;
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
     if (!enc) { gp3d_set_error("cuTensorMapEncodeTiled is not available from this driver"); return GP3D_E_UNSUPPORTED; }
-    CUtensorMap tmX, tmW;
-    {
+    CUtensorMap tmX, tmW, tmXl, tmWl;
+    for (int part = 0; part < (xl ? 2 : 1); part++) {
+        const void* xp = part ? xl : x;
+        CUtensorMap* tm = part ? &tmXl : &tmX;
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { gp3d_set_error("conv2d_nhwc_bf16: activation tensor map encode failed (CUresult %d)", (int)r); return GP3D_E_BADARG; }
     }
-    {
+    for (int part = 0; part < (wl ? 2 : 1); part++) {
+        const void* wp = part ? wl : w;
+        CUtensorMap* tm = part ? &tmWl : &tmW;
         const cuuint64_t Kt = (cuuint64_t)ksize * ksize * Cin;
         cuuint64_t dims[2] = {Kt, (cuuint64_t)Cout};
         cuuint64_t strides[1] = {Kt * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { gp3d_set_error("conv2d_nhwc_bf16: weight tensor map encode failed (CUresult %d)", (int)r); return GP3D_E_BADARG; }
     }
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = (BN == 128) ? tc::launch_conv<128>(tmX, tmW, y, g, accumulate, s)
-           : (BN == 96)  ? tc::launch_conv<96>(tmX, tmW, y, g, accumulate, s)
-                         : tc::launch_conv<64>(tmX, tmW, y, g, accumulate, s);
+    int rc;
+    if (!xl) {
+        tmXl = tmX; tmWl = tmW;
+        rc = (BN == 128) ? tc::launch_conv<128, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
+           : (BN == 96)  ? tc::launch_conv<96, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
+                         : tc::launch_conv<64, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s);
+    } else {
+        rc = (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
+           : (BN == 96)  ? tc::launch_conv<96, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
+                         : tc::launch_conv<64, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s);
+    }
     if (rc) return rc;
     GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
+                                     int ksize, int accumulate, void* stream) {
+    return conv_impl(x, nullptr, w, nullptr, y, N, H, W, Cin, Cout, ksize, accumulate, stream);
+}
+
+extern "C" int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                                       int Cin, int Cout, int ksize, int accumulate, void* stream) {
+    GP3D_CHECK_ARG(xl && wl, "conv2d_nhwc_bf16x3: null low-order operand");
+    return conv_impl(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, accumulate, stream);
 }

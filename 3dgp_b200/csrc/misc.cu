@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) grad_epilogue_kernel(float* g, int64_t nu
         for (int k = 0; k < 4; k++) {
             float a = f[k] * inv_world;
             a = (a != a) ? 0.f : a;
-            a = fminf(fmaxf(a, neginf), posinf);       // maps +-inf to posinf / neginf (torch.nan_to_num semantics) and clamps
+            a = isinf(a) ? (a > 0.f ? posinf : neginf) : a;   // torch.nan_to_num: only nan / +-inf are replaced
             f[k] = a;
         }
         reinterpret_cast<float4*>(g)[v] = make_float4(f[0], f[1], f[2], f[3]);
@@ -165,7 +165,38 @@ __global__ void __launch_bounds__(256) grad_epilogue_kernel(float* g, int64_t nu
         if (i < numel) {
             float a = g[i] * inv_world;
             a = (a != a) ? 0.f : a;
-            g[i] = fminf(fmaxf(a, neginf), posinf);
+            g[i] = isinf(a) ? (a > 0.f ? posinf : neginf) : a;
+        }
+    }
+}
+
+// hi = bf16(x * s), lo = bf16(x * s - hi); channel-minor tensors, 8 channels per thread
+template <class T>
+__global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, int N, int HW, int C) {
+    const int64_t nvec = (int64_t)N * HW * C / 8;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = v * 8;
+        float f[8];
+        if (sizeof(T) == 4) {
+            const float4 a = reinterpret_cast<const float4*>(x)[2 * v], b = reinterpret_cast<const float4*>(x)[2 * v + 1];
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+            vec16<__half> t; t.load(reinterpret_cast<const __half*>(x) + i0); t.unpack(f);
+        }
+        if (s) {
+            const int c0 = (int)(i0 % C);
+            const int n = (int)(i0 / ((int64_t)HW * C));
+            const float4 sa = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0), sb = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0 + 4);
+            f[0] *= sa.x; f[1] *= sa.y; f[2] *= sa.z; f[3] *= sa.w; f[4] *= sb.x; f[5] *= sb.y; f[6] *= sb.z; f[7] *= sb.w;
+        }
+        float r[8];
+        vec16<__nv_bfloat16> h; h.pack(f); h.store(hi + i0);
+        if (lo) {
+            float hf[8]; h.unpack(hf);
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] = f[k] - hf[k];
+            vec16<__nv_bfloat16> l; l.pack(r); l.store(lo + i0);
         }
     }
 }
@@ -242,5 +273,18 @@ extern "C" int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, floa
     GP3D_CHECK_ARG(gp3d_aligned16(g), "grad_epilogue: buffer must be 16-byte aligned");
     if (numel == 0) return GP3D_OK;
     grad_epilogue_kernel<<<gp3d_grid_for(numel / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, numel, inv_world, posinf, neginf);
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream) {
+    GP3D_CHECK_ARG(x && hi && N >= 1 && HW >= 1 && C >= 1, "split_bf16: bad arguments");
+    GP3D_CHECK_ARG(C % 8 == 0, "split_bf16: channel count must be a multiple of 8 (got %d)", C);
+    GP3D_CHECK_ARG(gp3d_aligned16(x) && gp3d_aligned16(hi) && (!lo || gp3d_aligned16(lo)) && (!s || gp3d_aligned16(s)), "split_bf16: pointers must be 16-byte aligned");
+    const int64_t nvec = (int64_t)N * HW * C / 8;
+    const int grid = gp3d_grid_for(nvec, 256, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C);
+    else if (src_dtype == GP3D_F16) split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C);
+    else { gp3d_set_error("split_bf16: source must be float32 or float16"); return GP3D_E_BADARG; }
     GP3D_RETURN_LAUNCH();
 }

@@ -9,8 +9,41 @@ import contextlib
 
 import torch
 
+from . import tc
+
 enabled = False                     # kept for training_loop.py:78 (`conv2d_gradfix.enabled = True`)
 weight_gradients_disabled = False   # toggled by no_weight_gradients()
+tc_enabled = True                   # route eligible convs (and their input-gradient convs) to the tcgen05 kernels
+tc_stats = dict(tc=0, aten=0)       # how many primitive convolutions went where (bench.py / tests)
+
+
+def _terms_for(dtype):
+    # float32 tensors (G is fp32-only in the reference, TF32 off): error-compensated bf16x3, fp32-grade accuracy.
+    # float16 tensors (D blocks >= 32^2 in the reference): plain bf16 operands with fp32 accumulation.
+    return 3 if dtype == torch.float32 else 1
+
+
+def _primitive_conv(input, weight, bias, stride, padding, dilation, groups):
+    k = weight.shape[2]
+    if (tc_enabled and bias is None and weight.shape[2] == weight.shape[3] and input.dtype in (torch.float32, torch.float16)
+            and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[0], k, stride, padding, dilation, groups)):
+        tc_stats['tc'] += 1
+        return tc.conv2d_forward(input, weight, _terms_for(input.dtype))
+    tc_stats['aten'] += 1
+    return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding, dilation=dilation, groups=groups)
+
+
+def _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups):
+    # stride-1 transposed conv == correlation with the flipped, transposed kernel and padding k-1-p
+    k = weight.shape[2]
+    if (tc_enabled and bias is None and tuple(stride) == (1, 1) and tuple(output_padding) == (0, 0) and weight.shape[2] == weight.shape[3]
+            and tuple(padding) == (k - 1 - k // 2, k - 1 - k // 2) and input.dtype in (torch.float32, torch.float16)
+            and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[1], k, (1, 1), (k // 2, k // 2), dilation, groups)):
+        tc_stats['tc'] += 1
+        return tc.conv2d_forward(input, weight.flip([2, 3]).transpose(0, 1), _terms_for(input.dtype))
+    tc_stats['aten'] += 1
+    return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
+                                                output_padding=output_padding, groups=groups, dilation=dilation)
 
 
 @contextlib.contextmanager
@@ -62,9 +95,9 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
         def forward(ctx, input, weight, bias):
             assert tuple(weight.shape) == weight_shape
             if not transpose:
-                out = torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, **kw)
+                out = _primitive_conv(input, weight, bias, stride, padding, dilation, groups)
             else:
-                out = torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, output_padding=output_padding, **kw)
+                out = _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups)
             ctx.save_for_backward(input, weight, bias)
             return out
 

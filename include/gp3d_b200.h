@@ -174,6 +174,18 @@ int gp3d_gemm_bf16_tn(const void* A, const void* B, float* D, int M, int N, int 
 int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
                           int ksize, int accumulate, void* stream);
 
+/* Error-compensated variant for fp32 parity ("bf16x3"): x = xh + xl, w = wh + wl are bf16 pairs produced by
+ * gp3d_split_bf16; y (+)= xh*wh + xh*wl + xl*wh, all three products accumulated in the same fp32 TMEM tile
+ * (relative error ~2^-16 instead of 2^-9).  Same shapes / constraints as gp3d_conv2d_nhwc_bf16.
+ */
+int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                            int Cin, int Cout, int ksize, int accumulate, void* stream);
+
+/* fp32 / fp16 -> bf16 hi (+ lo) split with optional per-(n, c) modulation (x * styles, networks_stylegan2.py:68), channel-minor
+ * (NHWC) tensors: hi = bf16(x * s[n][c]); lo = bf16(x * s[n][c] - hi) (lo may be NULL).  s may be NULL.  src_dtype: GP3D_F32 / F16.
+ */
+int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

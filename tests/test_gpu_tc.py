@@ -53,3 +53,57 @@ def test_conv2d_unsupported_shapes_fail_loudly():
     w = torch.zeros(128, 3, 3, 4, device='cuda', dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         tc.conv2d_nhwc_bf16(x, w)
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,ks', [(2, 128, 128, 32, 3), (4, 64, 256, 16, 3), (2, 128, 96, 32, 1), (8, 1024 // 4, 1024 // 4, 4, 3)])
+def test_conv2d_gradfix_tc_path_matches_aten_fp32(N, Cin, Cout, H, ks):
+    """conv2d_gradfix routes eligible fp32 convs (forward and input-gradient) to the bf16x3 tcgen05 kernel: fp32-grade results."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, H, device='cuda', generator=g).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, ks, ks, device='cuda', generator=g) / (ks * Cin ** 0.5)).requires_grad_(True)
+    dy = torch.randn(N, Cout, H, H, device='cuda', generator=g)
+    cg.tc_enabled = True
+    before = dict(cg.tc_stats)
+    y = cg.conv2d(x, w, padding=ks // 2)
+    gx, gw = torch.autograd.grad(y, [x, w], dy)
+    used_tc = cg.tc_stats['tc'] - before['tc']
+    cg.tc_enabled = False
+    y0 = cg.conv2d(x, w, padding=ks // 2)
+    gx0, gw0 = torch.autograd.grad(y0, [x, w], dy)
+    cg.tc_enabled = True
+    assert used_tc >= 1
+    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
+    assert rel(y, y0) < 1e-4 and rel(gx, gx0) < 1e-4 and rel(gw, gw0) < 1e-4, (rel(y, y0), rel(gx, gx0), rel(gw, gw0))
+
+
+def test_conv2d_gradfix_tc_double_backward_r1_style():
+    """R1-style second order through the tensor-core path: d/dw of |d logits / d x|^2 with weight gradients disabled in the inner pass."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(5)
+    w = (torch.randn(128, 64, 3, 3, device='cuda', generator=g) / 24).requires_grad_(True)
+    x = torch.randn(2, 64, 16, 16, device='cuda', generator=g).requires_grad_(True)
+
+    def r1(enabled):
+        cg.tc_enabled = enabled
+        y = cg.conv2d(x, w, padding=1)
+        with cg.no_weight_gradients():
+            gx = torch.autograd.grad(y.tanh().sum(), x, create_graph=True)[0]
+        (gw,) = torch.autograd.grad(gx.square().sum(), w)
+        return gw
+    a, b = r1(True), r1(False)
+    cg.tc_enabled = True
+    assert (a - b).abs().max().item() / b.abs().max().item() < 2e-4
+
+
+def test_conv2d_gradfix_fp16_uses_single_term_bf16():
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    g = torch.Generator(device='cuda').manual_seed(9)
+    x = torch.randn(2, 128, 32, 32, device='cuda', generator=g).half()
+    w = (torch.randn(128, 128, 3, 3, device='cuda', generator=g) / 34).half()
+    y = cg.conv2d(x, w, padding=1)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
+    assert y.dtype == torch.float16
+    assert (y.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
