@@ -17,8 +17,14 @@ constexpr int CBM = 128, CBK = 64;
 constexpr int kConvThreads = 256;
 
 struct ConvGeom {
-    int N, H, W, Cin, Cout, ks;
-    int TW, TH, TN;            // pixel tile: TN images x TH rows x TW cols = 128
+    int N, H, W, Cin, Cout;      // input tensor [N][H][W][Cin]; weights [Cout][num_slabs][Cin]
+    int ntaps;                   // filter taps of THIS launch
+    int tdy[9], tdx[9], tslab[9];  // input offset (in input pixels) and weight slab of each tap
+    int in_stride;               // 1, or 2 for strided gathers (the tensor map carries matching elementStrides)
+    int HoP, WoP;                // logical output grid of this launch (tile domain); pixel (iy, ix) reads input (iy*in_stride+tdy, ix*in_stride+tdx)
+    int Hout, Wout;              // output tensor [N][Hout][Wout][Cout]; pixel (iy, ix) is stored at (iy*osy + oy0, ix*osx + ox0)
+    int osy, osx, oy0, ox0;
+    int TW, TH, TN;              // pixel tile: TN images x TH rows x TW cols = 128
     int tiles_x, tiles_y, tiles_n, tiles_co;
 };
 
@@ -49,9 +55,8 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int ty = t % g.tiles_y; t /= g.tiles_y;
     const int tn = t;
     const int x0 = tx * g.TW, y0 = ty * g.TH, n0 = tn * g.TN, co0 = tco * BN;
-    const int pad = g.ks / 2;
     const int cblocks = g.Cin / CBK;
-    const int num_kb = g.ks * g.ks * cblocks;
+    const int num_kb = g.ntaps * cblocks;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW); }
     if (warp == 1 && lane == 0) {
@@ -70,16 +75,16 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int kb = 0; kb < num_kb; kb++) {
                 const int st = kb % CSTAGES; const uint32_t ph = (kb / CSTAGES) & 1;
                 const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int ky = tap / g.ks, kx = tap - ky * g.ks;
+                const int cx = x0 * g.in_stride + g.tdx[tap], cy = y0 * g.in_stride + g.tdy[tap], slab = g.tslab[tap];
                 mbar_wait(&empty_bar[st], ph ^ 1);
                 unsigned char* sa = tiles + (size_t)st * kStage;
                 unsigned char* sb = sa + CBM * CBK * 2;
                 mbar_expect_tx(&full_bar[st], kStage);
-                tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, x0 + kx - pad, y0 + ky - pad, n0);
-                tma_load_2d(sb, &tmW, &full_bar[st], tap * g.Cin + cb * CBK, co0);
+                tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, cx, cy, n0);
+                tma_load_2d(sb, &tmW, &full_bar[st], slab * g.Cin + cb * CBK, co0);
                 if (TERMS == 3) {
-                    tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, x0 + kx - pad, y0 + ky - pad, n0);
-                    tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], tap * g.Cin + cb * CBK, co0);
+                    tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, cx, cy, n0);
+                    tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], slab * g.Cin + cb * CBK, co0);
                 }
             }
         }
@@ -111,12 +116,15 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_fence_after();
         const int r = q * 32 + lane;                       // pixel index inside the tile: ((n*TH + h)*TW + w)
         const int wl = r % g.TW, hl = (r / g.TW) % g.TH, nl = r / (g.TW * g.TH);
-        float* yrow = Y + (((size_t)(n0 + nl) * g.H + (y0 + hl)) * g.W + (x0 + wl)) * g.Cout + co0;
+        const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
+        const bool inside = (ix < g.WoP) && (iy < g.HoP) && (nn < g.N);
+        float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + g.oy0)) * g.Wout + (size_t)(ix * g.osx + g.ox0)) * g.Cout + co0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective: every lane participates
             tmem_ld_wait();
+            if (!inside) continue;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -147,27 +155,32 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
 
 }  // namespace tc
 
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// General tap convolution.  taps: ntaps x (dy, dx, slab).  num_slabs = weight slabs per output channel.
 static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
-                     int ksize, int accumulate, void* stream) {
-    GP3D_CHECK_ARG(x && w && y, "conv2d_nhwc_bf16: null pointer");
-    GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "conv2d_nhwc_bf16x3: both low-order operands are required");
-    GP3D_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_nhwc_bf16: kernel size must be 1 or 3 (got %d)", ksize);
-    GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0, "conv2d_nhwc_bf16: empty tensor");
+                     int num_slabs, int ntaps, const int* taps, int in_stride, int HoP, int WoP, int Hout, int Wout,
+                     int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who) {
+    GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
+    GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "%s: both low-order operands are required", who);
+    GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && HoP > 0 && WoP > 0, "%s: empty tensor", who);
+    GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 9 && (in_stride == 1 || in_stride == 2), "%s: bad tap list / stride", who);
     if (Cin % 64 != 0 || !(Cout % 128 == 0 || Cout == 96 || Cout == 64)) {
-        gp3d_set_error("conv2d_nhwc_bf16: need Cin %% 64 == 0 and Cout %% 128 == 0 (or Cout in {64, 96}); got Cin=%d Cout=%d", Cin, Cout);
+        gp3d_set_error("%s: need Cin %% 64 == 0 and Cout %% 128 == 0 (or Cout in {64, 96}); got Cin=%d Cout=%d", who, Cin, Cout);
         return GP3D_E_UNSUPPORTED;
     }
+    GP3D_CHECK_ARG((HoP - 1) * osy + oy0 < Hout && (WoP - 1) * osx + ox0 < Wout, "%s: output lattice exceeds the output tensor", who);
     tc::ConvGeom g{};
-    g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.ks = ksize;
-    g.TW = W < 16 ? W : 16;
-    g.TH = (128 / g.TW) < H ? (128 / g.TW) : H;
+    g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.ntaps = ntaps; g.in_stride = in_stride;
+    for (int t = 0; t < ntaps; t++) { g.tdy[t] = taps[3 * t]; g.tdx[t] = taps[3 * t + 1]; g.tslab[t] = taps[3 * t + 2];
+        GP3D_CHECK_ARG(g.tslab[t] >= 0 && g.tslab[t] < num_slabs, "%s: weight slab out of range", who); }
+    g.HoP = HoP; g.WoP = WoP; g.Hout = Hout; g.Wout = Wout; g.osy = osy; g.osx = osx; g.oy0 = oy0; g.ox0 = ox0;
+    g.TW = pow2ceil(WoP) < 16 ? pow2ceil(WoP) : 16;
+    g.TH = pow2ceil(HoP) < (128 / g.TW) ? pow2ceil(HoP) : (128 / g.TW);
     g.TN = 128 / (g.TW * g.TH);
-    if (g.TW * g.TH * g.TN != 128 || W % g.TW || H % g.TH || N % g.TN) {
-        gp3d_set_error("conv2d_nhwc_bf16: cannot tile N=%d H=%d W=%d into 128-pixel blocks (W, H powers of two; N %% %d == 0)", N, H, W, g.TN);
-        return GP3D_E_UNSUPPORTED;
-    }
     const int BN = (Cout % 128 == 0) ? 128 : Cout;
-    g.tiles_x = W / g.TW; g.tiles_y = H / g.TH; g.tiles_n = N / g.TN; g.tiles_co = Cout / BN;
+    g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN; g.tiles_co = Cout / BN;
+    GP3D_CHECK_ARG((int64_t)g.tiles_x * g.tiles_y * g.tiles_n * g.tiles_co < 2147483647LL, "%s: grid too large", who);
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
     if (!enc) { gp3d_set_error("cuTensorMapEncodeTiled is not available from this driver"); return GP3D_E_UNSUPPORTED; }
     CUtensorMap tmX, tmW, tmXl, tmWl;
@@ -176,23 +189,23 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         CUtensorMap* tm = part ? &tmXl : &tmX;
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)(g.TW * in_stride), (cuuint32_t)(g.TH * in_stride), (cuuint32_t)g.TN};
+        cuuint32_t estr[4] = {1, (cuuint32_t)in_stride, (cuuint32_t)in_stride, 1};
         CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { gp3d_set_error("conv2d_nhwc_bf16: activation tensor map encode failed (CUresult %d)", (int)r); return GP3D_E_BADARG; }
+        if (r != CUDA_SUCCESS) { gp3d_set_error("%s: activation tensor map encode failed (CUresult %d)", who, (int)r); return GP3D_E_BADARG; }
     }
     for (int part = 0; part < (wl ? 2 : 1); part++) {
         const void* wp = part ? wl : w;
         CUtensorMap* tm = part ? &tmWl : &tmW;
-        const cuuint64_t Kt = (cuuint64_t)ksize * ksize * Cin;
+        const cuuint64_t Kt = (cuuint64_t)num_slabs * Cin;
         cuuint64_t dims[2] = {Kt, (cuuint64_t)Cout};
         cuuint64_t strides[1] = {Kt * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { gp3d_set_error("conv2d_nhwc_bf16: weight tensor map encode failed (CUresult %d)", (int)r); return GP3D_E_BADARG; }
+        if (r != CUDA_SUCCESS) { gp3d_set_error("%s: weight tensor map encode failed (CUresult %d)", who, (int)r); return GP3D_E_BADARG; }
     }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
@@ -210,13 +223,29 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     GP3D_RETURN_LAUNCH();
 }
 
+static int conv_same(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
+                     int ksize, int accumulate, void* stream, const char* who) {
+    GP3D_CHECK_ARG(ksize == 1 || ksize == 3, "%s: kernel size must be 1 or 3 (got %d)", who, ksize);
+    int taps[27]; int nt = 0;
+    for (int ky = 0; ky < ksize; ky++) for (int kx = 0; kx < ksize; kx++) { taps[3 * nt] = ky - ksize / 2; taps[3 * nt + 1] = kx - ksize / 2; taps[3 * nt + 2] = ky * ksize + kx; nt++; }
+    return conv_impl(x, xl, w, wl, y, N, H, W, Cin, Cout, ksize * ksize, nt, taps, 1, H, W, H, W, 1, 1, 0, 0, accumulate, stream, who);
+}
+
 extern "C" int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
                                      int ksize, int accumulate, void* stream) {
-    return conv_impl(x, nullptr, w, nullptr, y, N, H, W, Cin, Cout, ksize, accumulate, stream);
+    return conv_same(x, nullptr, w, nullptr, y, N, H, W, Cin, Cout, ksize, accumulate, stream, "conv2d_nhwc_bf16");
 }
 
 extern "C" int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                                        int Cin, int Cout, int ksize, int accumulate, void* stream) {
     GP3D_CHECK_ARG(xl && wl, "conv2d_nhwc_bf16x3: null low-order operand");
-    return conv_impl(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, accumulate, stream);
+    return conv_same(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, accumulate, stream, "conv2d_nhwc_bf16x3");
+}
+
+extern "C" int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, float* y,
+                                   int N, int H, int W, int Cin, int Cout, int num_slabs, int ntaps, const int* h_taps, int in_stride,
+                                   int HoP, int WoP, int Hout, int Wout, int osy, int osx, int oy0, int ox0, int accumulate, void* stream) {
+    GP3D_CHECK_ARG(h_taps != nullptr, "conv_taps_nhwc: null tap list");
+    return conv_impl(xh, xl, wh, wl, y, N, H, W, Cin, Cout, num_slabs, ntaps, h_taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0,
+                     accumulate, stream, "conv_taps_nhwc");
 }

@@ -29,6 +29,11 @@ def _primitive_conv(input, weight, bias, stride, padding, dilation, groups):
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[0], k, stride, padding, dilation, groups)):
         tc_stats['tc'] += 1
         return tc.conv2d_forward(input, weight, _terms_for(input.dtype))
+    if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and padding[0] == padding[1]
+            and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
+            and tc.channels_eligible(input.shape[1], weight.shape[0])):
+        tc_stats['tc'] += 1
+        return tc.conv2d_strided_forward(input, weight, 2, padding[0], _terms_for(input.dtype))
     tc_stats['aten'] += 1
     return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding, dilation=dilation, groups=groups)
 
@@ -41,6 +46,11 @@ def _primitive_conv_transpose(input, weight, bias, stride, padding, output_paddi
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[1], k, (1, 1), (k // 2, k // 2), dilation, groups)):
         tc_stats['tc'] += 1
         return tc.conv2d_forward(input, weight.flip([2, 3]).transpose(0, 1), _terms_for(input.dtype))
+    if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and tuple(padding) == (0, 0)
+            and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
+            and tc.channels_eligible(input.shape[1], weight.shape[1])):
+        tc_stats['tc'] += 1
+        return tc.conv_transpose2d_s2_forward(input, weight, tuple(output_padding), _terms_for(input.dtype))
     tc_stats['aten'] += 1
     return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
                                                 output_padding=output_padding, groups=groups, dilation=dilation)

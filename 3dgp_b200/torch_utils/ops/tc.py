@@ -61,29 +61,41 @@ def split_bf16(x_nhwc, styles=None, want_lo=True):
     return hi, lo
 
 
+def channels_eligible(Cin, Cout):
+    return Cin % 64 == 0 and (Cout % 128 == 0 or Cout in (64, 96))
+
+
 def conv_eligible(N, Cin, H, W, Cout, k, stride, padding, dilation, groups):
-    """Shapes the tcgen05 implicit-GEMM conv covers (csrc/conv_tc.cu)."""
+    """Stride-1 'same' shapes the tcgen05 implicit-GEMM conv covers (csrc/conv_tc.cu)."""
     if groups != 1 or tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or k not in (1, 3) or tuple(padding) != (k // 2, k // 2):
         return False
-    if Cin % 64 != 0 or not (Cout % 128 == 0 or Cout in (64, 96)):
-        return False
-    pow2 = lambda v: v >= 1 and (v & (v - 1)) == 0
-    if not (pow2(H) and pow2(W)):
-        return False
-    TW = min(W, 16); TH = min(H, 128 // TW); TN = 128 // (TW * TH)
-    return TW * TH * TN == 128 and N % TN == 0
+    return channels_eligible(Cin, Cout)
+
+
+def _prep(x, w_nhwc_f32, terms):
+    xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)          # NHWC view, contiguous
+    xh, xl = split_bf16(xn, want_lo=(terms == 3))
+    wh, wl = split_bf16(w_nhwc_f32.contiguous(), want_lo=(terms == 3))
+    return xh, xl, wh, wl
+
+
+def _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0):
+    import ctypes
+    L = _lib.lib()
+    arr = (ctypes.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
+    with torch.cuda.device(y.device):
+        rc = L.gp3d_conv_taps_nhwc(xh.data_ptr(), _lib.ptr(xl), wh.data_ptr(), _lib.ptr(wl), y.data_ptr(), N, H, W, Cin, Cout, slabs, len(taps),
+                                   ctypes.cast(arr, ctypes.c_void_p), in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0, 0, _lib.stream_ptr())
+    _lib.check(rc, 'conv_taps_nhwc')
 
 
 def conv2d_forward(x, w, terms):
-    """x [N,Cin,H,W] (any strides, float32/float16), w [Cout,Cin,k,k]  ->  y [N,Cout,H,W] in x.dtype with channels-last strides.
-    terms == 3: error-compensated bf16x3 (fp32-grade);  terms == 1: plain bf16 operands, fp32 accumulate."""
+    """Stride-1 'same' conv.  x [N,Cin,H,W] (any strides, float32/float16), w [Cout,Cin,k,k] -> y [N,Cout,H,W] in x.dtype, channels-last
+    strides.  terms == 3: error-compensated bf16x3 (fp32-grade); terms == 1: plain bf16 operands, fp32 accumulate."""
     L = _lib.lib()
     N, Cin, H, W = x.shape
     Cout, _, k, _ = w.shape
-    xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)          # NHWC view, contiguous
-    wn = w.to(torch.float32).permute(0, 2, 3, 1).contiguous()                            # [Cout,k,k,Cin]
-    xh, xl = split_bf16(xn, want_lo=(terms == 3))
-    wh, wl = split_bf16(wn, want_lo=(terms == 3))
+    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(0, 2, 3, 1), terms)
     y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         if terms == 3:
@@ -91,5 +103,40 @@ def conv2d_forward(x, w, terms):
         else:
             rc = L.gp3d_conv2d_nhwc_bf16(xh.data_ptr(), wh.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, 0, _lib.stream_ptr())
     _lib.check(rc, 'conv2d_nhwc_bf16x3' if terms == 3 else 'conv2d_nhwc_bf16')
+    y = y.permute(0, 3, 1, 2)
+    return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+
+def conv2d_strided_forward(x, w, stride, padding, terms):
+    """Stride-2 conv (correlation): y[n,co,i,j] = sum x[n,ci,2i+ky-p,2j+kx-p] w[co,ci,ky,kx]; one strided-gather launch."""
+    assert stride == 2
+    N, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    Ho = (H + 2 * padding - k) // 2 + 1
+    Wo = (W + 2 * padding - k) // 2 + 1
+    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(0, 2, 3, 1), terms)
+    y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=x.device)
+    taps = [(ky - padding, kx - padding, ky * k + kx) for ky in range(k) for kx in range(k)]
+    _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, k * k, taps, 2, Ho, Wo, Ho, Wo, 1, 1, 0, 0)
+    y = y.permute(0, 3, 1, 2)
+    return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+
+def conv_transpose2d_s2_forward(x, w, output_padding, terms):
+    """Stride-2 transposed conv, padding 0 (conv_transpose2d weight layout [Cin, Cout, k, k], k == 3):
+    y[n,co,2i+ky,2j+kx] += x[n,ci,i,j] w[ci,co,ky,kx], evaluated as four polyphase tap-convolutions on the low-resolution grid."""
+    N, Cin, H, W = x.shape
+    _, Cout, k, _ = w.shape
+    assert k == 3
+    Hout, Wout = 2 * H + 1 + output_padding[0], 2 * W + 1 + output_padding[1]
+    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(1, 2, 3, 0), terms)           # [Cout,3,3,Cin]
+    alloc = torch.zeros if (output_padding[0] or output_padding[1]) else torch.empty
+    y = alloc([N, Hout, Wout, Cout], dtype=torch.float32, device=x.device)
+    for a in (0, 1):
+        kys = [(0, 0), (-1, 2)] if a == 0 else [(0, 1)]         # (input offset, ky)
+        for b in (0, 1):
+            kxs = [(0, 0), (-1, 2)] if b == 0 else [(0, 1)]
+            taps = [(dy, dx, ky * 3 + kx) for (dy, ky) in kys for (dx, kx) in kxs]
+            _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Hout, Wout, 2, 2, a, b)
     y = y.permute(0, 3, 1, 2)
     return y if x.dtype == torch.float32 else y.to(x.dtype)

@@ -181,6 +181,18 @@ int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, 
 int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                             int Cin, int Cout, int ksize, int accumulate, void* stream);
 
+/* General tap convolution on the same tcgen05 pipeline -- the building block of the strided forms:
+ *   y[n][iy*osy+oy0][ix*osx+ox0][co] (+)= sum_t sum_ci x[n][iy*in_stride+dy_t][ix*in_stride+dx_t][ci] * w[co][slab_t][ci]
+ * for (iy, ix) in [0,HoP) x [0,WoP); out-of-range input pixels read as zero.  h_taps is a HOST array of ntaps x (dy, dx, slab).
+ *   - stride-2 transposed conv (G's up-sampling conv0, conv2d_resample.py:112-126; the input gradient of D's stride-2 convs) =
+ *     four polyphase launches (1, 2, 2 and 4 taps) with osy = osx = 2 and (oy0, ox0) in {0,1}^2: no zero-stuffed FLOPs;
+ *   - stride-2 conv (D's down-sampling conv1, conv2d_resample.py:106-109; the input gradient of G's conv0) = one launch with in_stride = 2.
+ * xl / wl may be NULL (single-term bf16) or both given (bf16x3).
+ */
+int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, float* y,
+                        int N, int H, int W, int Cin, int Cout, int num_slabs, int ntaps, const int* h_taps, int in_stride,
+                        int HoP, int WoP, int Hout, int Wout, int osy, int osx, int oy0, int ox0, int accumulate, void* stream);
+
 /* fp32 / fp16 -> bf16 hi (+ lo) split with optional per-(n, c) modulation (x * styles, networks_stylegan2.py:68), channel-minor
  * (NHWC) tensors: hi = bf16(x * s[n][c]); lo = bf16(x * s[n][c] - hi) (lo may be NULL).  s may be NULL.  src_dtype: GP3D_F32 / F16.
  */

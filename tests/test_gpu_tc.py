@@ -107,3 +107,52 @@ def test_conv2d_gradfix_fp16_uses_single_term_bf16():
     ref = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
     assert y.dtype == torch.float16
     assert (y.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H', [(2, 64, 128, 16), (3, 128, 128, 4), (1, 256, 128, 64)])
+def test_transposed_conv_stride2_polyphase_and_its_gradients(N, Cin, Cout, H):
+    """G's up-sampling conv0 (conv2d_resample.py:112-126): stride-2 transposed conv as four polyphase tap-convs; its input
+    gradient is the strided-gather conv.  Both against ATen fp32."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(N + Cin + H)
+    x = torch.randn(N, Cin, H, H, device='cuda', generator=g).requires_grad_(True)
+    w = (torch.randn(Cin, Cout, 3, 3, device='cuda', generator=g) / (3 * Cin ** 0.5)).requires_grad_(True)
+    dy = torch.randn(N, Cout, 2 * H + 1, 2 * H + 1, device='cuda', generator=g)
+    outs = []
+    for en in (True, False):
+        cg.tc_enabled = en
+        n0 = cg.tc_stats['tc']
+        y = cg.conv_transpose2d(x, w, stride=2, padding=0)
+        gx, gw = torch.autograd.grad(y, [x, w], dy)
+        outs.append((y, gx, gw, cg.tc_stats['tc'] - n0))
+    cg.tc_enabled = True
+    assert outs[0][3] >= 2 and outs[1][3] == 0
+    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
+    assert tuple(outs[0][0].shape) == (N, Cout, 2 * H + 1, 2 * H + 1)
+    for i in range(3):
+        assert rel(outs[0][i], outs[1][i]) < 1e-4, (i, rel(outs[0][i], outs[1][i]))
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,dtype', [(2, 128, 128, 36, torch.float32), (4, 64, 256, 12, torch.float32), (2, 128, 128, 20, torch.float16)])
+def test_strided_conv_and_its_transposed_gradient(N, Cin, Cout, H, dtype):
+    """D's down-sampling conv1 (FIR-padded input, stride-2 conv, conv2d_resample.py:106-109) and its input gradient (polyphase with output padding)."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(N + Cin + H)
+    x = torch.randn(N, Cin, H, H, device='cuda', generator=g).to(dtype).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) / (3 * Cin ** 0.5)).to(dtype).requires_grad_(True)
+    outs = []
+    for en in (True, False):
+        cg.tc_enabled = en
+        y = cg.conv2d(x, w, stride=2)
+        dy = torch.ones_like(y) * 0.5
+        dy[..., ::2, :] *= -1
+        gx, gw = torch.autograd.grad(y, [x, w], dy)
+        outs.append((y.float(), gx.float(), gw.float()))
+    cg.tc_enabled = True
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
+    for i in range(3):
+        assert outs[0][i].shape == outs[1][i].shape
+        assert rel(outs[0][i], outs[1][i]) < tol, (i, rel(outs[0][i], outs[1][i]))
