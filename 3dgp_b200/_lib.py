@@ -44,6 +44,7 @@ PROTOTYPES = {
     'gp3d_conv2d_nhwc_bf16': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16x3': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     'gp3d_conv_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p] + [c_int] * 10 + [c_void_p]),
+    'gp3d_wgrad_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 9 + [c_void_p] + [c_int] * 4 + [c_void_p]),
     'gp3d_split_bf16': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -140,3 +140,40 @@ def conv_transpose2d_s2_forward(x, w, output_padding, terms):
             _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Hout, Wout, 2, 2, a, b)
     y = y.permute(0, 3, 1, 2)
     return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+
+def wgrad_eligible(Cin, Cout):
+    return Cin % 128 == 0 and Cout % 128 == 0
+
+
+def conv_wgrad(dy, x, k, mode, stride, padding, terms):
+    """Weight gradient on the tcgen05 pixel-GEMM (csrc/wgrad_tc.cu).
+    mode 'conv'      : y = conv2d(x, w[Cout,Cin,k,k], stride, padding)            -> returns dW [Cout,Cin,k,k]
+    mode 'transpose' : y = conv_transpose2d(x, w[Cin,Cout,k,k], stride 2, pad 0)  -> returns dW [Cin,Cout,k,k]
+    dy: gradient of y, x: the op's input (any strides; float32 / float16)."""
+    import ctypes
+    L = _lib.lib()
+    N, Cx, Hx, Wx = x.shape
+    _, Cy, Hy, Wy = dy.shape
+    dn = dy.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+    xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+    dh, dl = split_bf16(dn, want_lo=(terms == 3))
+    xh, xl = split_bf16(xn, want_lo=(terms == 3))
+    if mode == 'conv':
+        # M operand = dy (Cout = Cy), N operand = x (Cin = Cx); pixel domain = output grid
+        taps = [(0, 0, ky - padding, kx - padding, ky * k + kx) for ky in range(k) for kx in range(k)]
+        sa, sb, HoP, WoP = 1, stride, Hy, Wy
+    else:
+        # y1[2i+ky][2j+kx] += x[i][j] w[ci][co][ky][kx]: M operand = dy1 read at stride 2 offset (ky,kx), N operand = x; domain = input grid
+        assert stride == 2 and padding == 0
+        taps = [(ky, kx, 0, 0, ky * k + kx) for ky in range(k) for kx in range(k)]
+        sa, sb, HoP, WoP = 2, 1, Hx, Wx
+    dW = torch.zeros([Cy, k * k, Cx], dtype=torch.float32, device=x.device)
+    arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
+    with torch.cuda.device(x.device):
+        rc = L.gp3d_wgrad_taps_nhwc(dh.data_ptr(), _lib.ptr(dl), xh.data_ptr(), _lib.ptr(xl), dW.data_ptr(), N, Hy, Wy, Cy, Hx, Wx, Cx, k * k,
+                                    len(taps), ctypes.cast(arr, ctypes.c_void_p), sa, sb, HoP, WoP, _lib.stream_ptr())
+    _lib.check(rc, 'wgrad_taps_nhwc')
+    dW = dW.view(Cy, k, k, Cx)
+    out = dW.permute(0, 3, 1, 2) if mode == 'conv' else dW.permute(3, 0, 1, 2)
+    return out.contiguous().to(x.dtype)

@@ -193,6 +193,16 @@ int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const vo
                         int N, int H, int W, int Cin, int Cout, int num_slabs, int ntaps, const int* h_taps, int in_stride,
                         int HoP, int WoP, int Hout, int Wout, int osy, int osx, int oy0, int ox0, int accumulate, void* stream);
 
+/* Weight gradient of the tap convolutions as a tcgen05 GEMM over pixels (replaces aten.convolution_backward's weight output,
+ * conv2d_gradfix.py:141-151):
+ *   dW[co][slab_t][ci] += sum_{n,iy,ix} dy[n][iy*sa+ay_t][ix*sa+ax_t][co] * x[n][iy*sb+by_t][ix*sb+bx_t][ci],  (iy,ix) in [0,HoP)x[0,WoP)
+ * dy [N][Hd][Wd][Cout], x [N][Hx][Wx][Cin] bf16 NHWC (hi, optional lo pair for bf16x3); h_taps: HOST array ntaps x (ay, ax, by, bx, slab);
+ * dW float32 [Cout][num_slabs][Cin], ACCUMULATED (caller zero-fills).  Cin % 128 == 0, Cout % 128 == 0.
+ */
+int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const void* xl, float* dW,
+                         int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
+                         int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream);
+
 /* fp32 / fp16 -> bf16 hi (+ lo) split with optional per-(n, c) modulation (x * styles, networks_stylegan2.py:68), channel-minor
  * (NHWC) tensors: hi = bf16(x * s[n][c]); lo = bf16(x * s[n][c] - hi) (lo may be NULL).  s may be NULL.  src_dtype: GP3D_F32 / F16.
  */
