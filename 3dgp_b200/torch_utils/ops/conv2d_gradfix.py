@@ -17,40 +17,57 @@ tc_enabled = True                   # route eligible convs (and their input-grad
 tc_stats = dict(tc=0, aten=0)       # how many primitive convolutions went where (bench.py / tests)
 
 
+_forced_terms = None
+
+
+@contextlib.contextmanager
+def tc_terms(n):
+    """Precision of the tensor-core convs issued inside the block: 3 = error-compensated bf16x3 (fp32-grade, default for float32
+    tensors), 1 = single bf16 product with fp32 accumulation (the class of arithmetic the reference's fp16 discriminator blocks use).
+    The choice is captured at forward time and reused by the corresponding backward convs."""
+    global _forced_terms
+    old = _forced_terms
+    _forced_terms = n
+    try:
+        yield
+    finally:
+        _forced_terms = old
+
+
 def _terms_for(dtype):
-    # float32 tensors (G is fp32-only in the reference, TF32 off): error-compensated bf16x3, fp32-grade accuracy.
-    # float16 tensors (D blocks >= 32^2 in the reference): plain bf16 operands with fp32 accumulation.
+    if _forced_terms is not None:
+        return _forced_terms
     return 3 if dtype == torch.float32 else 1
 
 
-def _primitive_conv(input, weight, bias, stride, padding, dilation, groups):
+def _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms):
     k = weight.shape[2]
     if (tc_enabled and bias is None and weight.shape[2] == weight.shape[3] and input.dtype in (torch.float32, torch.float16)
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[0], k, stride, padding, dilation, groups)):
         tc_stats['tc'] += 1
-        return tc.conv2d_forward(input, weight, _terms_for(input.dtype))
+        return tc.conv2d_forward(input, weight, terms)
     if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and padding[0] == padding[1]
             and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
             and tc.channels_eligible(input.shape[1], weight.shape[0])):
         tc_stats['tc'] += 1
-        return tc.conv2d_strided_forward(input, weight, 2, padding[0], _terms_for(input.dtype))
+        return tc.conv2d_strided_forward(input, weight, 2, padding[0], terms)
     tc_stats['aten'] += 1
     return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding, dilation=dilation, groups=groups)
 
 
-def _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups):
+def _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms):
     # stride-1 transposed conv == correlation with the flipped, transposed kernel and padding k-1-p
     k = weight.shape[2]
     if (tc_enabled and bias is None and tuple(stride) == (1, 1) and tuple(output_padding) == (0, 0) and weight.shape[2] == weight.shape[3]
             and tuple(padding) == (k - 1 - k // 2, k - 1 - k // 2) and input.dtype in (torch.float32, torch.float16)
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[1], k, (1, 1), (k // 2, k // 2), dilation, groups)):
         tc_stats['tc'] += 1
-        return tc.conv2d_forward(input, weight.flip([2, 3]).transpose(0, 1), _terms_for(input.dtype))
+        return tc.conv2d_forward(input, weight.flip([2, 3]).transpose(0, 1), terms)
     if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and tuple(padding) == (0, 0)
             and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
             and tc.channels_eligible(input.shape[1], weight.shape[1])):
         tc_stats['tc'] += 1
-        return tc.conv_transpose2d_s2_forward(input, weight, tuple(output_padding), _terms_for(input.dtype))
+        return tc.conv_transpose2d_s2_forward(input, weight, tuple(output_padding), terms)
     tc_stats['aten'] += 1
     return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
@@ -73,21 +90,21 @@ def _tuple2(v):
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     if input.device.type != 'cuda':
         raise RuntimeError('3dgp_b200.conv2d_gradfix: CUDA tensors only (no CPU path)')
-    return _conv(False, weight.shape, _tuple2(stride), _tuple2(padding), (0, 0), _tuple2(dilation), groups).apply(input, weight, bias)
+    return _conv(False, weight.shape, _tuple2(stride), _tuple2(padding), (0, 0), _tuple2(dilation), groups, _terms_for(input.dtype)).apply(input, weight, bias)
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
     if input.device.type != 'cuda':
         raise RuntimeError('3dgp_b200.conv2d_gradfix: CUDA tensors only (no CPU path)')
-    return _conv(True, weight.shape, _tuple2(stride), _tuple2(padding), _tuple2(output_padding), _tuple2(dilation), groups).apply(input, weight, bias)
+    return _conv(True, weight.shape, _tuple2(stride), _tuple2(padding), _tuple2(output_padding), _tuple2(dilation), groups, _terms_for(input.dtype)).apply(input, weight, bias)
 
 
 _cache = dict()
 
 
-def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
+def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms=3):
     weight_shape = tuple(weight_shape)
-    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms)
     if key in _cache:
         return _cache[key]
     ndim = 2
@@ -105,9 +122,9 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
         def forward(ctx, input, weight, bias):
             assert tuple(weight.shape) == weight_shape
             if not transpose:
-                out = _primitive_conv(input, weight, bias, stride, padding, dilation, groups)
+                out = _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms)
             else:
-                out = _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups)
+                out = _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms)
             ctx.save_for_backward(input, weight, bias)
             return out
 
@@ -117,7 +134,7 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
                 p = out_pad_for(input.shape, grad_output.shape)
-                gi = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups).apply(grad_output, weight, None)
+                gi = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms).apply(grad_output, weight, None)
                 assert gi.shape == input.shape
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 gw = Conv2dGradWeight.apply(grad_output, input, bias)
@@ -138,7 +155,7 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
                            or (transpose and tuple(stride) == (2, 2) and tuple(padding) == (0, 0) and k == 3)))
             if use_tc:
                 tc_stats['tc'] += 1
-                gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], _terms_for(input.dtype))
+                gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], terms)
                 ctx.save_for_backward(grad_output, input)
                 return gw
             tc_stats['aten'] += 1
@@ -158,7 +175,7 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
                 g2_go = Conv2d.apply(input, g2_gw, None)
             if ctx.needs_input_grad[1]:
                 p = out_pad_for(input.shape, grad_output.shape)
-                g2_in = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups).apply(grad_output, g2_gw, None)
+                g2_in = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms).apply(grad_output, g2_gw, None)
             return g2_go, g2_in, None
 
     _cache[key] = Conv2d

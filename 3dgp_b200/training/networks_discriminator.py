@@ -3,7 +3,7 @@
 import numpy as np
 import torch
 
-from ..torch_utils.ops import upfirdn2d
+from ..torch_utils.ops import conv2d_gradfix, upfirdn2d
 from .layers import Conv2dLayer, FullyConnectedLayer, MappingNetwork, ScalarEncoder1d
 
 
@@ -34,16 +34,19 @@ class DiscriminatorBlock(torch.nn.Module):
                                 trainable=trainable(), resample_filter=resample_filter, channels_last=cl)
 
     def forward(self, x, img, c=None, force_fp32=False):
-        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
-        mf = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
+        """Blocks the reference runs in fp16 (res >= 32, networks_discriminator.py:240) keep float32 STORAGE here and issue their
+        convolutions as single-product bf16 tensor-core convs with fp32 accumulation (conv2d_gradfix.tc_terms(1)); the fp32 blocks
+        use the error-compensated bf16x3 form.  This removes every fp16<->fp32 cast pass of the reference path."""
+        low_precision = self.use_fp16 and not force_fp32
         if x is not None:
-            x = x.to(dtype=dtype, memory_format=mf)
-        if self.in_channels == 0:
-            y = self.fromrgb(img.to(dtype=dtype, memory_format=mf), c=c)
-            x = x + y if x is not None else y
-        y = self.skip(x, c=c, gain=np.sqrt(0.5))
-        x = self.conv0(x, c=c)
-        x = self.conv1(x, c=c, gain=np.sqrt(0.5))
+            x = x.to(dtype=torch.float32)
+        with conv2d_gradfix.tc_terms(1 if low_precision else 3):
+            if self.in_channels == 0:
+                y = self.fromrgb(img.to(dtype=torch.float32), c=c)
+                x = x + y if x is not None else y
+            y = self.skip(x, c=c, gain=np.sqrt(0.5))
+            x = self.conv0(x, c=c)
+            x = self.conv1(x, c=c, gain=np.sqrt(0.5))
         return y.add_(x)
 
 
