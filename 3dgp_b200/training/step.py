@@ -39,6 +39,10 @@ class Trainer:
 
     def __init__(self, G, D, loss, cfg, rank=0, world_size=1, D_reg_interval=16, ema_kimg=10.0, ema_rampup=0.05, batch_size=None, micro_batch=None):
         self.G, self.D, self.loss, self.cfg, self.rank, self.world_size = G, D, loss, cfg, rank, world_size
+        if world_size > 1:   # training_loop.py:176-179: every rank starts from rank 0's parameters and buffers
+            for module in (G, D):
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=0)
         self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
         gk, dk = dict(cfg.model.generator.optim.kwargs), dict(cfg.model.discriminator.optim.kwargs)
         self.G_opt = torch.optim.Adam(G.parameters(), **gk)

@@ -281,7 +281,7 @@ def run_train_step(args, rank, world, local):
     rmod = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
     dev = torch.device('cuda', local)
     B = args.batch_gpu or 32
-    mb = args.micro_batch or min(B, 8)
+    mb = args.micro_batch or min(B, 16)
     assert B % mb == 0 and mb % 4 == 0, 'micro-batch must divide batch-gpu and be a multiple of the minibatch-std group (4)'
     small = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if args.small else {}
     cfg = cfgm.make_config(batch_size=B * world, **small)
