@@ -62,5 +62,5 @@ class ImportanceRenderer(torch.nn.Module):
             u_coarse=ro.get('u_coarse'), u_fine=ro.get('u_fine'), sn_coarse=ro.get('sn_coarse'), sn_fine=ro.get('sn_fine'),
             density_noise=ro.get('density_noise', 0.0), use_inf_depth=ro.get('use_inf_depth', True), last_back=ro.get('last_back', False),
             white_back_end_idx=ro.get('white_back_end_idx', 0), clamp_mode=ro.get('clamp_mode', 'softplus'),
-            mlp_mode=ro.get('mlp_mode', 0), seed=ro.get('seed', 0), offset=self.launch_counter)
+            mlp_mode=ro.get('mlp_mode', 2), seed=ro.get('seed', 0), offset=self.launch_counter)
         return rgb, depth, wsum, tfin

@@ -186,7 +186,7 @@ def run_raymarch(args, rank, world, local):
                     l2='inputs (%.2f GB of planes per GPU) larger than the 126 MB L2' % (B * 3 * RM['C'] * RM['P'] ** 2 * pb / 1e9),
                     rng='in-kernel Philox', mlp_mode=args.mlp_mode, parallelism=f'replicas x{world} (render does not shard)'),
         roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
-                      kernel='raymarch_fwd_kernel', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg),
+                      kernel='raymarch_fwd2_kernel' if args.mlp_mode else 'raymarch_fwd_kernel', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg),
         e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(2 * B * R_ * 12), d2h_bytes_per_step=int(B * R_ * 20)),
         gpu_launches=args.steps, clocks=clocks)
     return res
@@ -342,7 +342,7 @@ def run_train_step(args, rank, world, local):
                     parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)', conv_engine=args.conv_engine,
                     conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9)),
         roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
-                      kernel='raymarch_fwd_kernel (inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
+                      kernel='raymarch_fwd2_kernel (3xTF32 MLP, inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
                       launches_timed=len(kms), mean_ms=float(np.mean(kms))),
         roofline_step_tensor=dict(bound='tensor', achieved=flops_step / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
                                   frac=flops_step / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
@@ -414,7 +414,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=os.environ.get('GP3D_BENCH_WORKLOAD', 'train_step'), choices=['train_step', 'raymarch', 'ginfer'])
     ap.add_argument('--batch-gpu', type=int, default=0)
-    ap.add_argument('--mlp-mode', type=int, default=0)
+    ap.add_argument('--mlp-mode', type=int, default=2, help='tri-plane MLP arithmetic: 0 fp32 SIMT (v1 kernel), 1 TF32 mma, 2 3xTF32 mma (default)')
     ap.add_argument('--planes-fp16', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--micro-batch', type=int, default=0)

@@ -114,3 +114,16 @@ def test_render_full_size_properties():
     assert sat.any()
     d = depth.squeeze(-1)[sat]
     assert (d > 0.75 - 1e-3).all() and (d < 1.25 + 1e-3).all()
+
+
+@pytest.mark.parametrize('mode,tol', [(1, TOL), (2, 5e-5)])
+@pytest.mark.parametrize('name,kw', cases.render_cases(), ids=[c[0] for c in cases.render_cases()])
+def test_render_forward_tensor_core_mlp_vs_golden(golden, name, kw, mode, tol):
+    """Second-generation forward kernel (raymarch_fwd2.cu): MLP on mma.sync TF32 (mode 1) / 3xTF32 (mode 2), parallel per-ray phases."""
+    inp = cases.render_inputs(name, kw)
+    (rgb, depth, wsum, tfin), _ = _run(kw, inp, mlp_mode=mode)
+    g = golden('render')
+    assert maxrel(rgb.cpu().numpy(), g[name + '/rgb']) < tol
+    assert maxrel(depth.squeeze(-1).cpu().numpy(), g[name + '/depth']) < tol
+    assert maxrel(wsum.squeeze(-1).cpu().numpy(), g[name + '/wsum']) < tol
+    assert maxrel(tfin.cpu().numpy(), g[name + '/tfinal']) < tol
