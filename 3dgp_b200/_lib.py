@@ -39,6 +39,8 @@ PROTOTYPES = {
     'gp3d_raymarch_backward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 19 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
     'gp3d_modulate': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     'gp3d_demod_act': (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 6 + [c_float] * 3 + [c_void_p]),
+    'gp3d_demod_act_bwd': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
+    'gp3d_modulate_bwd': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     'gp3d_grad_epilogue': (c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     'gp3d_gemm_bf16_tn': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),

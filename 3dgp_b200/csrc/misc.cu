@@ -288,3 +288,142 @@ extern "C" int gp3d_split_bf16(const void* x, int src_dtype, const float* s, voi
     else { gp3d_set_error("split_bf16: source must be float32 or float16"); return GP3D_E_BADARG; }
     GP3D_RETURN_LAUNCH();
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Backward halves of the fused modulated-conv layer (channel-minor fp32 tensors [N][HW][C], C % 4 == 0).
+namespace {
+
+// Accumulates per-thread 4-channel partial sums across the pixel lanes of a block and adds them to global memory.
+__device__ __forceinline__ void block_channel_reduce_add(float4 v, float* smem4, int cv, int CV, int PL, int pl, float* dst /* [C] */) {
+    // smem4: [PL][CV] float4; threads with pl >= PL (when CV does not divide the block) hold zeros and stay out
+    if (pl < PL) reinterpret_cast<float4*>(smem4)[pl * CV + cv] = v;
+    __syncthreads();
+    if (pl == 0) {
+        float4 a = v;
+        for (int k = 1; k < PL; k++) {
+            const float4 b = reinterpret_cast<float4*>(smem4)[k * CV + cv];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        atomicAdd(dst + 4 * cv + 0, a.x); atomicAdd(dst + 4 * cv + 1, a.y); atomicAdd(dst + 4 * cv + 2, a.z); atomicAdd(dst + 4 * cv + 3, a.w);
+    }
+    __syncthreads();
+}
+
+// y = clamp-free act(c * d[n,co] + noise[n?,hw] + b[co]) * gain  (forward: demod_act_kernel).  Given dy and the saved y:
+//   dt = dy * gain * act'(y);  dc = dt * d;  g_b[co] += dt;  g_d[n,co] += dt * c  with c reconstructed from y;  g_ns += dt * noise.
+template <int ACT>
+__global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ d,
+                                                            const float* __restrict__ noise, const float* __restrict__ noise_scale,
+                                                            int noise_per_sample, const float* __restrict__ b,
+                                                            float* __restrict__ dc, float* __restrict__ g_d, float* __restrict__ g_b,
+                                                            float* __restrict__ g_ns, int N, int HW, int C, float alpha, float gain, int chunks) {
+    extern __shared__ float red_smem[];
+    const float nscale = (noise && noise_scale) ? *noise_scale : 1.f;
+    const int CV_all = C / 4;
+    const int CV = CV_all < 256 ? CV_all : 256;          // channel vectors handled per pass
+    const int PL = 256 / CV;                              // pixel lanes
+    const int cvl = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    float ns_acc = 0.f;
+    for (int cbase = 0; cbase < CV_all; cbase += CV) {
+        const int cv = cbase + cvl;
+        const bool act_thread = (pl < PL) && (cv < CV_all);
+        float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act_thread) {
+            const float4 dv = d ? *reinterpret_cast<const float4*>(d + (int64_t)n * C + 4 * cv) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 bv = b ? *reinterpret_cast<const float4*>(b + 4 * cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int px = p0 + pl; px < p1; px += PL) {
+                const int64_t off = ((int64_t)n * HW + px) * C + 4 * cv;
+                const float4 g = *reinterpret_cast<const float4*>(dy + off);
+                const float4 yy = *reinterpret_cast<const float4*>(y + off);
+                const float nraw = noise ? noise[(noise_per_sample ? (int64_t)n * HW : 0) + px] : 0.f;   // unscaled noise image
+                const float nz = nraw * nscale;
+                float gy[4] = {g.x, g.y, g.z, g.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+                const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+                float o[4], dt[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float slope = (ACT == 3 && yv[k] < 0.f) ? alpha : 1.f;
+                    dt[k] = gy[k] * gain * slope;
+                    const float t = yv[k] / (gain * slope);               // pre-activation: c * d + noise + b
+                    const float c = (t - nz - bb[k]) / dd[k];
+                    o[k] = dt[k] * dd[k];
+                    ns_acc += dt[k] * nraw;
+                    if (k == 0) { sb.x += dt[k]; sd.x += dt[k] * c; } else if (k == 1) { sb.y += dt[k]; sd.y += dt[k] * c; }
+                    else if (k == 2) { sb.z += dt[k]; sd.z += dt[k] * c; } else { sb.w += dt[k]; sd.w += dt[k] * c; }
+                }
+                *reinterpret_cast<float4*>(dc + off) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        if (g_b) block_channel_reduce_add(sb, red_smem, cvl, CV, PL, pl, g_b + 4 * cbase);
+        if (g_d && d) block_channel_reduce_add(sd, red_smem, cvl, CV, PL, pl, g_d + (int64_t)n * C + 4 * cbase);
+    }
+    if (g_ns && noise) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ns_acc += __shfl_xor_sync(0xffffffffu, ns_acc, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(g_ns, ns_acc);
+    }
+}
+
+// dx = dxs * s[n,ci];  g_s[n,ci] += sum_hw dxs * x
+__global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, const float* __restrict__ s,
+                                                           float* __restrict__ dx, float* __restrict__ g_s, int N, int HW, int C, int chunks) {
+    extern __shared__ float red_smem[];
+    const int CV_all = C / 4;
+    const int CV = CV_all < 256 ? CV_all : 256;
+    const int PL = 256 / CV;
+    const int cvl = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    for (int cbase = 0; cbase < CV_all; cbase += CV) {
+        const int cv = cbase + cvl;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pl < PL && cv < CV_all) {
+            const float4 sv = *reinterpret_cast<const float4*>(s + (int64_t)n * C + 4 * cv);
+            for (int px = p0 + pl; px < p1; px += PL) {
+                const int64_t off = ((int64_t)n * HW + px) * C + 4 * cv;
+                const float4 g = *reinterpret_cast<const float4*>(dxs + off);
+                const float4 xv = *reinterpret_cast<const float4*>(x + off);
+                acc.x += g.x * xv.x; acc.y += g.y * xv.y; acc.z += g.z * xv.z; acc.w += g.w * xv.w;
+                *reinterpret_cast<float4*>(dx + off) = make_float4(g.x * sv.x, g.y * sv.y, g.z * sv.z, g.w * sv.w);
+            }
+        }
+        block_channel_reduce_add(acc, red_smem, cvl, CV, PL, pl, g_s + (int64_t)n * C + 4 * cbase);
+    }
+}
+
+static int reduce_chunks(int N, int HW) {
+    int chunks = (GP3D_NUM_SMS * 4 + N - 1) / N;
+    if (chunks > HW) chunks = HW;
+    if (chunks < 1) chunks = 1;
+    return chunks;
+}
+
+}  // namespace
+
+extern "C" int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample, const float* b,
+                                  float* dc, float* g_d, float* g_b, float* g_ns, int N, int HW, int C, int act, float alpha, float gain,
+                                  void* stream) {
+    GP3D_CHECK_ARG(dy && y && dc && N >= 1 && HW >= 1 && C >= 4 && C % 4 == 0, "demod_act_bwd: bad arguments (C must be a multiple of 4)");
+    GP3D_CHECK_ARG(act == 1 || act == 3, "demod_act_bwd: only linear (1) and lrelu (3) are fused, got %d", act);
+    GP3D_CHECK_ARG(gain != 0.f, "demod_act_bwd: gain must be non-zero");
+    GP3D_CHECK_ARG(gp3d_aligned16(dy) && gp3d_aligned16(y) && gp3d_aligned16(dc) && (!d || gp3d_aligned16(d)) && (!b || gp3d_aligned16(b)),
+                   "demod_act_bwd: pointers must be 16-byte aligned");
+    const int chunks = reduce_chunks(N, HW);
+    const size_t smem = 256 * sizeof(float4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks);
+    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks);
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* dx, float* g_s, int N, int HW, int C, void* stream) {
+    GP3D_CHECK_ARG(dxs && x && s && dx && g_s && N >= 1 && HW >= 1 && C >= 4 && C % 4 == 0, "modulate_bwd: bad arguments (C must be a multiple of 4)");
+    GP3D_CHECK_ARG(gp3d_aligned16(dxs) && gp3d_aligned16(x) && gp3d_aligned16(s) && gp3d_aligned16(dx), "modulate_bwd: pointers must be 16-byte aligned");
+    const int chunks = reduce_chunks(N, HW);
+    modulate_bwd_kernel<<<N * chunks, 256, 256 * sizeof(float4), (cudaStream_t)stream>>>(dxs, x, s, dx, g_s, N, HW, C, chunks);
+    GP3D_RETURN_LAUNCH();
+}

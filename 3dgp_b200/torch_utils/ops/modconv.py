@@ -1,0 +1,158 @@
+"""Fused modulated-convolution layer for the tri-plane decoder's training path (fp32, CUDA):
+
+    y = lrelu( FIR_up?( conv( x * styles , W ) ) * dcoefs + noise * strength + bias ) * gain
+
+i.e. networks_stylegan2.py:67-76 + :142-144 (x*styles -> conv2d_resample -> fma -> bias_act) as ONE autograd node whose
+forward is   split(x*s -> bf16 hi/lo)  ->  tcgen05 conv (stride-1 or polyphase up-2)  [-> upfirdn2d]  ->  demod+noise+bias+act
+and whose backward is   demod_act_bwd (dt, dc, g_bias, g_dcoefs, g_strength in one pass)  [-> upfirdn2d adjoint]  ->  split  ->
+tcgen05 input-gradient conv + tcgen05 weight-gradient GEMM  ->  modulate_bwd (dx, g_styles in one pass).
+Nothing but x, y and the bf16 operand pair is kept for backward; no x*styles / pre-activation / FIR intermediates survive.
+First-order only (the reference differentiates G twice only when pl_weight > 0, which the 3dgp config sets to 0).
+"""
+import torch
+
+from ... import _lib
+from . import tc, upfirdn2d
+
+
+def eligible(x, weight, up, conv_clamp):
+    Cout, Cin, k, _ = weight.shape
+    return (x.is_cuda and x.dtype == torch.float32 and conv_clamp is None and up in (1, 2) and k in (1, 3) and (up == 1 or k == 3)
+            and tc.channels_eligible(Cin, Cout) and Cin % 4 == 0 and Cout % 4 == 0)
+
+
+def _nhwc(t):
+    return t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up):
+    L = _lib.lib()
+    dev = xh.device
+    if up == 1:
+        y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, 0, _lib.stream_ptr())
+        _lib.check(rc, 'conv2d_nhwc_bf16x3')
+        return y
+    Ho, Wo = 2 * H + 1, 2 * W + 1
+    y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=dev)
+    for a in (0, 1):
+        kys = [(0, 0), (-1, 2)] if a == 0 else [(0, 1)]
+        for b in (0, 1):
+            kxs = [(0, 0), (-1, 2)] if b == 0 else [(0, 1)]
+            taps = [(dy, dx, ky * 3 + kx) for (dy, ky) in kys for (dx, kx) in kxs]
+            tc._taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Ho, Wo, 2, 2, a, b)
+    return y
+
+
+class _ModConvLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain):
+        L = _lib.lib()
+        N, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        dev = x.device
+        xn = _nhwc(x)
+        st = styles.to(torch.float32).contiguous()
+        xh, xl = tc.split_bf16(xn, styles=st)
+        wn = weight.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        wh, wl = tc.split_bf16(wn)
+        c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
+        if up == 2:   # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
+            c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
+        Ho, Wo = c.shape[1], c.shape[2]
+        y = torch.empty_like(c)
+        d = dcoefs.to(torch.float32).contiguous() if dcoefs is not None else None
+        nz = None
+        nps = 0
+        if noise is not None:
+            nz = (noise.to(torch.float32) * noise_strength).contiguous()          # [1|N, 1, Ho, Wo] or [Ho, Wo]
+            nps = 1 if (nz.dim() == 4 and nz.shape[0] == N and N > 1) else 0
+        b = bias.to(torch.float32).contiguous() if bias is not None else None
+        with torch.cuda.device(dev):
+            rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
+                                  3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
+        _lib.check(rc, 'demod_act')
+        ctx.save_for_backward(xn, xh, xl, weight, st, d if d is not None else torch.empty(0, device=dev), y,
+                              noise if noise is not None else torch.empty(0, device=dev),
+                              noise_strength if noise is not None else torch.empty(0, device=dev),
+                              b if b is not None else torch.empty(0, device=dev), fir if fir is not None else torch.empty(0, device=dev))
+        ctx.cfg = (N, Cin, H, W, Cout, k, up, act, float(alpha), float(gain), nps, Ho, Wo)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        xn, xh, xl, weight, st, d, y, noise, noise_strength, b, fir = ctx.saved_tensors
+        N, Cin, H, W, Cout, k, up, act, alpha, gain, nps, Ho, Wo = ctx.cfg
+        dev = dy.device
+        has_d, has_n, has_b = d.numel() > 0, noise.numel() > 0, b.numel() > 0
+        dyn = _nhwc(dy.to(torch.float32))
+        dc = torch.empty_like(dyn)
+        g_d = torch.zeros_like(d) if has_d else None
+        g_b = torch.zeros([Cout], dtype=torch.float32, device=dev) if has_b else None
+        nz_img = noise.to(torch.float32).contiguous() if has_n else None                 # unscaled noise image
+        ns = noise_strength.to(torch.float32).reshape(1).contiguous() if has_n else None
+        g_ns = torch.zeros([1], dtype=torch.float32, device=dev) if has_n else None
+        with torch.cuda.device(dev):
+            rc = L.gp3d_demod_act_bwd(dyn.data_ptr(), y.data_ptr(), _lib.ptr(d if has_d else None), _lib.ptr(nz_img), _lib.ptr(ns), nps,
+                                      _lib.ptr(b if has_b else None), dc.data_ptr(), _lib.ptr(g_d), _lib.ptr(g_b), _lib.ptr(g_ns), N, Ho * Wo, Cout,
+                                      3 if act == 'lrelu' else 1, alpha, gain, _lib.stream_ptr())
+        _lib.check(rc, 'demod_act_bwd')
+        if g_ns is not None:
+            g_ns = g_ns.reshape(noise_strength.shape)
+        if up == 2:   # adjoint of the FIR (upfirdn2d.py:250-269): same filter, flipped, padding p = fw - pad - 1 = 2
+            dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
+        dch, dcl = tc.split_bf16(dc)
+        # input gradient
+        w32 = weight.detach().to(torch.float32)
+        dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
+        if tc.channels_eligible(Cout, Cin):
+            if up == 1:
+                wd = w32.flip([2, 3]).permute(1, 2, 3, 0).contiguous()               # [Cin,k,k,Cout]
+                wdh, wdl = tc.split_bf16(wd)
+                with torch.cuda.device(dev):
+                    rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
+                _lib.check(rc, 'conv2d_nhwc_bf16x3')
+            else:   # dx[i,j] = sum dc1[2i+ky, 2j+kx] w[co][ci][ky][kx]: strided gather over the (2H+1)^2 gradient
+                wd = w32.permute(1, 2, 3, 0).contiguous()                              # [Cin,ky,kx,Cout]
+                wdh, wdl = tc.split_bf16(wd)
+                taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+                tc._taps_launch(dch, dcl, wdh, wdl, dxs, N, 2 * H + 1, 2 * W + 1, Cout, Cin, 9, taps, 2, H, W, H, W, 1, 1, 0, 0)
+        else:       # e.g. toRGB (Cout = 96): tiny 1x1 contraction, ATen
+            assert up == 1
+            dxs = torch.nn.functional.conv2d(dc.permute(0, 3, 1, 2), w32.flip([2, 3]).transpose(0, 1), padding=k // 2).permute(0, 2, 3, 1).contiguous()
+        # weight gradient
+        if tc.wgrad_eligible(Cin, Cout):
+            import ctypes
+            if up == 1:
+                taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
+                sa, sb, HoP, WoP, Hd, Wd = 1, 1, H, W, H, W
+            else:
+                taps = [(ky, kx, 0, 0, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+                sa, sb, HoP, WoP, Hd, Wd = 2, 1, H, W, 2 * H + 1, 2 * W + 1
+            gw = torch.zeros([Cout, k * k, Cin], dtype=torch.float32, device=dev)
+            arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
+            with torch.cuda.device(dev):
+                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), dcl.data_ptr(), xh.data_ptr(), xl.data_ptr(), gw.data_ptr(), N, Hd, Wd, Cout, H, W, Cin, k * k,
+                                            len(taps), ctypes.cast(arr, ctypes.c_void_p), sa, sb, HoP, WoP, _lib.stream_ptr())
+            _lib.check(rc, 'wgrad_taps_nhwc')
+            gw = gw.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+        else:
+            assert up == 1
+            xs = (xh.float() + xl.float()).permute(0, 3, 1, 2)
+            gw = torch.ops.aten.convolution_backward(dc.permute(0, 3, 1, 2), xs, w32, bias_sizes=None, stride=[1, 1], padding=[k // 2, k // 2], dilation=[1, 1],
+                                                     transposed=False, output_padding=[0, 0], groups=1, output_mask=[False, True, False])[1]
+        # through the modulation
+        dx = torch.empty_like(dxs)
+        g_s = torch.zeros_like(st)
+        with torch.cuda.device(dev):
+            rc = L.gp3d_modulate_bwd(dxs.data_ptr(), xn.data_ptr(), st.data_ptr(), dx.data_ptr(), g_s.data_ptr(), N, H * W, Cin, _lib.stream_ptr())
+        _lib.check(rc, 'modulate_bwd')
+        return (dx.permute(0, 3, 1, 2), gw.to(weight.dtype), g_s, g_d, None, g_ns, g_b, None, None, None, None, None)
+
+
+def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=None, bias=None, up=1, fir=None, act='lrelu', alpha=0.2, gain=1.0):
+    if noise is not None and not torch.is_tensor(noise_strength):
+        noise_strength = torch.as_tensor(float(noise_strength if noise_strength is not None else 1.0), device=x.device)
+    return _ModConvLayer.apply(x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain)

@@ -4,7 +4,9 @@ upfirdn2d); the dense contraction goes through conv2d_resample -> conv2d_gradfix
 import numpy as np
 import torch
 
-from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
+from ..torch_utils.ops import bias_act, conv2d_resample, fma, modconv, upfirdn2d
+
+fused_layer_enabled = True   # route eligible training-path layers through the fused modulated-conv node (ops/modconv.py)
 from .layers import Conv2dLayer, FullyConnectedLayer
 
 
@@ -71,6 +73,18 @@ class SynthesisLayer(torch.nn.Module):
             noise = noise_in * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
+        if (fused_layer_enabled and not fused_modconv and self.activation == 'lrelu' and modconv.eligible(x, self.weight, self.up, self.conv_clamp)
+                and x.shape[2] >= 8):
+            # training path, fp32: x*styles -> conv(+FIR) -> *dcoefs + noise + bias -> lrelu*gain as one autograd node.
+            # dcoefs = rsqrt(sum_{i,k} (w[o,i,k] s[n,i])^2 + 1e-8) (:62) evaluated as a [B,Cin] x [Cin,Cout] product of squares.
+            dcoefs = (styles.square() @ self.weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+            nimg = None
+            if self.use_noise and noise_mode == 'random':
+                nimg = noise_in
+            elif self.use_noise and noise_mode == 'const':
+                nimg = self.noise_const
+            return modconv.modconv_layer(x, self.weight, styles, dcoefs=dcoefs, noise=nimg, noise_strength=self.noise_strength if nimg is not None else None,
+                                         bias=self.bias, up=self.up, fir=self.resample_filter, act='lrelu', alpha=0.2, gain=self.act_gain * gain)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                              resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
@@ -89,6 +103,8 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
+        if fused_layer_enabled and not fused_modconv and modconv.eligible(x, self.weight, 1, self.conv_clamp) and x.shape[2] >= 8:
+            return modconv.modconv_layer(x, self.weight, styles, bias=self.bias, up=1, act='linear', gain=1.0)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 

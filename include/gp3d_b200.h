@@ -153,6 +153,16 @@ int gp3d_demod_act(const void* x, const void* d, const void* noise, int noise_pe
                    void* y, int dtype, int N, int C, int HW, int cl,
                    int act, float alpha, float gain, float clamp, void* stream);
 
+/* Backward halves of the fused modulated-conv layer, channel-minor float32 [N][HW][C] (C % 4 == 0):
+ *   gp3d_demod_act_bwd : given dy and the saved OUTPUT y of gp3d_demod_act (no clamp): dt = dy*gain*act'(y); dc = dt*d[n,c];
+ *                        g_b[c] += sum dt; g_d[n,c] += sum_hw dt*c (c rebuilt from y); g_ns += sum dt*noise  (noise = UNSCALED image, *noise_scale = its device-side strength).  (fma.py:33-53 +
+ *                        bias_act.py:157-172 in one pass; g_* are ACCUMULATED, caller zero-fills; any of d/noise/b/g_* may be NULL)
+ *   gp3d_modulate_bwd  : dx = dxs * s[n,c];  g_s[n,c] += sum_hw dxs * x           (backward of x * styles, networks_stylegan2.py:68)
+ */
+int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample, const float* b,
+                       float* dc, float* g_d, float* g_b, float* g_ns, int N, int HW, int C, int act, float alpha, float gain, void* stream);
+int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* dx, float* g_s, int N, int HW, int C, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Gradient all-reduce epilogue (reference training_loop.py:340-341): in place
  *   g = nan_to_num(g / world, nan=0, posinf=1e5, neginf=-1e5)    over a flat float32 buffer.
