@@ -49,6 +49,7 @@ class _ModConvLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain):
         L = _lib.lib()
+        upfirdn2d._init()
         N, Cin, H, W = x.shape
         Cout, _, k, _ = weight.shape
         dev = x.device
