@@ -34,109 +34,133 @@ template <int BN, int TERMS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmWl,
-                      float* __restrict__ Y, ConvGeom g, int accumulate) {
+                      float* __restrict__ Y, ConvGeom g, int accumulate, int num_tiles) {
+    // Persistent: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers (2 x 128 columns) let the epilogue of
+    // tile i overlap the TMA / MMA main loop of tile i+1; the smem ring and its phases run continuously across tiles.
     constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
     constexpr uint32_t kOperand = (CBM + BN) * CBK * 2;
     constexpr uint32_t kStage = kOperand * (TERMS == 3 ? 2 : 1);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // keep every stage 1024-byte aligned: A tile is 16 KB, B tile BN*128 B (multiple of 1024 for BN % 8 == 0)
     unsigned char* tiles = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)CSTAGES * kStage);
     uint64_t* empty_bar = full_bar + CSTAGES;
-    uint64_t* accum_bar = empty_bar + CSTAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + CSTAGES;       // [2] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile decomposition: blockIdx.x = ((tn * tiles_y + ty) * tiles_x + tx) * tiles_co + tco   (cout fastest: activations reused from L2)
-    int t = blockIdx.x;
-    const int tco = t % g.tiles_co; t /= g.tiles_co;
-    const int tx = t % g.tiles_x; t /= g.tiles_x;
-    const int ty = t % g.tiles_y; t /= g.tiles_y;
-    const int tn = t;
-    const int x0 = tx * g.TW, y0 = ty * g.TH, n0 = tn * g.TN, co0 = tco * BN;
     const int cblocks = g.Cin / CBK;
     const int num_kb = g.ntaps * cblocks;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < CSTAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(accum_bar, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }   // 4 epilogue warps arrive
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile decomposition: tile = ((tn * tiles_y + ty) * tiles_x + tx) * tiles_co + tco   (cout fastest: activations reused from L2)
+    auto decode = [&](int t, int& x0, int& y0, int& n0, int& co0) {
+        const int tco = t % g.tiles_co; t /= g.tiles_co;
+        const int tx = t % g.tiles_x; t /= g.tiles_x;
+        const int ty = t % g.tiles_y; t /= g.tiles_y;
+        x0 = tx * g.TW; y0 = ty * g.TH; n0 = t * g.TN; co0 = tco * BN;
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int st = kb % CSTAGES; const uint32_t ph = (kb / CSTAGES) & 1;
-                const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int cx = x0 * g.in_stride + g.tdx[tap], cy = y0 * g.in_stride + g.tdy[tap], slab = g.tslab[tap];
-                mbar_wait(&empty_bar[st], ph ^ 1);
-                unsigned char* sa = tiles + (size_t)st * kStage;
-                unsigned char* sb = sa + CBM * CBK * 2;
-                mbar_expect_tx(&full_bar[st], kStage);
-                tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, cx, cy, n0);
-                tma_load_2d(sb, &tmW, &full_bar[st], slab * g.Cin + cb * CBK, co0);
-                if (TERMS == 3) {
-                    tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, cx, cy, n0);
-                    tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], slab * g.Cin + cb * CBK, co0);
+            uint32_t it = 0;                                  // global k-block counter (ring position)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int x0, y0, n0, co0;
+                decode(tile, x0, y0, n0, co0);
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int st = it % CSTAGES; const uint32_t ph = (it / CSTAGES) & 1;
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int cx = x0 * g.in_stride + g.tdx[tap], cy = y0 * g.in_stride + g.tdy[tap], slab = g.tslab[tap];
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    unsigned char* sa = tiles + (size_t)st * kStage;
+                    unsigned char* sb = sa + CBM * CBK * 2;
+                    mbar_expect_tx(&full_bar[st], kStage);
+                    tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, cx, cy, n0);
+                    tma_load_2d(sb, &tmW, &full_bar[st], slab * g.Cin + cb * CBK, co0);
+                    if (TERMS == 3) {
+                        tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, cx, cy, n0);
+                        tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], slab * g.Cin + cb * CBK, co0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16_f32(CBM, BN);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int st = kb % CSTAGES; const uint32_t ph = (kb / CSTAGES) & 1;
-                mbar_wait(&full_bar[st], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+                const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + (size_t)st * kStage);
-                const uint32_t sb = sa + CBM * CBK * 2;
+                const uint32_t tmem_d = tmem_base + buf * 128;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int st = it % CSTAGES; const uint32_t ph = (it / CSTAGES) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)st * kStage);
+                    const uint32_t sb = sa + CBM * CBK * 2;
 #pragma unroll
-                for (int k = 0; k < CBK / 16; k++) {
-                    const uint64_t dah = make_desc_k_sw128(sa + k * 32), dbh = make_desc_k_sw128(sb + k * 32);
-                    umma_bf16(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    if (TERMS == 3) {
-                        umma_bf16(tmem_base, dah, make_desc_k_sw128(sb + kOperand + k * 32), idesc, 1u);
-                        umma_bf16(tmem_base, make_desc_k_sw128(sa + kOperand + k * 32), dbh, idesc, 1u);
+                    for (int k = 0; k < CBK / 16; k++) {
+                        const uint64_t dah = make_desc_k_sw128(sa + k * 32), dbh = make_desc_k_sw128(sb + k * 32);
+                        umma_bf16(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (TERMS == 3) {
+                            umma_bf16(tmem_d, dah, make_desc_k_sw128(sb + kOperand + k * 32), idesc, 1u);
+                            umma_bf16(tmem_d, make_desc_k_sw128(sa + kOperand + k * 32), dbh, idesc, 1u);
+                        }
                     }
+                    umma_commit(&empty_bar[st]);
                 }
-                umma_commit(&empty_bar[st]);
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(accum_bar);
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int r = q * 32 + lane;                       // pixel index inside the tile: ((n*TH + h)*TW + w)
-        const int wl = r % g.TW, hl = (r / g.TW) % g.TH, nl = r / (g.TW * g.TH);
-        const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
-        const bool inside = (ix < g.WoP) && (iy < g.HoP) && (nn < g.N);
-        float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + g.oy0)) * g.Wout + (size_t)(ix * g.osx + g.ox0)) * g.Cout + co0;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+            const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+            int x0, y0, n0, co0;
+            decode(tile, x0, y0, n0, co0);
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const int r = q * 32 + lane;                       // pixel index inside the tile: ((n*TH + h)*TW + w)
+            const int wl = r % g.TW, hl = (r / g.TW) % g.TH, nl = r / (g.TW * g.TH);
+            const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
+            const bool inside = (ix < g.WoP) && (iy < g.HoP) && (nn < g.N);
+            float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + g.oy0)) * g.Wout + (size_t)(ix * g.osx + g.ox0)) * g.Cout + co0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective: every lane participates
-            tmem_ld_wait();
-            if (!inside) continue;
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
+                tmem_ld_wait();
+                if (!inside) continue;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                float4* dst = reinterpret_cast<float4*>(yrow + c + j);
-                if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                *dst = o;
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    float4* dst = reinterpret_cast<float4*>(yrow + c + j);
+                    if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                    *dst = o;
+                }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);       // this warp's quarter of the buffer is free again
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 128);
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 template <int BN, int TERMS>
@@ -148,8 +172,11 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
     auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { gp3d_set_error("conv2d_nhwc_bf16: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    const int64_t grid = (int64_t)g.tiles_n * g.tiles_y * g.tiles_x * g.tiles_co;
-    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, tmXl, tmWl, y, g, accumulate);
+    const int64_t num_tiles = (int64_t)g.tiles_n * g.tiles_y * g.tiles_x * g.tiles_co;
+    int sms = GP3D_NUM_SMS, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t grid = num_tiles < sms ? num_tiles : sms;        // persistent: one CTA per SM
+    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, tmXl, tmWl, y, g, accumulate, (int)num_tiles);
     return 0;
 }
 

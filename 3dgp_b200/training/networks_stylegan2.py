@@ -73,9 +73,8 @@ class SynthesisLayer(torch.nn.Module):
             noise = noise_in * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        if (fused_layer_enabled and not fused_modconv and self.activation == 'lrelu' and modconv.eligible(x, self.weight, self.up, self.conv_clamp)
-                and x.shape[2] >= 8):
-            # training path, fp32: x*styles -> conv(+FIR) -> *dcoefs + noise + bias -> lrelu*gain as one autograd node.
+        if (fused_layer_enabled and self.activation == 'lrelu' and modconv.eligible(x, self.weight, self.up, self.conv_clamp) and x.shape[2] >= 8):
+            # fp32 CUDA path (training AND inference: scaling activations (:67-76) and scaling weights (:78-88) are the same map, Appendix A): x*styles -> conv(+FIR) -> *dcoefs + noise + bias -> lrelu*gain as one autograd node.
             # dcoefs = rsqrt(sum_{i,k} (w[o,i,k] s[n,i])^2 + 1e-8) (:62) evaluated as a [B,Cin] x [Cin,Cout] product of squares.
             dcoefs = (styles.square() @ self.weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
             nimg = None
@@ -103,7 +102,7 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        if fused_layer_enabled and not fused_modconv and modconv.eligible(x, self.weight, 1, self.conv_clamp) and x.shape[2] >= 8:
+        if fused_layer_enabled and modconv.eligible(x, self.weight, 1, self.conv_clamp) and x.shape[2] >= 8:
             return modconv.modconv_layer(x, self.weight, styles, bias=self.bias, up=1, act='linear', gain=1.0)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)

@@ -352,6 +352,57 @@ def run_train_step(args, rank, world, local):
     return res
 
 
+def run_ginfer(args, rank, world, local):
+    """BASELINE configs[4]: G-only inference (the FID2k path, metric_utils.py:303-319): G(z, c, camera) in eval mode, full-frame
+    256x256 render (65 536 rays / image, 48+48 samples / ray), images converted to uint8 on the device and read back."""
+    gp = importlib.import_module('3dgp_b200')
+    cfgm = importlib.import_module('3dgp_b200.config'); dn = importlib.import_module('3dgp_b200.dnnlib')
+    dev = torch.device('cuda', local)
+    B = args.batch_gpu or 16
+    cfg = cfgm.make_config(batch_size=B * world)
+    torch.manual_seed(99 + rank)
+    G, _ = cfgm.build_networks(cfg, dev)
+    G.eval().requires_grad_(False)
+    host = synthetic_batch(cfg, B, dev, seed=rank)
+    keys = ('z', 'c', 'angles', 'fov', 'radius', 'look_at')
+    d = {k: host[k].to(dev) for k in keys}
+    cam = dn.TensorGroup(angles=d['angles'], fov=d['fov'], radius=d['radius'], look_at=d['look_at'])
+
+    def step():
+        with torch.no_grad():
+            img = G(d['z'], d['c'], cam, noise_mode='const')
+            return (img[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8)
+
+    c0 = gp._lib.launch_count
+    ms, clocks = timed_region(step, args.steps, args.warmup, world)
+    launches = (gp._lib.launch_count - c0) // (args.steps + max(args.warmup, 3))
+    out_h = torch.empty([B, 3, cfg.dataset.resolution, cfg.dataset.resolution], dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        cm = dn.TensorGroup(angles=dd['angles'], fov=dd['fov'], radius=dd['radius'], look_at=dd['look_at'])
+        with torch.no_grad():
+            img = G(dd['z'], dd['c'], cm, noise_mode='const')
+            out_h.copy_((img[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8), non_blocking=True)
+
+    ms_e2e, _ = timed_region(step_e2e, args.steps, 1, world)
+    fg, _ = conv_flops_per_image(cfg)
+    peaks = measured_peaks()
+    R_ = cfg.dataset.resolution ** 2
+    alg = raymarch_algorithmic_bytes(B, R_, cfg.model.generator.num_ray_steps, 512, 32)
+    return dict(metric='G-only inference images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
+                dtype='fp32 (bf16x3 tensor-core convs, 3xTF32 tri-plane MLP)',
+                config=dict(workload='ginfer (BASELINE configs[4]: G-only inference, 256x256 full-frame render)', batch_per_gpu=B,
+                            rays_per_image=R_, l2='tri-planes of the batch (%.1f GB) larger than the 126 MB L2' % (B * 100.66e6 / 1e9),
+                            parallelism=f'replicas x{world} (no collective)'),
+                roofline=dict(bound='tensor', achieved=B * fg / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
+                              frac=B * fg / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'], traffic=None, kernel='conv_nhwc_bf16_kernel (whole forward)',
+                              peak_source=peaks['source'], note='decoder conv FLOPs (x1, not x3) of the batch / step time; ray-march bytes/launch = %d' % alg),
+                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(sum(host[k].numel() * host[k].element_size() for k in keys)),
+                         d2h_bytes_per_step=int(out_h.numel())),
+                gpu_launches=int(launches * args.steps), clocks=clocks)
+
+
 def cpu_train_step(small=False, budget_s=25.0):
     """Reference algorithm on the host cores (oracle port, torch-CPU / numpy, all threads) for the training-step metric.
     Bounded sample: ONE image through the generator forward (mapping + tri-plane decoder + ray-march at the training patch
@@ -361,7 +412,9 @@ def cpu_train_step(small=False, budget_s=25.0):
     passes (6)), i.e. images/s = 1 / (4 * tG + 8 * tD) -- an optimistic bound for the CPU since backward passes are costed at
     forward speed x2."""
     from oracle import ref_harness as rh, restated as R, shapes, cases
-    torch.set_num_threads(os.cpu_count())
+    threads = min(os.cpu_count(), 32)      # beyond ~32 threads ATen's CPU convs stop scaling on these hosts
+    torch.set_num_threads(threads)
+    R.FAST_FIR = True                      # FIR through grouped F.conv2d, as the reference's CPU path does
     kw = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if small else {}
     Gc, Dc, m = rh.make_cfg(**kw)
     gs, num_ws = shapes.generator_shapes(Gc)
@@ -401,7 +454,7 @@ def cpu_train_step(small=False, budget_s=25.0):
     R.discriminator(sdD, img, c4, torch.full((4, 2), 0.5), torch.full((4, 2), 0.25), dres, Dc['num_additional_start_blocks'], predict_feat=False)
     tD = (time.perf_counter() - t0) / 4
     val = 1.0 / (4 * tG + 8 * tD)
-    return dict(value=val, unit='images/s', cores=os.cpu_count(), kind='port',
+    return dict(value=val, unit='images/s', cores=threads, kind='port',
                 sample=f'G forward 1 image {tG:.2f} s + D forward 4 patches {4 * tD:.2f} s at the BASELINE widths; step = 4 G-forward-equivalents + 8 D-forward-equivalents per image')
 
 
@@ -447,7 +500,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl')
-    res = run_train_step(args, rank, world, local) if args.workload == 'train_step' else run_raymarch(args, rank, world, local)
+    res = {'train_step': run_train_step, 'raymarch': run_raymarch, 'ginfer': run_ginfer}[args.workload](args, rank, world, local)
     if rank == 0:
         line = dict(metric=res['metric'], value=res['value'], unit=res['unit'], n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
@@ -455,7 +508,8 @@ def main():
         if 'roofline_step_tensor' in res:
             line['roofline_step_tensor'] = res['roofline_step_tensor']
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)
+            if args.workload != 'ginfer':
+                line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -41,10 +41,39 @@ def _parse_scaling(s):
     return (s, s) if isinstance(s, int) else (int(s[0]), int(s[1]))
 
 
+FAST_FIR = False   # bench.py's CPU arm sets this: FIR through ATen's grouped conv2d exactly as the reference's own CPU path does
+
+
+def _upfirdn2d_aten(x, f, up, down, padding, flip_filter, gain):
+    """torch_utils/ops/upfirdn2d.py:167-211 evaluated the way the reference does on CPU: zero-stuff, pad, grouped F.conv2d, slice.
+    Multi-threaded; used only for CPU timing (tests/test_cpu_oracle.py checks it against the explicit restatement)."""
+    xt = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32)
+    N, C, H, W = xt.shape
+    upx, upy = _parse_scaling(up); downx, downy = _parse_scaling(down)
+    px0, px1, py0, py1 = _parse_padding(padding)
+    ft = torch.ones([1, 1]) if f is None else torch.as_tensor(np.ascontiguousarray(f), dtype=torch.float32)
+    xt = xt.reshape([N, C, H, 1, W, 1])
+    xt = F.pad(xt, [0, upx - 1, 0, 0, 0, upy - 1]).reshape([N, C, H * upy, W * upx])
+    xt = F.pad(xt, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    xt = xt[:, :, max(-py0, 0): xt.shape[2] - max(-py1, 0), max(-px0, 0): xt.shape[3] - max(-px1, 0)]
+    ft = ft * (gain ** (ft.ndim / 2))
+    if not flip_filter:
+        ft = ft.flip(list(range(ft.ndim)))
+    ft = ft[None, None].repeat([C, 1] + [1] * ft.ndim)
+    if ft.ndim == 4:
+        xt = F.conv2d(xt, ft, groups=C)
+    else:
+        xt = F.conv2d(xt, ft.unsqueeze(2), groups=C)
+        xt = F.conv2d(xt, ft.unsqueeze(3), groups=C)
+    return xt[:, :, ::downy, ::downx].numpy()
+
+
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
     """torch_utils/ops/upfirdn2d.py:167-211 (`_upfirdn2d_ref`) restated with explicit indexing in numpy float32:
     zero-insert upsample -> pad / crop -> FIR (true convolution unless flip_filter) -> decimate.
     Accumulation order: taps (ky, kx) ascending, float32, gain applied to the filter like the reference."""
+    if FAST_FIR:
+        return _upfirdn2d_aten(x, f, up, down, padding, flip_filter, gain)
     x = np.asarray(x, dtype=np.float32)
     assert x.ndim == 4
     N, C, H, W = x.shape

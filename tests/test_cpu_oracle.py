@@ -120,3 +120,16 @@ def test_oracle_repinned_against_live_reference():
     assert maxrel(R.upfirdn2d(x, f, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain']), y_ref) < TOL
     rep = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'oracle_pin_report.json')))
     assert max(rep.values()) < 2e-4 and len(rep) > 60
+
+
+def test_fast_fir_path_used_for_cpu_timing_matches_the_restatement():
+    name, kw = cases.upfirdn2d_cases()[5]
+    x, f = cases.upfirdn2d_inputs(name, kw)
+    a = R.upfirdn2d(x, f, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain'])
+    b = R._upfirdn2d_aten(x, f, kw['up'], kw['down'], kw['padding'], kw['flip_filter'], kw['gain'])
+    assert a.shape == b.shape and maxrel(a, b) < TOL
+    name, kw = cases.upfirdn2d_cases()[8]           # separable 61-tap blur
+    x, f = cases.upfirdn2d_inputs(name, kw)
+    a = R.upfirdn2d(x, f, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain'])
+    b = R._upfirdn2d_aten(x, f, kw['up'], kw['down'], kw['padding'], kw['flip_filter'], kw['gain'])
+    assert a.shape == b.shape and maxrel(a, b) < TOL
