@@ -19,7 +19,7 @@ constexpr int kConvThreads = 256;
 struct ConvGeom {
     int N, H, W, Cin, Cout;      // input tensor [N][H][W][Cin]; weights [Cout][num_slabs][Cin]
     int ntaps;                   // filter taps of THIS launch
-    int tdy[9], tdx[9], tslab[9];  // input offset (in input pixels) and weight slab of each tap
+    int tdy[25], tdx[25], tslab[25];  // input offset (in input pixels) and weight slab of each tap (up to 5x5)
     int in_stride;               // 1, or 2 for strided gathers (the tensor map carries matching elementStrides)
     int HoP, WoP;                // logical output grid of this launch (tile domain); pixel (iy, ix) reads input (iy*in_stride+tdy, ix*in_stride+tdx)
     int Hout, Wout;              // output tensor [N][Hout][Wout][Cout]; pixel (iy, ix) is stored at (iy*osy + oy0, ix*osx + ox0)
@@ -191,7 +191,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
     GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "%s: both low-order operands are required", who);
     GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && HoP > 0 && WoP > 0, "%s: empty tensor", who);
-    GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 9 && (in_stride == 1 || in_stride == 2), "%s: bad tap list / stride", who);
+    GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (in_stride == 1 || in_stride == 2), "%s: bad tap list / stride", who);
     if (Cin % 64 != 0 || !(Cout % 128 == 0 || Cout == 96 || Cout == 64)) {
         gp3d_set_error("%s: need Cin %% 64 == 0 and Cout %% 128 == 0 (or Cout in {64, 96}); got Cin=%d Cout=%d", who, Cin, Cout);
         return GP3D_E_UNSUPPORTED;
@@ -252,8 +252,8 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
 
 static int conv_same(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
                      int ksize, int accumulate, void* stream, const char* who) {
-    GP3D_CHECK_ARG(ksize == 1 || ksize == 3, "%s: kernel size must be 1 or 3 (got %d)", who, ksize);
-    int taps[27]; int nt = 0;
+    GP3D_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5, "%s: kernel size must be 1, 3 or 5 (got %d)", who, ksize);
+    int taps[75]; int nt = 0;
     for (int ky = 0; ky < ksize; ky++) for (int kx = 0; kx < ksize; kx++) { taps[3 * nt] = ky - ksize / 2; taps[3 * nt + 1] = kx - ksize / 2; taps[3 * nt + 2] = ky * ksize + kx; nt++; }
     return conv_impl(x, xl, w, wl, y, N, H, W, Cin, Cout, ksize * ksize, nt, taps, 1, H, W, H, W, 1, 1, 0, 0, accumulate, stream, who);
 }

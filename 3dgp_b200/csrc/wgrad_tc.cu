@@ -19,7 +19,7 @@ constexpr int kWgradThreads = 256;
 struct WgradGeom {
     int N, Cin, Cout, num_slabs;
     int ntaps;
-    int ay[9], ax[9], by[9], bx[9], slab[9];
+    int ay[25], ax[25], by[25], bx[25], slab[25];
     int sa, sb;                 // traversal strides of the dy / x tensor maps
     int HoP, WoP;               // pixel domain
     int TW, TH, TN, tiles_x, tiles_y, tiles_n;
@@ -142,8 +142,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
 #pragma unroll 1
             for (int c = 0; c < WBN; c += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
                 tmem_ld_wait();
+                if (co >= g.Cout || tci * WBN + c >= g.Cin) continue;                       // half-empty tiles of 64-channel tensors
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     red_add_v4f(row + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -178,10 +179,10 @@ extern "C" int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void
     const char* who = "wgrad_taps_nhwc";
     GP3D_CHECK_ARG(dyh && xh && dW && h_taps, "%s: null pointer", who);
     GP3D_CHECK_ARG((dyl == nullptr) == (xl == nullptr), "%s: both low-order operands are required", who);
-    GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 9 && (sa == 1 || sa == 2) && (sb == 1 || sb == 2), "%s: bad tap list / strides", who);
+    GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (sa == 1 || sa == 2) && (sb == 1 || sb == 2), "%s: bad tap list / strides", who);
     GP3D_CHECK_ARG(N > 0 && HoP > 0 && WoP > 0, "%s: empty domain", who);
-    if (Cin % 128 != 0 || Cout % 128 != 0) {
-        gp3d_set_error("%s: need Cin %% 128 == 0 and Cout %% 128 == 0 (got Cin=%d Cout=%d)", who, Cin, Cout);
+    if (Cin % 64 != 0 || Cout % 64 != 0) {      // 64-channel tensors use half of a 128-wide tile: the missing block is TMA zero fill
+        gp3d_set_error("%s: need Cin %% 64 == 0 and Cout %% 64 == 0 (got Cin=%d Cout=%d)", who, Cin, Cout);
         return GP3D_E_UNSUPPORTED;
     }
     tc::WgradGeom g{};
@@ -194,7 +195,7 @@ extern "C" int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void
     g.TH = wg_pow2ceil(HoP) < (64 / g.TW) ? wg_pow2ceil(HoP) : (64 / g.TW);
     g.TN = 64 / (g.TW * g.TH);
     g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN;
-    g.tiles_co = Cout / 128; g.tiles_ci = Cin / 128;
+    g.tiles_co = (Cout + 127) / 128; g.tiles_ci = (Cin + 127) / 128;
     const int64_t ptiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
     const int out_tiles = g.tiles_co * g.tiles_ci * ntaps;
     int sms = GP3D_NUM_SMS, dev = 0;

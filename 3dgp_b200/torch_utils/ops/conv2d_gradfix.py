@@ -149,7 +149,7 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
             k = weight_shape[2]
             cin_op = input.shape[1]
             cout_op = grad_output.shape[1]
-            use_tc = (tc_enabled and groups == 1 and tuple(dilation) == (1, 1) and weight_shape[2] == weight_shape[3] and k in (1, 3)
+            use_tc = (tc_enabled and groups == 1 and tuple(dilation) == (1, 1) and weight_shape[2] == weight_shape[3] and k in (1, 3, 5)
                       and input.dtype in (torch.float32, torch.float16) and tc.wgrad_eligible(cin_op, cout_op)
                       and ((not transpose and ((tuple(stride) == (1, 1) and tuple(padding) == (k // 2, k // 2)) or (tuple(stride) == (2, 2) and k == 3 and padding[0] == padding[1])))
                            or (transpose and tuple(stride) == (2, 2) and tuple(padding) == (0, 0) and k == 3)))

@@ -67,7 +67,7 @@ def channels_eligible(Cin, Cout):
 
 def conv_eligible(N, Cin, H, W, Cout, k, stride, padding, dilation, groups):
     """Stride-1 'same' shapes the tcgen05 implicit-GEMM conv covers (csrc/conv_tc.cu)."""
-    if groups != 1 or tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or k not in (1, 3) or tuple(padding) != (k // 2, k // 2):
+    if groups != 1 or tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or k not in (1, 3, 5) or tuple(padding) != (k // 2, k // 2):
         return False
     return channels_eligible(Cin, Cout)
 
@@ -143,7 +143,7 @@ def conv_transpose2d_s2_forward(x, w, output_padding, terms):
 
 
 def wgrad_eligible(Cin, Cout):
-    return Cin % 128 == 0 and Cout % 128 == 0
+    return Cin % 64 == 0 and Cout % 64 == 0
 
 
 def conv_wgrad(dy, x, k, mode, stride, padding, terms):

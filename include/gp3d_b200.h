@@ -178,8 +178,8 @@ int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, float posinf, f
 int gp3d_gemm_bf16_tn(const void* A, const void* B, float* D, int M, int N, int K, int accumulate, void* stream);
 
 /* 3x3 / 1x1 stride-1 "same" convolution as an implicit GEMM on tcgen05 (NHWC bf16 activations,
- * weights [Cout][kh][kw][Cin] bf16, fp32 NHWC output).  Replaces the cuDNN call of
- * conv2d_gradfix.py:113 for the hot shapes.  Cin % 64 == 0, Cout % 128 == 0, W % 8 == 0.
+ * weights [Cout][kh][kw][Cin] bf16, fp32 NHWC output; ksize in {1, 3, 5}).  Replaces the cuDNN call of
+ * conv2d_gradfix.py:113 for the hot shapes.  Cin % 64 == 0, Cout % 128 == 0 (or Cout in {64, 96}); any N, H, W.
  */
 int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
                           int ksize, int accumulate, void* stream);
@@ -207,7 +207,7 @@ int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const vo
  * conv2d_gradfix.py:141-151):
  *   dW[co][slab_t][ci] += sum_{n,iy,ix} dy[n][iy*sa+ay_t][ix*sa+ax_t][co] * x[n][iy*sb+by_t][ix*sb+bx_t][ci],  (iy,ix) in [0,HoP)x[0,WoP)
  * dy [N][Hd][Wd][Cout], x [N][Hx][Wx][Cin] bf16 NHWC (hi, optional lo pair for bf16x3); h_taps: HOST array ntaps x (ay, ax, by, bx, slab);
- * dW float32 [Cout][num_slabs][Cin], ACCUMULATED (caller zero-fills).  Cin % 128 == 0, Cout % 128 == 0.
+ * dW float32 [Cout][num_slabs][Cin], ACCUMULATED (caller zero-fills).  Cin % 64 == 0, Cout % 64 == 0; up to 25 taps.
  */
 int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const void* xl, float* dW,
                          int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,

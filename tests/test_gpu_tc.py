@@ -204,3 +204,25 @@ def test_fused_torgb_matches_unfused():
     assert rel(out[0][0], out[1][0]) < 1e-4
     for a, b in zip(out[0][1], out[1][1]):
         assert rel(a, b) < 3e-4
+
+
+def test_conv5x5_depth_adaptor_shape_forward_and_input_gradient():
+    """5x5 'same' convs of the depth adaptor (networks_depth_adaptor.py:31-33: 64 -> 64 channels at the patch resolution)."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn(4, 64, 64, 64, device='cuda', generator=g).requires_grad_(True)
+    w = (torch.randn(64, 64, 5, 5, device='cuda', generator=g) / 40).requires_grad_(True)
+    dy = torch.randn(4, 64, 64, 64, device='cuda', generator=g)
+    outs = []
+    for en in (True, False):
+        cg.tc_enabled = en
+        n0 = cg.tc_stats['tc']
+        y = cg.conv2d(x, w, padding=2)
+        gx, gw = torch.autograd.grad(y, [x, w], dy)
+        outs.append((y, gx, gw, cg.tc_stats['tc'] - n0))
+    cg.tc_enabled = True
+    assert outs[0][3] >= 2
+    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
+    for i in range(3):
+        assert rel(outs[0][i], outs[1][i]) < 1e-4
