@@ -151,6 +151,61 @@ __global__ void __launch_bounds__(256) upfirdn2d_cminor_kernel(UpfirdnParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// C-minor register-tiled kernel for the 4x4 [1,3,3,1] cases that dominate G and D (fp32): each thread produces PX consecutive
+// output pixels of one row for one 16-byte channel vector, loading every needed input vector ONCE (7 x 4 loads for 4 outputs of the
+// up=1 FIR instead of 64).  Grid: (x-groups, 1, N*outH); threads: channel vector fastest -> 512 contiguous bytes per warp and pixel.
+template <int UP, int DOWN, int PX>
+__global__ void __launch_bounds__(256) upfirdn2d_cminor4_kernel(UpfirdnParams p) {
+    constexpr int FS = 4;
+    constexpr int NIX = ((PX - 1) * DOWN + FS - 1) / UP + 2;       // input columns that can touch PX outputs
+    __shared__ float sf[FS * FS];
+    stage_filter(sf, p);
+    const int CV = p.C / 4;
+    const int cv_per = CV < 256 ? CV : 256;
+    const int groups = 256 / cv_per;                                 // x-groups per block
+    const int cvl = threadIdx.x % cv_per, xg = threadIdx.x / cv_per;
+    const int n = blockIdx.z / p.outH, oy = blockIdx.z - n * p.outH;
+    const int ox0 = (blockIdx.x * groups + xg) * PX;
+    if (xg >= groups || ox0 >= p.outW) return;
+    const int by = oy * DOWN - p.pady0;
+    int iy0 = ceil_div_s(by, UP); if (iy0 < 0) iy0 = 0;
+    int iy1 = floor_div(by + FS - 1, UP); if (iy1 > p.inH - 1) iy1 = p.inH - 1;
+    const int bx0 = ox0 * DOWN - p.padx0;
+    const int ixb = ceil_div_s(bx0, UP);                             // first input column that can contribute to output ox0
+    for (int cv = cvl; cv < CV; cv += cv_per) {
+        const float* xb = (const float*)p.x + (int64_t)n * p.xsN + 4 * cv;
+        float4 acc[PX];
+#pragma unroll
+        for (int j = 0; j < PX; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int iy = iy0; iy <= iy1; iy++) {
+            const float* fr = sf + (iy * UP - by) * FS;
+            const float* xr = xb + (int64_t)iy * p.xsH;
+#pragma unroll
+            for (int t = 0; t < NIX; t++) {
+                const int ix = ixb + t;
+                if (ix < 0 || ix >= p.inW) continue;
+                const float4 v = *reinterpret_cast<const float4*>(xr + (int64_t)ix * p.xsW);
+#pragma unroll
+                for (int j = 0; j < PX; j++) {
+                    const int kx = ix * UP - (bx0 + j * DOWN);
+                    if (kx >= 0 && kx < FS) {
+                        const float w = fr[kx];
+                        acc[j].x = fmaf(v.x, w, acc[j].x); acc[j].y = fmaf(v.y, w, acc[j].y);
+                        acc[j].z = fmaf(v.z, w, acc[j].z); acc[j].w = fmaf(v.w, w, acc[j].w);
+                    }
+                }
+            }
+        }
+        float* yo = (float*)p.y + (int64_t)n * p.ysN + (int64_t)oy * p.ysH + 4 * cv;
+#pragma unroll
+        for (int j = 0; j < PX; j++)
+            if (ox0 + j < p.outW)
+                *reinterpret_cast<float4*>(yo + (int64_t)(ox0 + j) * p.ysW) =
+                    make_float4(acc[j].x * p.gain, acc[j].y * p.gain, acc[j].z * p.gain, acc[j].w * p.gain);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Any-stride scalar fallback: one output element per thread.
 template <class T>
 __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p) {
@@ -186,6 +241,16 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
     const bool cminor = (p.xsC == 1 && p.ysC == 1 && p.C % VEC == 0 && gp3d_aligned16(p.x) && gp3d_aligned16(p.y) &&
                          p.xsW % VEC == 0 && p.xsH % VEC == 0 && p.xsN % VEC == 0 &&
                          p.ysW % VEC == 0 && p.ysH % VEC == 0 && p.ysN % VEC == 0);
+    if (cminor && !(wminor && p.C == 1) && sizeof(T) == 4 && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
+        ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2)) && (int64_t)p.N * p.outH <= 65535) {
+        constexpr int PX = 4;
+        const int CV = p.C / 4, cv_per = CV < 256 ? CV : 256, groups = 256 / cv_per;
+        dim3 grid((p.outW + groups * PX - 1) / (groups * PX), 1, p.N * p.outH);
+        if (p.upx == 1 && p.downx == 1) upfirdn2d_cminor4_kernel<1, 1, PX><<<grid, 256, 0, s>>>(p);
+        else if (p.upx == 2) upfirdn2d_cminor4_kernel<2, 1, PX><<<grid, 256, 0, s>>>(p);
+        else upfirdn2d_cminor4_kernel<1, 2, PX><<<grid, 256, 0, s>>>(p);
+        return 0;
+    }
     if (cminor && !(wminor && p.C == 1)) {
         int64_t total = (int64_t)p.N * p.outH * p.outW * (p.C / VEC);
         upfirdn2d_cminor_kernel<T><<<gp3d_grid_for(total, 256, 8), 256, 0, s>>>(p);

@@ -142,3 +142,21 @@ def test_filtered_lrelu_vs_golden(golden, name, kw):
     gx, gb = torch.autograd.grad(y, [xt, bt], dy)
     assert maxrel(gx.cpu().numpy(), g[name + '/dx']) < 5e-5
     assert maxrel(gb.cpu().numpy(), g[name + '/db']) < 5e-5
+
+
+@pytest.mark.parametrize('kw', [dict(up=1, down=1, padding=[1, 1, 1, 1], gain=4), dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4),
+                                dict(up=1, down=2, padding=[1, 1, 1, 1], gain=1), dict(up=1, down=1, padding=[2, 2, 2, 2], gain=1),
+                                dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4, flip_filter=True)])
+@pytest.mark.parametrize('shape', [(2, 8, 13, 11), (1, 96, 16, 16), (3, 128, 9, 33), (1, 1024, 4, 4)])
+def test_upfirdn2d_register_tiled_channels_last_kernel(kw, shape):
+    """The C-minor 4x4 kernel (4 output pixels per thread) must reproduce the W-minor kernel bit for bit (same tap order) and the oracle."""
+    _, up, _ = _ops()
+    rs = np.random.RandomState(sum(shape))
+    x = rs.standard_normal(shape).astype(np.float32)
+    f = cases._f2d(cases.F1331)
+    y_nchw = up.upfirdn2d(cu(x), cu(f), **kw)
+    y_cl = up.upfirdn2d(cu(x).contiguous(memory_format=torch.channels_last), cu(f), **kw)
+    assert y_cl.shape == y_nchw.shape
+    assert torch.equal(y_cl.contiguous(), y_nchw)
+    yo = R.upfirdn2d(x, f, **kw)
+    assert maxrel(y_nchw.cpu().numpy(), yo) < TOL

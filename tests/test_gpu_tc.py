@@ -207,22 +207,21 @@ def test_fused_torgb_matches_unfused():
 
 
 def test_conv5x5_depth_adaptor_shape_forward_and_input_gradient():
-    """5x5 'same' convs of the depth adaptor (networks_depth_adaptor.py:31-33: 64 -> 64 channels at the patch resolution)."""
+    """5x5 'same' convs of the depth adaptor (networks_depth_adaptor.py:31-33: 64 -> 64 channels at the patch resolution), forward,
+    input gradient and weight gradient on the tcgen05 path.  Checked against a float64 CPU convolution: cuDNN's own fp32 5x5 kernel
+    for this shape is only accurate to ~1e-2 on B200 (measured, tools/debug_conv5.py), so it cannot serve as the comparator."""
     cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
-    torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device='cuda').manual_seed(11)
     x = torch.randn(4, 64, 64, 64, device='cuda', generator=g).requires_grad_(True)
     w = (torch.randn(64, 64, 5, 5, device='cuda', generator=g) / 40).requires_grad_(True)
     dy = torch.randn(4, 64, 64, 64, device='cuda', generator=g)
-    outs = []
-    for en in (True, False):
-        cg.tc_enabled = en
-        n0 = cg.tc_stats['tc']
-        y = cg.conv2d(x, w, padding=2)
-        gx, gw = torch.autograd.grad(y, [x, w], dy)
-        outs.append((y, gx, gw, cg.tc_stats['tc'] - n0))
     cg.tc_enabled = True
-    assert outs[0][3] >= 2
-    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
-    for i in range(3):
-        assert rel(outs[0][i], outs[1][i]) < 1e-4
+    n0 = cg.tc_stats['tc']
+    y = cg.conv2d(x, w, padding=2)
+    gx, gw = torch.autograd.grad(y, [x, w], dy)
+    assert cg.tc_stats['tc'] - n0 >= 3          # forward, input gradient and weight gradient all on the tensor-core path
+    xd = x.detach().double().cpu().requires_grad_(True); wd = w.detach().double().cpu().requires_grad_(True)
+    yd = torch.nn.functional.conv2d(xd, wd, padding=2)
+    gxd, gwd = torch.autograd.grad(yd, [xd, wd], dy.double().cpu())
+    rel = lambda a, b: ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
+    assert rel(y, yd.detach()) < 5e-5 and rel(gx, gxd) < 5e-5 and rel(gw, gwd) < 5e-5, (rel(y, yd.detach()), rel(gx, gxd), rel(gw, gwd))
