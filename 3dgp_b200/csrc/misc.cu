@@ -173,30 +173,36 @@ __global__ void __launch_bounds__(256) grad_epilogue_kernel(float* g, int64_t nu
 // hi = bf16(x * s), lo = bf16(x * s - hi); channel-minor tensors, 8 channels per thread
 template <class T>
 __global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
-                                                         __nv_bfloat16* __restrict__ lo, int N, int HW, int C) {
-    const int64_t nvec = (int64_t)N * HW * C / 8;
+                                                         __nv_bfloat16* __restrict__ lo, int N, int HW, int C, int Cp) {
+    // Cp >= C: channel count of the outputs (zero-padded tail so that 96-channel tensors fill whole 64-channel TMA blocks)
+    const int64_t nvec = (int64_t)N * HW * Cp / 8;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i0 = v * 8;
+        const int64_t o0 = v * 8;                       // output element index
+        const int64_t pix = o0 / Cp;
+        const int c0 = (int)(o0 - pix * Cp);
+        const int64_t i0 = pix * C + c0;                // input element index
         float f[8];
-        if (sizeof(T) == 4) {
-            const float4 a = reinterpret_cast<const float4*>(x)[2 * v], b = reinterpret_cast<const float4*>(x)[2 * v + 1];
+        if (c0 >= C) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[k] = 0.f;
+        } else if (sizeof(T) == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i0), b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i0 + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
         } else {
             vec16<__half> t; t.load(reinterpret_cast<const __half*>(x) + i0); t.unpack(f);
         }
-        if (s) {
-            const int c0 = (int)(i0 % C);
-            const int n = (int)(i0 / ((int64_t)HW * C));
+        if (s && c0 < C) {
+            const int n = (int)(pix / HW);
             const float4 sa = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0), sb = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0 + 4);
             f[0] *= sa.x; f[1] *= sa.y; f[2] *= sa.z; f[3] *= sa.w; f[4] *= sb.x; f[5] *= sb.y; f[6] *= sb.z; f[7] *= sb.w;
         }
         float r[8];
-        vec16<__nv_bfloat16> h; h.pack(f); h.store(hi + i0);
+        vec16<__nv_bfloat16> h; h.pack(f); h.store(hi + o0);
         if (lo) {
             float hf[8]; h.unpack(hf);
 #pragma unroll
             for (int k = 0; k < 8; k++) r[k] = f[k] - hf[k];
-            vec16<__nv_bfloat16> l; l.pack(r); l.store(lo + i0);
+            vec16<__nv_bfloat16> l; l.pack(r); l.store(lo + o0);
         }
     }
 }
@@ -276,17 +282,21 @@ extern "C" int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, floa
     GP3D_RETURN_LAUNCH();
 }
 
-extern "C" int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream) {
+extern "C" int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream) {
     GP3D_CHECK_ARG(x && hi && N >= 1 && HW >= 1 && C >= 1, "split_bf16: bad arguments");
-    GP3D_CHECK_ARG(C % 8 == 0, "split_bf16: channel count must be a multiple of 8 (got %d)", C);
+    GP3D_CHECK_ARG(C % 8 == 0 && C_out % 8 == 0 && C_out >= C, "split_bf16: channel counts must be multiples of 8 with C_out >= C (got %d -> %d)", C, C_out);
     GP3D_CHECK_ARG(gp3d_aligned16(x) && gp3d_aligned16(hi) && (!lo || gp3d_aligned16(lo)) && (!s || gp3d_aligned16(s)), "split_bf16: pointers must be 16-byte aligned");
-    const int64_t nvec = (int64_t)N * HW * C / 8;
+    const int64_t nvec = (int64_t)N * HW * C_out / 8;
     const int grid = gp3d_grid_for(nvec, 256, 8);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C);
-    else if (src_dtype == GP3D_F16) split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C);
+    if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
+    else if (src_dtype == GP3D_F16) split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     else { gp3d_set_error("split_bf16: source must be float32 or float16"); return GP3D_E_BADARG; }
     GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream) {
+    return gp3d_split_bf16_pad(x, src_dtype, s, hi, lo, N, HW, C, C, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------

@@ -56,8 +56,7 @@ class _ModConvLayer(torch.autograd.Function):
         xn = _nhwc(x)
         st = styles.to(torch.float32).contiguous()
         xh, xl = tc.split_bf16(xn, styles=st)
-        wn = weight.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous()
-        wh, wl = tc.split_bf16(wn)
+        wh, wl = tc.weight_operands(weight, 'fwd', lambda w_: w_.permute(0, 2, 3, 1))
         c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
         if up == 2:   # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
             c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
@@ -104,27 +103,23 @@ class _ModConvLayer(torch.autograd.Function):
             g_ns = g_ns.reshape(noise_strength.shape)
         if up == 2:   # adjoint of the FIR (upfirdn2d.py:250-269): same filter, flipped, padding p = fw - pad - 1 = 2
             dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
-        dch, dcl = tc.split_bf16(dc)
+        # channels of the gradient operand are zero-padded to whole 64-channel TMA blocks (toRGB: 96 -> 128)
+        Cp = ((Cout + 63) // 64) * 64
+        dch, dcl = tc.split_bf16(dc, pad_to=Cp)
         # input gradient
-        w32 = weight.detach().to(torch.float32)
         dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
-        if tc.channels_eligible(Cout, Cin):
-            if up == 1:
-                wd = w32.flip([2, 3]).permute(1, 2, 3, 0).contiguous()               # [Cin,k,k,Cout]
-                wdh, wdl = tc.split_bf16(wd)
-                with torch.cuda.device(dev):
-                    rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
-                _lib.check(rc, 'conv2d_nhwc_bf16x3')
-            else:   # dx[i,j] = sum dc1[2i+ky, 2j+kx] w[co][ci][ky][kx]: strided gather over the (2H+1)^2 gradient
-                wd = w32.permute(1, 2, 3, 0).contiguous()                              # [Cin,ky,kx,Cout]
-                wdh, wdl = tc.split_bf16(wd)
-                taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
-                tc._taps_launch(dch, dcl, wdh, wdl, dxs, N, 2 * H + 1, 2 * W + 1, Cout, Cin, 9, taps, 2, H, W, H, W, 1, 1, 0, 0)
-        else:       # e.g. toRGB (Cout = 96): tiny 1x1 contraction, ATen
-            assert up == 1
-            dxs = torch.nn.functional.conv2d(dc.permute(0, 3, 1, 2), w32.flip([2, 3]).transpose(0, 1), padding=k // 2).permute(0, 2, 3, 1).contiguous()
+        assert tc.channels_eligible(Cp, Cin)
+        if up == 1:
+            wdh, wdl = tc.weight_operands(weight, 'dgrad1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), pad_to=Cp)    # [Cin,k,k,Cout(+pad)]
+            with torch.cuda.device(dev):
+                rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cp, Cin, k, 0, _lib.stream_ptr())
+            _lib.check(rc, 'conv2d_nhwc_bf16x3')
+        else:   # dx[i,j] = sum dc1[2i+ky, 2j+kx] w[co][ci][ky][kx]: strided gather over the (2H+1)^2 gradient
+            wdh, wdl = tc.weight_operands(weight, 'dgrad2', lambda w_: w_.permute(1, 2, 3, 0), pad_to=Cp)                 # [Cin,ky,kx,Cout]
+            taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+            tc._taps_launch(dch, dcl, wdh, wdl, dxs, N, 2 * H + 1, 2 * W + 1, Cp, Cin, 9, taps, 2, H, W, H, W, 1, 1, 0, 0)
         # weight gradient
-        if tc.wgrad_eligible(Cin, Cout):
+        if tc.wgrad_eligible(Cin, Cp):
             import ctypes
             if up == 1:
                 taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
@@ -132,18 +127,15 @@ class _ModConvLayer(torch.autograd.Function):
             else:
                 taps = [(ky, kx, 0, 0, ky * 3 + kx) for ky in range(3) for kx in range(3)]
                 sa, sb, HoP, WoP, Hd, Wd = 2, 1, H, W, 2 * H + 1, 2 * W + 1
-            gw = torch.zeros([Cout, k * k, Cin], dtype=torch.float32, device=dev)
+            gw = torch.zeros([Cp, k * k, Cin], dtype=torch.float32, device=dev)
             arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
             with torch.cuda.device(dev):
-                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), dcl.data_ptr(), xh.data_ptr(), xl.data_ptr(), gw.data_ptr(), N, Hd, Wd, Cout, H, W, Cin, k * k,
+                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), dcl.data_ptr(), xh.data_ptr(), xl.data_ptr(), gw.data_ptr(), N, Hd, Wd, Cp, H, W, Cin, k * k,
                                             len(taps), ctypes.cast(arr, ctypes.c_void_p), sa, sb, HoP, WoP, _lib.stream_ptr())
             _lib.check(rc, 'wgrad_taps_nhwc')
-            gw = gw.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+            gw = gw[:Cout].view(Cout, k, k, Cin).permute(0, 3, 1, 2)
         else:
-            assert up == 1
-            xs = (xh.float() + xl.float()).permute(0, 3, 1, 2)
-            gw = torch.ops.aten.convolution_backward(dc.permute(0, 3, 1, 2), xs, w32, bias_sizes=None, stride=[1, 1], padding=[k // 2, k // 2], dilation=[1, 1],
-                                                     transposed=False, output_padding=[0, 0], groups=1, output_mask=[False, True, False])[1]
+            raise RuntimeError('modconv: weight-gradient shape not covered by the tensor-core kernel (Cin %% 64 != 0)')
         # through the modulation
         dx = torch.empty_like(dxs)
         g_s = torch.zeros_like(st)

@@ -45,20 +45,40 @@ def conv2d_nhwc_bf16(x, w, out=None, accumulate=False):
     return out
 
 
-def split_bf16(x_nhwc, styles=None, want_lo=True):
+def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None):
     """x [N, ..., C] channel-minor contiguous (float32 / float16) -> (hi, lo) bfloat16 with x * styles == hi + lo up to 2^-16.
-    styles: optional float32 [N, C] per-sample channel scale fused into the split."""
+    styles: optional float32 [N, C] per-sample channel scale fused into the split.  pad_to: output channel count (zero tail)."""
     L = _lib.lib()
     _lib.require_cuda(x_nhwc, 'x')
     assert x_nhwc.is_contiguous()
     N = x_nhwc.shape[0]; C = x_nhwc.shape[-1]
+    Cp = C if pad_to is None else int(pad_to)
     HW = x_nhwc.numel() // (N * C)
-    hi = torch.empty_like(x_nhwc, dtype=torch.bfloat16)
+    hi = torch.empty(list(x_nhwc.shape[:-1]) + [Cp], dtype=torch.bfloat16, device=x_nhwc.device)
     lo = torch.empty_like(hi) if want_lo else None
     with torch.cuda.device(x_nhwc.device):
-        rc = L.gp3d_split_bf16(x_nhwc.data_ptr(), _lib.dtype_code(x_nhwc), _lib.ptr(styles), hi.data_ptr(), _lib.ptr(lo), N, HW, C, _lib.stream_ptr())
+        rc = L.gp3d_split_bf16_pad(x_nhwc.data_ptr(), _lib.dtype_code(x_nhwc), _lib.ptr(styles), hi.data_ptr(), _lib.ptr(lo), N, HW, C, Cp, _lib.stream_ptr())
     _lib.check(rc, 'split_bf16')
     return hi, lo
+
+
+_weight_cache = {}
+
+
+def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
+    """bf16 (hi, lo) operand pair of a weight tensor in the layout `make_nhwc(weight)` produces ([rows][taps][cols], cols contiguous).
+    Parameters are re-laid-out and split ONCE per optimiser step: the cache is keyed by (id, tag) and invalidated by the tensor's
+    autograd version counter (bumped by every in-place update)."""
+    key = (id(weight), tag, terms, pad_to)
+    ver = (weight._version, weight.data_ptr(), tuple(weight.shape))
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    wn = make_nhwc(weight.detach().to(torch.float32)).contiguous()
+    wh, wl = split_bf16(wn, want_lo=(terms == 3), pad_to=pad_to)
+    if isinstance(weight, torch.nn.Parameter):
+        _weight_cache[key] = (ver, wh, wl)
+    return wh, wl
 
 
 def channels_eligible(Cin, Cout):

@@ -20,9 +20,12 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
         weight = weight * (1 / np.sqrt(ic * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
         styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
     w = dcoefs = None
-    if demodulate or fused_modconv:
+    if fused_modconv:
         w = weight.unsqueeze(0) * styles.reshape(B, 1, -1, 1, 1)
-    if demodulate:
+    if demodulate and not fused_modconv:
+        # sum_{i,k} (w[o,i,k] s[n,i])^2 as a [B,Cin] x [Cin,Cout] product of squares: same value, no [B,Cout,Cin,k,k] temporary
+        dcoefs = (styles.square() @ weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    elif demodulate:
         dcoefs = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()
     if demodulate and fused_modconv:
         w = w * dcoefs.reshape(B, -1, 1, 1, 1)
@@ -73,7 +76,7 @@ class SynthesisLayer(torch.nn.Module):
             noise = noise_in * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        if (fused_layer_enabled and self.activation == 'lrelu' and modconv.eligible(x, self.weight, self.up, self.conv_clamp) and x.shape[2] >= 8):
+        if (fused_layer_enabled and self.activation == 'lrelu' and modconv.eligible(x, self.weight, self.up, self.conv_clamp)):
             # fp32 CUDA path (training AND inference: scaling activations (:67-76) and scaling weights (:78-88) are the same map, Appendix A): x*styles -> conv(+FIR) -> *dcoefs + noise + bias -> lrelu*gain as one autograd node.
             # dcoefs = rsqrt(sum_{i,k} (w[o,i,k] s[n,i])^2 + 1e-8) (:62) evaluated as a [B,Cin] x [Cin,Cout] product of squares.
             dcoefs = (styles.square() @ self.weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
@@ -102,7 +105,7 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        if fused_layer_enabled and modconv.eligible(x, self.weight, 1, self.conv_clamp) and x.shape[2] >= 8:
+        if fused_layer_enabled and modconv.eligible(x, self.weight, 1, self.conv_clamp):
             return modconv.modconv_layer(x, self.weight, styles, bias=self.bias, up=1, act='linear', gain=1.0)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
@@ -150,7 +153,9 @@ class SynthesisBlock(torch.nn.Module):
         if self.in_channels == 0:
             x = self.const.to(dtype=dtype, memory_format=mf).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
         else:
-            x = x.to(dtype=dtype, memory_format=mf)
+            # keep whatever layout the previous block produced (channel-minor on the tensor-core path): a forced
+            # memory_format=contiguous here costs one full-tensor copy per block and another one back inside the next conv
+            x = x.to(dtype=dtype, memory_format=torch.channels_last) if self.channels_last and not force_fp32 else x.to(dtype=dtype)
         if self.in_channels == 0:
             x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, noise_in=nxt(), **layer_kwargs)
         elif self.architecture == 'resnet':

@@ -217,6 +217,8 @@ int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const
  * (NHWC) tensors: hi = bf16(x * s[n][c]); lo = bf16(x * s[n][c] - hi) (lo may be NULL).  s may be NULL.  src_dtype: GP3D_F32 / F16.
  */
 int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream);
+/* same, with the outputs zero-padded to C_out >= C channels (96-channel toRGB tensors -> 128 so that they fill whole 64-channel TMA blocks) */
+int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream);
 
 #ifdef __cplusplus
 }

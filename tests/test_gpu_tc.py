@@ -225,3 +225,58 @@ def test_conv5x5_depth_adaptor_shape_forward_and_input_gradient():
     gxd, gwd = torch.autograd.grad(yd, [xd, wd], dy.double().cpu())
     rel = lambda a, b: ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
     assert rel(y, yd.detach()) < 5e-5 and rel(gx, gxd) < 5e-5 and rel(gw, gwd) < 5e-5, (rel(y, yd.detach()), rel(gx, gxd), rel(gw, gwd))
+
+
+def test_split_bf16_zero_pads_the_channel_tail():
+    tc = _tc()
+    torch.manual_seed(0)
+    x = torch.randn(3, 5, 7, 96, device='cuda')
+    s = torch.rand(3, 96, device='cuda') + 0.5
+    hi, lo = tc.split_bf16(x, styles=s, pad_to=128)
+    assert hi.shape == (3, 5, 7, 128) and lo.shape == hi.shape
+    assert (hi[..., 96:] == 0).all() and (lo[..., 96:] == 0).all()
+    ref = x * s[:, None, None, :]
+    got = hi[..., :96].float() + lo[..., :96].float()
+    assert (got - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -15
+    h2, l2 = tc.split_bf16(x, styles=s)
+    assert torch.equal(h2, hi[..., :96]) and torch.equal(l2, lo[..., :96])
+
+
+def test_weight_operand_cache_follows_in_place_updates():
+    tc = _tc()
+    w = torch.nn.Parameter(torch.randn(128, 64, 3, 3, device='cuda'))
+    a = tc.weight_operands(w, 'fwd', lambda t: t.permute(0, 2, 3, 1))
+    b = tc.weight_operands(w, 'fwd', lambda t: t.permute(0, 2, 3, 1))
+    assert a[0] is b[0] and a[1] is b[1]                                   # one split per optimiser step
+    with torch.no_grad():
+        w.mul_(2.0)                                                         # what an optimiser does
+    c = tc.weight_operands(w, 'fwd', lambda t: t.permute(0, 2, 3, 1))
+    assert c[0] is not a[0]
+    assert torch.equal(c[0].float(), a[0].float() * 2)
+    t = torch.randn(128, 64, 3, 3, device='cuda')                           # temporaries are never cached
+    assert tc.weight_operands(t, 'fwd', lambda u: u.permute(0, 2, 3, 1))[0] is not tc.weight_operands(t, 'fwd', lambda u: u.permute(0, 2, 3, 1))[0]
+
+
+@pytest.mark.parametrize('res,up', [(4, 1), (8, 2)])
+def test_fused_modconv_layer_at_the_coarsest_resolutions(res, up):
+    """b4.conv1 (4x4) and b8.conv0 (4x4 -> 8x8) run the same fused node as the large layers."""
+    sg = importlib.import_module('3dgp_b200.training.networks_stylegan2')
+    torch.manual_seed(5)
+    layer = sg.SynthesisLayer(128, 128, w_dim=64, resolution=res, up=up, conv_clamp=None).cuda()
+    with torch.no_grad():
+        layer.noise_strength.fill_(0.2)
+    B = 5
+    x = torch.randn(B, 128, res // up, res // up, device='cuda', requires_grad=True)
+    w = torch.randn(B, 64, device='cuda', requires_grad=True)
+    nz = torch.randn(B, 1, res, res, device='cuda')
+    dy = torch.randn(B, 128, res, res, device='cuda')
+    out = []
+    for fused in (True, False):
+        sg.fused_layer_enabled = fused
+        y = layer(x, w, noise_mode='random', fused_modconv=False, noise_in=nz)
+        out.append((y, torch.autograd.grad(y, [x, w, layer.weight, layer.bias, layer.noise_strength], dy)))
+    sg.fused_layer_enabled = True
+    rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+    assert rel(out[0][0], out[1][0]) < 1e-4
+    for a, b in zip(out[0][1], out[1][1]):
+        assert rel(a, b) < 3e-4, rel(a, b)
