@@ -48,6 +48,7 @@ PROTOTYPES = {
     'gp3d_conv_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p] + [c_int] * 10 + [c_void_p]),
     'gp3d_wgrad_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 9 + [c_void_p] + [c_int] * 4 + [c_void_p]),
     'gp3d_split_bf16': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'gp3d_adam_ema_step': (c_int, [c_void_p] * 5 + [c_int64] + [c_float] * 11 + [c_void_p, c_void_p, c_void_p]),
     'gp3d_split_bf16_pad': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -352,6 +352,7 @@ int launch_bwd(const Params& p, cudaStream_t st) {
 
 int gp3d_raymarch_check(const void* planes, int planes_dtype, int64_t psB, int64_t psP, int64_t psC, int64_t psY,
                         int64_t psX, const gp3d_raymarch_opts* o, const char* who);
+int gp3d_raymarch_backward_v2(const rm::Params& p, int planes_dtype, int mode, cudaStream_t st);   // raymarch_bwd2.cu
 
 extern "C" int gp3d_raymarch_backward(const void* planes, int planes_dtype,
                                       int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
@@ -376,7 +377,10 @@ extern "C" int gp3d_raymarch_backward(const void* planes, int planes_dtype,
     p.g_ray_o = g_ray_o; p.g_ray_d = g_ray_d;
     p.o = *opts;
     cudaStream_t s = (cudaStream_t)stream;
-    int r = (planes_dtype == GP3D_F32) ? rm::launch_bwd<float>(p, s) : rm::launch_bwd<__half>(p, s);
+    GP3D_CHECK_ARG(opts->mlp_mode >= 0 && opts->mlp_mode <= 2, "raymarch_backward: mlp_mode must be 0 (fp32 SIMT), 1 (TF32) or 2 (3xTF32)");
+    int r;
+    if (opts->mlp_mode == 0) r = (planes_dtype == GP3D_F32) ? rm::launch_bwd<float>(p, s) : rm::launch_bwd<__half>(p, s);
+    else r = gp3d_raymarch_backward_v2(p, planes_dtype, opts->mlp_mode, s);
     if (r != 0) return r;
     GP3D_RETURN_LAUNCH();
 }

@@ -65,6 +65,11 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None):
 _weight_cache = {}
 
 
+def invalidate_weight_cache():
+    """Drop every cached weight operand (for writers that bypass autograd's version counters, e.g. the fused optimiser kernel)."""
+    _weight_cache.clear()
+
+
 def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
     """bf16 (hi, lo) operand pair of a weight tensor in the layout `make_nhwc(weight)` produces ([rows][taps][cols], cols contiguous).
     Parameters are re-laid-out and split ONCE per optimiser step: the cache is keyed by (id, tag) and invalidated by the tensor's

@@ -10,6 +10,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib
+from ..torch_utils.ops import tc as _tc
 from ..dnnlib import EasyDict
 
 
@@ -33,6 +34,111 @@ def allreduce_gradients(params, world_size, group=None):
     return flat.numel()
 
 
+class FlatAdam:
+    """torch.optim.Adam over ONE flat float32 storage per module (training_loop.py:190-205, 335-346, 357-364).
+
+    Parameters, gradients, second moments (first moments only when beta1 != 0) and, for G, the EMA copy live in parallel
+    flat buffers carved in 1024-element blocks; each `p.data` / `p.grad` / `p_ema.data` is a view into them.  A phase is then
+      zero the flat gradient -> backward accumulates in place -> ONE all-reduce of the flat gradient ->
+      ONE kernel: /world + nan_to_num + Adam + p_ema lerp   (csrc/optim.cu)
+    instead of cat + all_reduce + 2 elementwise passes + split/copy-back + ~12 foreach kernels + lerp/copy per tensor.
+    Parameters that received no gradient in a phase are left untouched and keep their own step count, as torch.optim does
+    for `.grad is None`."""
+    BLOCK = 1024
+
+    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, ema_module=None, **unused):
+        assert not unused.get('weight_decay') and not unused.get('amsgrad'), 'only the options the reference configs use are built'
+        self.params = [p for p in module.parameters() if p.numel() > 0]
+        dev = self.params[0].device
+        assert dev.type == 'cuda' and all(p.dtype == torch.float32 and p.device == dev for p in self.params)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.BLOCK) * self.BLOCK
+        self.numel = off
+        self.flat_p = torch.zeros(off, device=dev)
+        self.flat_g = torch.zeros(off, device=dev)
+        self.flat_v = torch.zeros(off, device=dev)
+        self.flat_m = torch.zeros(off, device=dev) if self.betas[0] != 0 else None
+        self.flat_ema = torch.zeros(off, device=dev) if ema_module is not None else None
+        self.grad_views = []
+        for p, o in zip(self.params, self.offsets):
+            v = self.flat_p[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
+        if ema_module is not None:
+            ema_params = [p for p in ema_module.parameters() if p.numel() > 0]
+            assert [p.shape for p in ema_params] == [p.shape for p in self.params]
+            for p, o in zip(ema_params, self.offsets):
+                v = self.flat_ema[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+        seg = torch.full([off // self.BLOCK], -1, dtype=torch.int32)
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            seg[o // self.BLOCK:(o + p.numel() + self.BLOCK - 1) // self.BLOCK] = i
+        self.blk_seg = seg.to(dev)
+        self.steps = [0] * len(self.params)
+        self.active = set()
+        self._hooks = [p.register_post_accumulate_grad_hook(lambda p_, i=i: self.active.add(i)) for i, p in enumerate(self.params) if p.requires_grad]
+
+    def zero_grad(self):
+        """Start of a phase: clear the flat gradient and (re-)attach every parameter's .grad view."""
+        self.flat_g.zero_()
+        self.active.clear()
+        for p, g in zip(self.params, self.grad_views):
+            p.grad = g
+
+    def step(self, world_size=1, group=None, ema_beta=None):
+        """All-reduce the flat gradient, then the fused epilogue + Adam (+ EMA) kernel."""
+        if world_size > 1:
+            dist.all_reduce(self.flat_g, group=group)
+        b1, b2 = self.betas
+        for i in self.active:
+            self.steps[i] += 1
+        scal = lambda t: (self.lr / (1 - b1 ** t), (1 - b2 ** t) ** 0.5)
+        uniform = len(self.active) == len(self.params) and len(set(self.steps)) == 1
+        desc = None
+        if uniform:
+            step_size, bc2s = scal(self.steps[0])
+        else:
+            step_size, bc2s = 0.0, 1.0
+            rows = []
+            for i, t in enumerate(self.steps):
+                a = i in self.active
+                ss, bc = scal(t) if a else (0.0, 1.0)
+                rows.append([ss, bc, 1.0 if a else 0.0, 0.0])
+            desc = torch.tensor(rows, dtype=torch.float32).to(self.flat_p.device)
+        with torch.cuda.device(self.flat_p.device):
+            rc = _lib.lib().gp3d_adam_ema_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), _lib.ptr(self.flat_m), self.flat_v.data_ptr(),
+                                               _lib.ptr(self.flat_ema) if ema_beta is not None else None, self.numel,
+                                               1.0 / world_size, 1e5, -1e5, b1, b2, 1 - b1, 1 - b2, self.eps, step_size, bc2s,
+                                               float(ema_beta) if ema_beta is not None else 0.0,
+                                               None if desc is None else self.blk_seg.data_ptr(), _lib.ptr(desc), _lib.stream_ptr())
+        _lib.check(rc, 'adam_ema_step')
+        _tc.invalidate_weight_cache()                         # the kernel wrote the parameters behind autograd's version counters
+        self.active.clear()
+        return self.numel
+
+    def state_dict(self):
+        """Per-parameter state in torch.optim.Adam's layout (step, exp_avg, exp_avg_sq), for checkpoints."""
+        st = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            sl = slice(o, o + p.numel())
+            st[i] = dict(step=self.steps[i], exp_avg_sq=self.flat_v[sl].view(p.shape).clone(),
+                         exp_avg=(self.flat_m[sl].view(p.shape).clone() if self.flat_m is not None else None))
+        return dict(state=st, lr=self.lr, betas=self.betas, eps=self.eps)
+
+    def load_state_dict(self, sd):
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            e = sd['state'][i]; sl = slice(o, o + p.numel())
+            self.steps[i] = int(e['step'])
+            self.flat_v[sl].copy_(e['exp_avg_sq'].flatten())
+            if self.flat_m is not None:
+                self.flat_m[sl].copy_(e['exp_avg'].flatten())
+
+
 class Trainer:
     """Holds G, D, G_ema, the loss and both Adam optimisers with the reference's lazy-regularisation scaling
     (training_loop.py:190-205: lr *= mb_ratio, betas ** mb_ratio with mb_ratio = interval / (interval + 1))."""
@@ -45,26 +151,37 @@ class Trainer:
                     dist.broadcast(t.data, src=0)
         self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
         gk, dk = dict(cfg.model.generator.optim.kwargs), dict(cfg.model.discriminator.optim.kwargs)
-        self.G_opt = torch.optim.Adam(G.parameters(), **gk)
         mb = D_reg_interval / (D_reg_interval + 1) if D_reg_interval else 1.0
         dk['lr'] = dk['lr'] * mb
         dk['betas'] = [b ** mb for b in dk['betas']]
-        self.D_opt = torch.optim.Adam(D.parameters(), **dk)
+        self.flat = next(G.parameters()).is_cuda      # CUDA: flat storage + fused kernel; CPU (gloo host-logic tests): torch ops
+        if self.flat:
+            self.G_opt = FlatAdam(G, ema_module=self.G_ema, **gk)
+            self.D_opt = FlatAdam(D, **dk)
+        else:
+            self.G_opt = torch.optim.Adam(G.parameters(), **gk)
+            self.D_opt = torch.optim.Adam(D.parameters(), **dk)
         self.D_reg_interval = D_reg_interval
         self.ema_kimg, self.ema_rampup, self.batch_size = ema_kimg, ema_rampup, batch_size
         self.micro_batch = micro_batch
         self.cur_nimg = 0
         self.it = 0
 
-    def _phase(self, name, module, opt, real, gen, gain, render_opts=None):
-        opt.zero_grad(set_to_none=True)
+    def _phase(self, name, module, opt, real, gen, gain, render_opts=None, ema_beta=None):
+        if self.flat:
+            opt.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
         module.requires_grad_(True)
         stats = {}
         for r_mb, g_mb in self._micro_batches(real, gen):     # gradient accumulation, training_loop.py:329-330
             stats = self.loss.accumulate_gradients(phase=name, real_data=r_mb, gen_data=g_mb, gain=gain, cur_nimg=self.cur_nimg, render_opts=render_opts)
         module.requires_grad_(False)
-        allreduce_gradients([p for p in module.parameters() if p.numel() > 0], self.world_size)
-        opt.step()
+        if self.flat:
+            opt.step(self.world_size, ema_beta=ema_beta)
+        else:
+            allreduce_gradients([p for p in module.parameters() if p.numel() > 0], self.world_size)
+            opt.step()
         return stats
 
     def _micro_batches(self, real, gen):
@@ -80,21 +197,23 @@ class Trainer:
     def step(self, real, gen, render_opts=None):
         """real/gen: EasyDicts of this rank's micro-batch (see loss.accumulate_gradients).  Returns scalar stats."""
         stats = {}
-        self.D.requires_grad_(False)
-        stats.update(self._phase('Gmain', self.G, self.G_opt, real, gen, 1, render_opts))
-        self.G.requires_grad_(False)
-        stats.update(self._phase('Dmain', self.D, self.D_opt, real, gen, 1, render_opts))
-        if self.D_reg_interval and self.it % self.D_reg_interval == 0:
-            stats.update(self._phase('Dreg', self.D, self.D_opt, real, gen, self.D_reg_interval, render_opts))
-        # G_ema (training_loop.py:357-366)
+        # G_ema coefficient (training_loop.py:357-362); G does not change after Gmain, so the lerp rides in G's optimiser kernel
         bs = self.batch_size or (len(gen.z) * self.world_size)
         ema_nimg = self.ema_kimg * 1000
         if self.ema_rampup is not None:
             ema_nimg = min(ema_nimg, self.cur_nimg * self.ema_rampup)
         beta = 0.5 ** (bs / max(ema_nimg, 1e-8))
+        self.D.requires_grad_(False)
+        stats.update(self._phase('Gmain', self.G, self.G_opt, real, gen, 1, render_opts, ema_beta=beta))
+        self.G.requires_grad_(False)
+        stats.update(self._phase('Dmain', self.D, self.D_opt, real, gen, 1, render_opts))
+        if self.D_reg_interval and self.it % self.D_reg_interval == 0:
+            stats.update(self._phase('Dreg', self.D, self.D_opt, real, gen, self.D_reg_interval, render_opts))
+        # G_ema (training_loop.py:357-366)
         with torch.no_grad():
-            for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
-                pe.copy_(p.lerp(pe, beta))
+            if not self.flat:
+                for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
+                    pe.copy_(p.lerp(pe, beta))
             for be, b in zip(self.G_ema.buffers(), self.G.buffers()):
                 be.copy_(b)
         self.cur_nimg += bs

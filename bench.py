@@ -175,6 +175,21 @@ def run_raymarch(args, rank, world, local):
         out_h.copy_(torch.cat([rgb, depth, wsum], dim=-1), non_blocking=True)
 
     ms_e2e, _ = timed_region(step_e2e, args.steps, args.warmup, world)
+    # config 3 also asks for forward + backward: gradients w.r.t. planes and MLP (the training configuration), CUDA events per leg
+    plg = pl.detach().clone().requires_grad_(True)
+    wsg = [d[k].clone().requires_grad_(True) for k in ('w1', 'b1', 'w2', 'b2')]
+    tf = tb = 0.0
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for i in range(args.warmup + args.steps):
+        evs[0].record()
+        rgb, depth, _, _ = rmod.render_rays(plg, *wsg, d['ray_o'], d['ray_d'], seed=i, density_noise=0.5, **kw)
+        evs[1].record()
+        torch.autograd.grad([rgb, depth], [plg] + wsg, [torch.ones_like(rgb), torch.ones_like(depth)])
+        evs[2].record()
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            tf += evs[0].elapsed_time(evs[1]); tb += evs[1].elapsed_time(evs[2])
+    del plg
     pb = 2 if args.planes_fp16 else 4
     alg = raymarch_algorithmic_bytes(B, R_, RM['N'], RM['P'], RM['C'], plane_bytes=pb)
     peaks = measured_peaks()
@@ -188,7 +203,9 @@ def run_raymarch(args, rank, world, local):
         roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
                       kernel='raymarch_fwd2_kernel' if args.mlp_mode else 'raymarch_fwd_kernel', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg),
         e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(2 * B * R_ * 12), d2h_bytes_per_step=int(B * R_ * 20)),
-        gpu_launches=args.steps, clocks=clocks)
+        gpu_launches=args.steps, clocks=clocks,
+        forward_backward=dict(forward_ms=tf / args.steps, backward_ms=tb / args.steps, kernel_bwd='raymarch_bwd2_kernel' if args.mlp_mode else 'raymarch_bwd_kernel',
+                              note='backward includes the zero-fill of the plane-gradient buffer (B*3*C*P^2*4 bytes)'))
     return res
 
 
@@ -281,7 +298,7 @@ def run_train_step(args, rank, world, local):
     rmod = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
     dev = torch.device('cuda', local)
     B = args.batch_gpu or 32
-    mb = args.micro_batch or min(B, 16)
+    mb = args.micro_batch or min(B, 32)
     assert B % mb == 0 and mb % 4 == 0, 'micro-batch must divide batch-gpu and be a multiple of the minibatch-std group (4)'
     small = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if args.small else {}
     cfg = cfgm.make_config(batch_size=B * world, **small)
@@ -337,7 +354,7 @@ def run_train_step(args, rank, world, local):
         metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
         dtype='G fp32 (TF32 off) / D fp16+fp32, as the reference (configs/model/3dgp.yaml:8)',
         config=dict(workload='train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64)' if not args.small else 'train_step SMALL (debug)',
-                    batch_per_gpu=B, micro_batch=mb, global_batch=B * world, phases='Gmain + Dmain every iteration, Dreg (R1) every 16th',
+                    batch_per_gpu=B, micro_batch=mb, global_batch=B * world, peak_mem_gb=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1), phases='Gmain + Dmain every iteration, Dreg (R1) every 16th',
                     l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
                     parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)', conv_engine=args.conv_engine,
                     conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9)),

@@ -170,6 +170,24 @@ int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* d
 int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, float posinf, float neginf, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimiser step fused with the all-reduce epilogue and the G_ema update (reference training_loop.py:340-341 nan_to_num,
+ * :346 opt.step() = torch.optim.Adam built at :190-205, :357-364 p_ema.copy_(p.lerp(p_ema, beta))): one pass over a
+ * module's flat float32 storage.  p, g, v (and m, ema when given) are parallel buffers of `numel` floats, numel % 1024 == 0,
+ * every parameter tensor starting on a 1024-element boundary.
+ *   g' = nan_to_num(g * grad_scale, 0, posinf, neginf);  m = lerp(m, g', 1-beta1) (m == NULL iff beta1 == 0);
+ *   v = v*beta2 + (1-beta2) g'^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps);  ema = lerp(p, ema, ema_beta) if ema != NULL
+ * with step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t), one_minus_beta* = 1 - beta* computed by the caller in double
+ * precision and rounded once (torch.optim.Adam's python scalars).
+ * blk_seg / seg_desc (both or neither): blk_seg[numel/1024] = tensor index of each block (-1: padding), seg_desc[4*i] =
+ * {step_size_i, bc2_sqrt_i, active_i, 0}: per-tensor step counts and "received no gradient this phase => untouched"
+ * (torch.optim skips parameters whose .grad is None); the EMA update still applies to inactive tensors.
+ */
+int gp3d_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t numel,
+                       float grad_scale, float posinf, float neginf, float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                       float step_size, float bc2_sqrt, float ema_beta,
+                       const int* blk_seg, const float* seg_desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 / TMEM (sm_100a):  D[M][N] (+)= A[M][K] * B[N][K]^T, bf16 operands,
  * fp32 accumulate in TMEM, TMA-fed 128B-swizzled smem tiles.  This is the engine under the modulated /
  * discriminator convolutions (implicit GEMM: the conv front-end lays the im2col tiles out through TMA).

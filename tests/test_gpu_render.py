@@ -127,3 +127,60 @@ def test_render_forward_tensor_core_mlp_vs_golden(golden, name, kw, mode, tol):
     assert maxrel(depth.squeeze(-1).cpu().numpy(), g[name + '/depth']) < tol
     assert maxrel(wsum.squeeze(-1).cpu().numpy(), g[name + '/wsum']) < tol
     assert maxrel(tfin.cpu().numpy(), g[name + '/tfinal']) < tol
+
+
+@pytest.mark.parametrize('mode,tol', [(1, 6e-3), (2, TOL)])
+@pytest.mark.parametrize('name,kw', cases.render_cases(), ids=[c[0] for c in cases.render_cases()])
+def test_render_backward_tensor_core_vs_golden(golden, name, kw, mode, tol):
+    """Second-generation backward kernel (raymarch_bwd2.cu): recompute + every MLP contraction (layer 1, dW2, dW1, d feature) on
+    mma.sync TF32 (mode 1) / 3xTF32 (mode 2), parallel compositing backward; all seven gradients against the reference's autograd."""
+    inp = cases.render_inputs(name, kw)
+    (rgb, depth, _, _), args = _run(kw, inp, requires_grad=True, mlp_mode=mode)
+    g_rgb = cu(cases.cotangent(rgb.shape, 21)); g_dep = cu(cases.cotangent(depth.shape, 22))
+    grads = torch.autograd.grad([rgb, depth], args, [g_rgb, g_dep], retain_graph=True)
+    g = golden('render')
+    names = ['g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2', 'g_ray_o', 'g_ray_d']
+    for nm, gr in zip(names, grads):
+        gr = gr.contiguous()
+        if nm == 'g_planes' and (name + '/g_planes') not in g.files:
+            probe = gr.flatten()[::97].cpu().numpy()
+            assert l2rel(probe, g[name + '/g_planes_probe']) < tol
+            st = np.array([gr.double().sum().item(), gr.double().abs().sum().item(), gr.double().square().sum().item()])
+            assert np.allclose(st[1:], g[name + '/g_planes_sum'][1:], rtol=max(tol, 1e-3))
+            continue
+        ref = g[name + '/' + nm]
+        assert gr.shape == ref.shape, (nm, gr.shape, ref.shape)
+        assert l2rel(gr.cpu().numpy(), ref) < tol, (nm, l2rel(gr.cpu().numpy(), ref))
+        assert maxrel(gr.cpu().numpy(), ref) < 5 * tol, (nm, maxrel(gr.cpu().numpy(), ref))
+    # the training configuration asks for no ray gradients (learn_camera_dist = false): same kernel without the tap dot-products
+    g2 = torch.autograd.grad([rgb, depth], args[:5], [g_rgb, g_dep])
+    for a, b in zip(g2, grads[:5]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(b.abs().max()))
+
+
+def test_render_backward_generations_agree_at_full_size():
+    """BASELINE config 3 geometry, one image: first-generation (fp32 SIMT) and second-generation (3xTF32) backward kernels on the
+    same inputs in Philox mode (same seed => same samples)."""
+    rm = _rm()
+    torch.manual_seed(1)
+    B, P, Rr, N = 1, 512, 4096, 48
+    planes = (torch.randn([B, P, P, 96], device='cuda') * 0.5).permute(0, 3, 1, 2).view(B, 3, 32, P, P).requires_grad_(True)
+    w1 = torch.randn(64, 32, device='cuda', requires_grad=True); b1 = (torch.randn(64, device='cuda') * 0.1).requires_grad_(True)
+    w2 = torch.randn(4, 64, device='cuda', requires_grad=True); b2 = torch.zeros(4, device='cuda', requires_grad=True)
+    inp = cases.render_inputs('full_rays', dict(B=B, R=Rr, N=4, P=2, C=32, H=64))
+    ro, rd = cu(inp['ray_o']), cu(inp['ray_d'])
+    kw = dict(num_steps=N, ray_start=0.75, ray_end=1.25, box_size=1.0, seed=11, density_noise=0.3)
+    res = []
+    for mode in (0, 2):
+        rgb, depth, _, _ = rm.render_rays(planes, w1, b1, w2, b2, ro, rd, mlp_mode=mode, **kw)
+        gr = torch.autograd.grad([rgb, depth], [planes, w1, b1, w2, b2], [torch.ones_like(rgb) * 0.3, torch.ones_like(depth)])
+        res.append(gr)
+    # Importance sampling is discontinuous (searchsorted): a 1e-6 difference in a coarse weight can move a handful of the 196 608 fine
+    # samples to another bin, so the norms are compared loosely and the typical element tightly.
+    for i, (a, b) in enumerate(zip(*res)):
+        assert torch.isfinite(a).all() and torch.isfinite(b).all()
+        assert ((a - b).norm() / b.norm()).item() < (1e-2 if i == 0 else 5e-3), i
+    a, b = res[0][0].flatten(), res[1][0].flatten()
+    nzi = b.abs() > 1e-3 * b.abs().max()
+    rel = ((a[nzi] - b[nzi]).abs() / b[nzi].abs())
+    assert rel.median().item() < 1e-4 and (rel > 1e-2).float().mean().item() < 1e-3
