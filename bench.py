@@ -524,6 +524,8 @@ def main():
                     config=res['config'], roofline=res['roofline'], e2e=res['e2e'], gpu_launches=res['gpu_launches'], clocks=res['clocks'])
         if 'roofline_step_tensor' in res:
             line['roofline_step_tensor'] = res['roofline_step_tensor']
+        if 'forward_backward' in res:
+            line['forward_backward'] = res['forward_backward']
         if world == 1 and not args.no_cpu_baseline:
             if args.workload != 'ginfer':
                 line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)

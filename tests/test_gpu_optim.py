@@ -27,16 +27,14 @@ def test_flat_adam_tracks_torch_adam_with_nan_to_num_and_ema(betas):
         opt.zero_grad(); ropt.zero_grad(set_to_none=True)
         x = torch.randn(8, 37, device='cuda', generator=g)
         skip_last = it in (2, 3)                       # the last layer gets no gradient in two of the phases
-        for n_, o_ in ((net, None), (ref, None)):
-            h = n_[1](n_[0](x))
-            loss = (h.square().mean() if skip_last else n_[2](h).square().mean()) * (3.0 ** it)
-            loss.backward()
+        h = net[1](net[0](x))
+        loss = (h.square().mean() if skip_last else net[2](h).square().mean()) * (3.0 ** it)
+        loss.backward()
         if it == 4:                                    # non-finite gradients: nan -> 0, +-inf -> +-1e5 (training_loop.py:341)
-            for n_ in (net, ref):
-                n_[0].weight.grad[0, 0] = float('nan'); n_[0].weight.grad[0, 1] = float('inf'); n_[1].bias.grad[3] = -float('inf')
-        for p in ref.parameters():
-            if p.grad is not None:
-                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+            net[0].weight.grad[0, 0] = float('nan'); net[0].weight.grad[0, 1] = float('inf'); net[1].bias.grad[3] = -float('inf')
+        # the same gradients go to torch.optim.Adam, so that only the optimiser arithmetic is compared
+        for i, (p, q) in enumerate(zip(net.parameters(), ref.parameters())):
+            q.grad = torch.nan_to_num(p.grad.detach().clone(), nan=0, posinf=1e5, neginf=-1e5) if i in opt.active else None
         opt.step(ema_beta=0.75 if it % 2 else 0.25)
         ropt.step()
         with torch.no_grad():
@@ -53,7 +51,7 @@ def test_flat_adam_tracks_torch_adam_with_nan_to_num_and_ema(betas):
     rs = ropt.state_dict()['state']
     for i in range(len(opt.params)):
         assert sd['state'][i]['step'] == int(rs[i]['step'])
-        assert torch.allclose(sd['state'][i]['exp_avg_sq'], rs[i]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
+        assert torch.allclose(sd['state'][i]['exp_avg_sq'], rs[i]['exp_avg_sq'], rtol=2e-6, atol=1e-30)
 
 
 def test_flat_adam_parameters_are_views_of_one_storage_and_grads_accumulate_in_place():
