@@ -28,18 +28,27 @@ struct ConvGeom {
     int tiles_x, tiles_y, tiles_n, tiles_co;
 };
 
+// Optional fused epilogue of the modulated-conv layer (networks_stylegan2.py:71 fma + :144 bias_act, no clamp):
+//   y = act(acc * dcoef[n][co] + noise[n?][oy][ox] + bias[co]) * gain      -- the raw conv output never reaches HBM.
+struct ConvEpi {
+    const float* dcoef; const float* noise; const float* bias;
+    int enabled, noise_per_sample, act;
+    float alpha, gain;
+};
+
 // TERMS == 1: y += xh * wh.   TERMS == 3 (error-compensated "bf16x3", ~2^-16 relative): y += xh*wh + xh*wl + xl*wh with
 // x = xh + xl, w = wh + wl split into bf16 pairs; all three products accumulate into the same TMEM tile.
 template <int BN, int TERMS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmWl,
-                      float* __restrict__ Y, ConvGeom g, int accumulate, int num_tiles) {
+                      float* __restrict__ Y, ConvGeom g, int accumulate, int num_tiles, ConvEpi ep) {
     // Persistent: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers (2 x 128 columns) let the epilogue of
     // tile i overlap the TMA / MMA main loop of tile i+1; the smem ring and its phases run continuously across tiles.
     constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
     constexpr uint32_t kOperand = (CBM + BN) * CBK * 2;
     constexpr uint32_t kStage = kOperand * (TERMS == 3 ? 2 : 1);
+    constexpr uint32_t kAccStride = (BN <= 128) ? 128 : 256;      // TMEM columns per accumulator buffer (two buffers: 256 or all 512 columns)
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* tiles = smem;
@@ -59,7 +68,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }   // 4 epilogue warps arrive
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * kAccStride);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -104,7 +113,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * 128;
+                const uint32_t tmem_d = tmem_base + buf * kAccStride;
                 for (int kb = 0; kb < num_kb; kb++, it++) {
                     const int st = it % CSTAGES; const uint32_t ph = (it / CSTAGES) & 1;
                     mbar_wait(&full_bar[st], ph);
@@ -139,15 +148,31 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
             const bool inside = (ix < g.WoP) && (iy < g.HoP) && (nn < g.N);
             float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + g.oy0)) * g.Wout + (size_t)(ix * g.osx + g.ox0)) * g.Cout + co0;
+            float nz = 0.f;
+            const float* drow = nullptr;
+            if (ep.enabled && inside) {
+                if (ep.noise) nz = ep.noise[(ep.noise_per_sample ? (size_t)nn * g.Hout * g.Wout : 0) + (size_t)(iy * g.osy + g.oy0) * g.Wout + (size_t)(ix * g.osx + g.ox0)];
+                if (ep.dcoef) drow = ep.dcoef + (size_t)nn * g.Cout + co0;
+            }
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
+                tmem_ld_32x32(tmem_base + buf * kAccStride + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
                 tmem_ld_wait();
                 if (!inside) continue;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    if (ep.enabled) {
+                        const float4 dv = drow ? *reinterpret_cast<const float4*>(drow + c + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        const float4 bv = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + co0 + c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        o.x = fmaf(o.x, dv.x, nz) + bv.x; o.y = fmaf(o.y, dv.y, nz) + bv.y; o.z = fmaf(o.z, dv.z, nz) + bv.z; o.w = fmaf(o.w, dv.w, nz) + bv.w;
+                        if (ep.act == 3) {
+                            o.x = (o.x > 0.f) ? o.x : o.x * ep.alpha; o.y = (o.y > 0.f) ? o.y : o.y * ep.alpha;
+                            o.z = (o.z > 0.f) ? o.z : o.z * ep.alpha; o.w = (o.w > 0.f) ? o.w : o.w * ep.alpha;
+                        }
+                        o.x *= ep.gain; o.y *= ep.gain; o.z *= ep.gain; o.w *= ep.gain;
+                    }
                     float4* dst = reinterpret_cast<float4*>(yrow + c + j);
                     if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
                     *dst = o;
@@ -160,12 +185,12 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * kAccStride);
 }
 
 template <int BN, int TERMS>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXl, const CUtensorMap& tmWl, float* y, const ConvGeom& g,
-                int accumulate, cudaStream_t s) {
+                int accumulate, cudaStream_t s, const ConvEpi& ep) {
     constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
     constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1);
     const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256;
@@ -176,7 +201,7 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
     int sms = GP3D_NUM_SMS, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t grid = num_tiles < sms ? num_tiles : sms;        // persistent: one CTA per SM
-    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, tmXl, tmWl, y, g, accumulate, (int)num_tiles);
+    kern<<<(unsigned)grid, kConvThreads, smem, s>>>(tmX, tmW, tmXl, tmWl, y, g, accumulate, (int)num_tiles, ep);
     return 0;
 }
 
@@ -187,8 +212,16 @@ static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // General tap convolution.  taps: ntaps x (dy, dx, slab).  num_slabs = weight slabs per output channel.
 static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
                      int num_slabs, int ntaps, const int* taps, int in_stride, int HoP, int WoP, int Hout, int Wout,
-                     int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who) {
+                     int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who, const gp3d_conv_epilogue* epi = nullptr) {
     GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
+    tc::ConvEpi ep{};
+    if (epi) {
+        GP3D_CHECK_ARG(!accumulate, "%s: the fused epilogue cannot accumulate into y", who);
+        GP3D_CHECK_ARG(epi->act == 1 || epi->act == 3, "%s: fused epilogue activation must be linear (1) or lrelu (3), got %d", who, epi->act);
+        GP3D_CHECK_ARG((!epi->dcoef || gp3d_aligned16(epi->dcoef)) && (!epi->bias || gp3d_aligned16(epi->bias)), "%s: epilogue vectors must be 16-byte aligned", who);
+        ep.dcoef = epi->dcoef; ep.noise = epi->noise; ep.bias = epi->bias; ep.enabled = 1; ep.noise_per_sample = epi->noise_per_sample;
+        ep.act = epi->act; ep.alpha = epi->alpha; ep.gain = epi->gain;
+    }
     GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "%s: both low-order operands are required", who);
     GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && HoP > 0 && WoP > 0, "%s: empty tensor", who);
     GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (in_stride == 1 || in_stride == 2), "%s: bad tap list / stride", who);
@@ -205,7 +238,9 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     g.TW = pow2ceil(WoP) < 16 ? pow2ceil(WoP) : 16;
     g.TH = pow2ceil(HoP) < (128 / g.TW) ? pow2ceil(HoP) : (128 / g.TW);
     g.TN = 128 / (g.TW * g.TH);
-    const int BN = (Cout % 128 == 0) ? 128 : Cout;
+    // single-term launches are bound by the L2 -> SM operand stream (96 B/clk/SM at 128x128 tiles): 256-wide tiles reuse each
+    // activation tile for twice the MMAs.  The three-term form is MMA-bound already and keeps 128 (its stage would not fit twice).
+    const int BN = (!xl && Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : Cout;
     g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN; g.tiles_co = Cout / BN;
     GP3D_CHECK_ARG((int64_t)g.tiles_x * g.tiles_y * g.tiles_n * g.tiles_co < 2147483647LL, "%s: grid too large", who);
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
@@ -238,24 +273,25 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     int rc;
     if (!xl) {
         tmXl = tmX; tmWl = tmW;
-        rc = (BN == 128) ? tc::launch_conv<128, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
-           : (BN == 96)  ? tc::launch_conv<96, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
-                         : tc::launch_conv<64, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s);
+        rc = (BN == 256) ? tc::launch_conv<256, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+           : (BN == 128) ? tc::launch_conv<128, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+           : (BN == 96)  ? tc::launch_conv<96, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+                         : tc::launch_conv<64, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
     } else {
-        rc = (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
-           : (BN == 96)  ? tc::launch_conv<96, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s)
-                         : tc::launch_conv<64, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s);
+        rc = (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+           : (BN == 96)  ? tc::launch_conv<96, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+                         : tc::launch_conv<64, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
     }
     if (rc) return rc;
     GP3D_RETURN_LAUNCH();
 }
 
 static int conv_same(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
-                     int ksize, int accumulate, void* stream, const char* who) {
+                     int ksize, int accumulate, void* stream, const char* who, const gp3d_conv_epilogue* epi = nullptr) {
     GP3D_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5, "%s: kernel size must be 1, 3 or 5 (got %d)", who, ksize);
     int taps[75]; int nt = 0;
     for (int ky = 0; ky < ksize; ky++) for (int kx = 0; kx < ksize; kx++) { taps[3 * nt] = ky - ksize / 2; taps[3 * nt + 1] = kx - ksize / 2; taps[3 * nt + 2] = ky * ksize + kx; nt++; }
-    return conv_impl(x, xl, w, wl, y, N, H, W, Cin, Cout, ksize * ksize, nt, taps, 1, H, W, H, W, 1, 1, 0, 0, accumulate, stream, who);
+    return conv_impl(x, xl, w, wl, y, N, H, W, Cin, Cout, ksize * ksize, nt, taps, 1, H, W, H, W, 1, 1, 0, 0, accumulate, stream, who, epi);
 }
 
 extern "C" int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, int W, int Cin, int Cout,
@@ -267,6 +303,13 @@ extern "C" int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const voi
                                        int Cin, int Cout, int ksize, int accumulate, void* stream) {
     GP3D_CHECK_ARG(xl && wl, "conv2d_nhwc_bf16x3: null low-order operand");
     return conv_same(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, accumulate, stream, "conv2d_nhwc_bf16x3");
+}
+
+extern "C" int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                                           int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream) {
+    GP3D_CHECK_ARG(xl && wl, "conv2d_nhwc_bf16x3_act: null low-order operand");
+    GP3D_CHECK_ARG(epi != nullptr, "conv2d_nhwc_bf16x3_act: null epilogue description");
+    return conv_same(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, 0, stream, "conv2d_nhwc_bf16x3_act", epi);
 }
 
 extern "C" int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, float* y,

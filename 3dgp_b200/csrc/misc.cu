@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restr
                                                             const float* __restrict__ noise, const float* __restrict__ noise_scale,
                                                             int noise_per_sample, const float* __restrict__ b,
                                                             float* __restrict__ dc, float* __restrict__ g_d, float* __restrict__ g_b,
-                                                            float* __restrict__ g_ns, int N, int HW, int C, float alpha, float gain, int chunks) {
+                                                            float* __restrict__ g_ns, int N, int HW, int C, float alpha, float gain, int chunks,
+                                                            __nv_bfloat16* __restrict__ dc_hi, __nv_bfloat16* __restrict__ dc_lo, int Cp) {
     extern __shared__ float red_smem[];
     const float nscale = (noise && noise_scale) ? *noise_scale : 1.f;
     const int CV_all = C / 4;
@@ -364,7 +365,20 @@ __global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restr
                     if (k == 0) { sb.x += dt[k]; sd.x += dt[k] * c; } else if (k == 1) { sb.y += dt[k]; sd.y += dt[k] * c; }
                     else if (k == 2) { sb.z += dt[k]; sd.z += dt[k] * c; } else { sb.w += dt[k]; sd.w += dt[k] * c; }
                 }
-                *reinterpret_cast<float4*>(dc + off) = make_float4(o[0], o[1], o[2], o[3]);
+                if (dc_hi) {   // hand the conv kernels their bf16 (hi, lo) operand pair directly, channel tail zero-padded to Cp
+                    const int64_t offp = ((int64_t)n * HW + px) * Cp + 4 * cv;
+                    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { h[k] = __float2bfloat16_rn(o[k]); l[k] = __float2bfloat16_rn(o[k] - __bfloat162float(h[k])); }
+                    *reinterpret_cast<uint2*>(dc_hi + offp) = *reinterpret_cast<const uint2*>(h);
+                    *reinterpret_cast<uint2*>(dc_lo + offp) = *reinterpret_cast<const uint2*>(l);
+                    if (4 * cv < Cp - C) {     // Cp - C <= C: the first (Cp-C)/4 channel lanes also clear the padding
+                        *reinterpret_cast<uint2*>(dc_hi + ((int64_t)n * HW + px) * Cp + C + 4 * cv) = make_uint2(0u, 0u);
+                        *reinterpret_cast<uint2*>(dc_lo + ((int64_t)n * HW + px) * Cp + C + 4 * cv) = make_uint2(0u, 0u);
+                    }
+                } else {
+                    *reinterpret_cast<float4*>(dc + off) = make_float4(o[0], o[1], o[2], o[3]);
+                }
             }
         }
         if (g_b) block_channel_reduce_add(sb, red_smem, cvl, CV, PL, pl, g_b + 4 * cbase);
@@ -414,20 +428,30 @@ static int reduce_chunks(int N, int HW) {
 
 }  // namespace
 
-extern "C" int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample, const float* b,
-                                  float* dc, float* g_d, float* g_b, float* g_ns, int N, int HW, int C, int act, float alpha, float gain,
-                                  void* stream) {
-    GP3D_CHECK_ARG(dy && y && dc && N >= 1 && HW >= 1 && C >= 4 && C % 4 == 0, "demod_act_bwd: bad arguments (C must be a multiple of 4)");
+extern "C" int gp3d_demod_act_bwd_split(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample,
+                                        const float* b, float* dc, void* dc_hi, void* dc_lo, int C_pad, float* g_d, float* g_b, float* g_ns,
+                                        int N, int HW, int C, int act, float alpha, float gain, void* stream) {
+    GP3D_CHECK_ARG(dy && y && N >= 1 && HW >= 1 && C >= 4 && C % 4 == 0, "demod_act_bwd: bad arguments (C must be a multiple of 4)");
+    GP3D_CHECK_ARG((dc != nullptr) != (dc_hi != nullptr) && (dc_hi == nullptr) == (dc_lo == nullptr), "demod_act_bwd: give either dc (float32) or the dc_hi / dc_lo bf16 pair");
+    GP3D_CHECK_ARG(!dc_hi || (C_pad >= C && C_pad % 4 == 0 && C_pad - C <= C), "demod_act_bwd: padded channel count %d incompatible with C=%d", C_pad, C);
     GP3D_CHECK_ARG(act == 1 || act == 3, "demod_act_bwd: only linear (1) and lrelu (3) are fused, got %d", act);
     GP3D_CHECK_ARG(gain != 0.f, "demod_act_bwd: gain must be non-zero");
-    GP3D_CHECK_ARG(gp3d_aligned16(dy) && gp3d_aligned16(y) && gp3d_aligned16(dc) && (!d || gp3d_aligned16(d)) && (!b || gp3d_aligned16(b)),
-                   "demod_act_bwd: pointers must be 16-byte aligned");
+    GP3D_CHECK_ARG(gp3d_aligned16(dy) && gp3d_aligned16(y) && (!dc || gp3d_aligned16(dc)) && (!dc_hi || (gp3d_aligned16(dc_hi) && gp3d_aligned16(dc_lo)))
+                   && (!d || gp3d_aligned16(d)) && (!b || gp3d_aligned16(b)), "demod_act_bwd: pointers must be 16-byte aligned");
     const int chunks = reduce_chunks(N, HW);
     const size_t smem = 256 * sizeof(float4);
     cudaStream_t st = (cudaStream_t)stream;
-    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks);
-    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks);
+    __nv_bfloat16* hi = (__nv_bfloat16*)dc_hi; __nv_bfloat16* lo = (__nv_bfloat16*)dc_lo;
+    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad);
+    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad);
     GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample, const float* b,
+                                  float* dc, float* g_d, float* g_b, float* g_ns, int N, int HW, int C, int act, float alpha, float gain,
+                                  void* stream) {
+    GP3D_CHECK_ARG(dc != nullptr, "demod_act_bwd: dc is null");
+    return gp3d_demod_act_bwd_split(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, nullptr, nullptr, C, g_d, g_b, g_ns, N, HW, C, act, alpha, gain, stream);
 }
 
 extern "C" int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* dx, float* g_s, int N, int HW, int C, void* stream) {

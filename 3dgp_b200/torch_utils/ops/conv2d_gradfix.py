@@ -62,7 +62,7 @@ def _primitive_conv_transpose(input, weight, bias, stride, padding, output_paddi
             and tuple(padding) == (k - 1 - k // 2, k - 1 - k // 2) and input.dtype in (torch.float32, torch.float16)
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[1], k, (1, 1), (k // 2, k // 2), dilation, groups)):
         tc_stats['tc'] += 1
-        return tc.conv2d_forward(input, weight.flip([2, 3]).transpose(0, 1), terms)
+        return tc.conv2d_forward(input, weight, terms, adjoint=True)
     if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and tuple(padding) == (0, 0)
             and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
             and tc.channels_eligible(input.shape[1], weight.shape[1])):

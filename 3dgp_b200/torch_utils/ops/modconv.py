@@ -9,6 +9,8 @@ tcgen05 input-gradient conv + tcgen05 weight-gradient GEMM  ->  modulate_bwd (dx
 Nothing but x, y and the bf16 operand pair is kept for backward; no x*styles / pre-activation / FIR intermediates survive.
 First-order only (the reference differentiates G twice only when pl_weight > 0, which the 3dgp config sets to 0).
 """
+import ctypes
+
 import torch
 
 from ... import _lib
@@ -57,11 +59,6 @@ class _ModConvLayer(torch.autograd.Function):
         st = styles.to(torch.float32).contiguous()
         xh, xl = tc.split_bf16(xn, styles=st)
         wh, wl = tc.weight_operands(weight, 'fwd', lambda w_: w_.permute(0, 2, 3, 1))
-        c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
-        if up == 2:   # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
-            c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
-        Ho, Wo = c.shape[1], c.shape[2]
-        y = torch.empty_like(c)
         d = dcoefs.to(torch.float32).contiguous() if dcoefs is not None else None
         nz = None
         nps = 0
@@ -69,10 +66,24 @@ class _ModConvLayer(torch.autograd.Function):
             nz = (noise.to(torch.float32) * noise_strength).contiguous()          # [1|N, 1, Ho, Wo] or [Ho, Wo]
             nps = 1 if (nz.dim() == 4 and nz.shape[0] == N and N > 1) else 0
         b = bias.to(torch.float32).contiguous() if bias is not None else None
-        with torch.cuda.device(dev):
-            rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
-                                  3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
-        _lib.check(rc, 'demod_act')
+        if up == 1:   # demodulation, noise, bias and activation ride in the conv kernel's TMEM -> HBM epilogue: the raw conv output is never stored
+            Ho, Wo = H, W
+            y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=dev)
+            epi = _lib.ConvEpilogue(_lib.ptr(d), _lib.ptr(nz), _lib.ptr(b), nps, 3 if act == 'lrelu' else 1, float(alpha), float(gain))
+            with torch.cuda.device(dev):
+                rc = L.gp3d_conv2d_nhwc_bf16x3_act(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k,
+                                                   ctypes.byref(epi), _lib.stream_ptr())
+            _lib.check(rc, 'conv2d_nhwc_bf16x3_act')
+        else:
+            c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
+            # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
+            c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
+            Ho, Wo = c.shape[1], c.shape[2]
+            y = torch.empty_like(c)
+            with torch.cuda.device(dev):
+                rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
+                                      3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
+            _lib.check(rc, 'demod_act')
         ctx.save_for_backward(xn, xh, xl, weight, st, d if d is not None else torch.empty(0, device=dev), y,
                               noise if noise is not None else torch.empty(0, device=dev),
                               noise_strength if noise is not None else torch.empty(0, device=dev),
@@ -88,24 +99,30 @@ class _ModConvLayer(torch.autograd.Function):
         dev = dy.device
         has_d, has_n, has_b = d.numel() > 0, noise.numel() > 0, b.numel() > 0
         dyn = _nhwc(dy.to(torch.float32))
-        dc = torch.empty_like(dyn)
+        # channels of the gradient operand are zero-padded to whole 64-channel TMA blocks (toRGB: 96 -> 128)
+        Cp = ((Cout + 63) // 64) * 64
+        if up == 1:    # no FIR in between: the activation backward writes the conv kernels' bf16 (hi, lo) operands directly
+            dc = None
+            dch = torch.empty([N, Ho, Wo, Cp], dtype=torch.bfloat16, device=dev)
+            dcl = torch.empty_like(dch)
+        else:
+            dc = torch.empty_like(dyn)
+            dch = dcl = None
         g_d = torch.zeros_like(d) if has_d else None
         g_b = torch.zeros([Cout], dtype=torch.float32, device=dev) if has_b else None
         nz_img = noise.to(torch.float32).contiguous() if has_n else None                 # unscaled noise image
         ns = noise_strength.to(torch.float32).reshape(1).contiguous() if has_n else None
         g_ns = torch.zeros([1], dtype=torch.float32, device=dev) if has_n else None
         with torch.cuda.device(dev):
-            rc = L.gp3d_demod_act_bwd(dyn.data_ptr(), y.data_ptr(), _lib.ptr(d if has_d else None), _lib.ptr(nz_img), _lib.ptr(ns), nps,
-                                      _lib.ptr(b if has_b else None), dc.data_ptr(), _lib.ptr(g_d), _lib.ptr(g_b), _lib.ptr(g_ns), N, Ho * Wo, Cout,
-                                      3 if act == 'lrelu' else 1, alpha, gain, _lib.stream_ptr())
+            rc = L.gp3d_demod_act_bwd_split(dyn.data_ptr(), y.data_ptr(), _lib.ptr(d if has_d else None), _lib.ptr(nz_img), _lib.ptr(ns), nps,
+                                            _lib.ptr(b if has_b else None), _lib.ptr(dc), _lib.ptr(dch), _lib.ptr(dcl), Cp, _lib.ptr(g_d), _lib.ptr(g_b), _lib.ptr(g_ns),
+                                            N, Ho * Wo, Cout, 3 if act == 'lrelu' else 1, alpha, gain, _lib.stream_ptr())
         _lib.check(rc, 'demod_act_bwd')
         if g_ns is not None:
             g_ns = g_ns.reshape(noise_strength.shape)
         if up == 2:   # adjoint of the FIR (upfirdn2d.py:250-269): same filter, flipped, padding p = fw - pad - 1 = 2
             dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
-        # channels of the gradient operand are zero-padded to whole 64-channel TMA blocks (toRGB: 96 -> 128)
-        Cp = ((Cout + 63) // 64) * 64
-        dch, dcl = tc.split_bf16(dc, pad_to=Cp)
+            dch, dcl = tc.split_bf16(dc, pad_to=Cp)
         # input gradient
         dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
         assert tc.channels_eligible(Cp, Cin)

@@ -65,9 +65,31 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None):
 _weight_cache = {}
 
 
-def invalidate_weight_cache():
-    """Drop every cached weight operand (for writers that bypass autograd's version counters, e.g. the fused optimiser kernel)."""
-    _weight_cache.clear()
+def invalidate_weight_cache(param_ids=None):
+    """Drop cached weight operands (for writers that bypass autograd's version counters, e.g. the fused optimiser kernel):
+    all of them, or those of the parameters whose id() is in `param_ids`."""
+    if param_ids is None:
+        _weight_cache.clear()
+    else:
+        for key in [k_ for k_ in _weight_cache if k_[0] in param_ids]:
+            del _weight_cache[key]
+
+
+def tag_weight_source(w, param, gain):
+    """Marks `w` (= (param * gain) possibly cast) with the Parameter it was derived from, so that the conv wrappers below can reuse the
+    bf16 operands of that parameter across the forward / input-gradient calls of one optimiser step (Conv2dLayer, layers.py:229)."""
+    w._gp3d_src = (param, float(gain))
+    return w
+
+
+def _operands_of(w, tag, make_nhwc, terms):
+    """(hi, lo) bf16 operands of conv weight `w` in layout make_nhwc(w): cached per source Parameter when `w` carries a tag."""
+    src = getattr(w, '_gp3d_src', None)
+    if src is not None and src[0].shape == w.shape and isinstance(src[0], torch.nn.Parameter):
+        param, gain = src
+        dt = w.dtype
+        return weight_operands(param, (tag, gain, dt), lambda p_: make_nhwc((p_ * gain).to(dt).to(torch.float32)), terms)
+    return split_bf16(make_nhwc(w.detach().to(torch.float32)).contiguous(), want_lo=(terms == 3))
 
 
 def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
@@ -97,10 +119,10 @@ def conv_eligible(N, Cin, H, W, Cout, k, stride, padding, dilation, groups):
     return channels_eligible(Cin, Cout)
 
 
-def _prep(x, w_nhwc_f32, terms):
+def _prep(x, w, tag, make_nhwc, terms):
     xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)          # NHWC view, contiguous
     xh, xl = split_bf16(xn, want_lo=(terms == 3))
-    wh, wl = split_bf16(w_nhwc_f32.contiguous(), want_lo=(terms == 3))
+    wh, wl = _operands_of(w, tag, make_nhwc, terms)
     return xh, xl, wh, wl
 
 
@@ -114,13 +136,17 @@ def _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, 
     _lib.check(rc, 'conv_taps_nhwc')
 
 
-def conv2d_forward(x, w, terms):
-    """Stride-1 'same' conv.  x [N,Cin,H,W] (any strides, float32/float16), w [Cout,Cin,k,k] -> y [N,Cout,H,W] in x.dtype, channels-last
+def conv2d_forward(x, w, terms, adjoint=False):
+    """Stride-1 'same' conv (adjoint=True: w is a conv weight [Cin_op... ] used flipped + transposed, i.e. the input-gradient form).  x [N,Cin,H,W] (any strides, float32/float16), w [Cout,Cin,k,k] -> y [N,Cout,H,W] in x.dtype, channels-last
     strides.  terms == 3: error-compensated bf16x3 (fp32-grade); terms == 1: plain bf16 operands, fp32 accumulate."""
     L = _lib.lib()
     N, Cin, H, W = x.shape
-    Cout, _, k, _ = w.shape
-    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(0, 2, 3, 1), terms)
+    if adjoint:     # y = conv(x, flip(w).transpose(0, 1)): operand layout [w.shape[1]][k][k][w.shape[0]]
+        Cout, k = w.shape[1], w.shape[2]
+        xh, xl, wh, wl = _prep(x, w, 'adj1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), terms)
+    else:
+        Cout, _, k, _ = w.shape
+        xh, xl, wh, wl = _prep(x, w, 'fwd', lambda w_: w_.permute(0, 2, 3, 1), terms)
     y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         if terms == 3:
@@ -139,7 +165,7 @@ def conv2d_strided_forward(x, w, stride, padding, terms):
     Cout, _, k, _ = w.shape
     Ho = (H + 2 * padding - k) // 2 + 1
     Wo = (W + 2 * padding - k) // 2 + 1
-    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(0, 2, 3, 1), terms)
+    xh, xl, wh, wl = _prep(x, w, 'fwd', lambda w_: w_.permute(0, 2, 3, 1), terms)
     y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=x.device)
     taps = [(ky - padding, kx - padding, ky * k + kx) for ky in range(k) for kx in range(k)]
     _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, k * k, taps, 2, Ho, Wo, Ho, Wo, 1, 1, 0, 0)
@@ -154,7 +180,7 @@ def conv_transpose2d_s2_forward(x, w, output_padding, terms):
     _, Cout, k, _ = w.shape
     assert k == 3
     Hout, Wout = 2 * H + 1 + output_padding[0], 2 * W + 1 + output_padding[1]
-    xh, xl, wh, wl = _prep(x, w.to(torch.float32).permute(1, 2, 3, 0), terms)           # [Cout,3,3,Cin]
+    xh, xl, wh, wl = _prep(x, w, 'tr2', lambda w_: w_.permute(1, 2, 3, 0), terms)           # [Cout,3,3,Cin]
     alloc = torch.zeros if (output_padding[0] or output_padding[1]) else torch.empty
     y = alloc([N, Hout, Wout, Cout], dtype=torch.float32, device=x.device)
     for a in (0, 1):

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from ..torch_utils.ops import bias_act, conv2d_resample, upfirdn2d
+from ..torch_utils.ops import tc, bias_act, conv2d_resample, upfirdn2d
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -178,7 +178,10 @@ class Conv2dLayer(torch.nn.Module):
         w = self.weight * self.weight_gain
         if self.affine is not None:
             x = (x * (1.0 + self.affine(c).tanh().unsqueeze(2).unsqueeze(3)).to(x.dtype)).to(x.dtype)
-        x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
+        w = w.to(x.dtype)
+        if x.is_cuda and isinstance(self.weight, torch.nn.Parameter):
+            tc.tag_weight_source(w, self.weight, self.weight_gain)     # lets the tensor-core wrappers reuse this parameter's bf16 operands
+        x = conv2d_resample.conv2d_resample(x=x, w=w, f=self.resample_filter, up=self.up, down=self.down,
                                             padding=self.padding, flip_weight=(self.up == 1))
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         b = self.bias.to(x.dtype) if self.bias is not None else None

@@ -80,6 +80,7 @@ class FlatAdam:
             seg[o // self.BLOCK:(o + p.numel() + self.BLOCK - 1) // self.BLOCK] = i
         self.blk_seg = seg.to(dev)
         self.steps = [0] * len(self.params)
+        self._param_ids = {id(p) for p in self.params}
         self.active = set()
         self._hooks = [p.register_post_accumulate_grad_hook(lambda p_, i=i: self.active.add(i)) for i, p in enumerate(self.params) if p.requires_grad]
 
@@ -117,7 +118,7 @@ class FlatAdam:
                                                float(ema_beta) if ema_beta is not None else 0.0,
                                                None if desc is None else self.blk_seg.data_ptr(), _lib.ptr(desc), _lib.stream_ptr())
         _lib.check(rc, 'adam_ema_step')
-        _tc.invalidate_weight_cache()                         # the kernel wrote the parameters behind autograd's version counters
+        _tc.invalidate_weight_cache(self._param_ids)          # the kernel wrote the parameters behind autograd's version counters
         self.active.clear()
         return self.numel
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- one JSON line per run (driver contract, see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train_step|raymarch|ginfer] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train_step|raymarch|ginfer|ops] [--impl ours|reference]
 
 Workloads (BASELINE.json `configs`):
   train_step : configs[1]  ImageNet-256 G+D training step (Gmain + Dmain phases), cmax=1024, 48 samples/ray,
@@ -420,6 +420,73 @@ def run_ginfer(args, rank, world, local):
                 gpu_launches=int(launches * args.steps), clocks=clocks)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# workload: op-level microbench (BASELINE configs[3]: upsample2d / upfirdn2d / bias_act / filtered_lrelu against the HBM roofline)
+def run_ops(args, rank, world, local):
+    """Plugin ops on their own: every case reports algorithmic bytes (input + output once) / time.  The headline
+    value is the byte-weighted aggregate GB/s over all cases; per-case numbers are in config.cases."""
+    up = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    ba = importlib.import_module('3dgp_b200.torch_utils.ops.bias_act')
+    fl = importlib.import_module('3dgp_b200.torch_utils.ops.filtered_lrelu')
+    gp = importlib.import_module('3dgp_b200')
+    dev = torch.device('cuda', local)
+    torch.manual_seed(5 + rank)
+    f4 = up.setup_filter([1, 3, 3, 1], device=dev)
+    f12 = up.setup_filter(np.kaiser(12, 8.0), device=dev)
+    B = args.batch_gpu or 16
+    cases = []
+
+    def add(name, fn, x, note=''):
+        y = fn(x)
+        cases.append(dict(name=name, fn=fn, x=x, bytes=x.numel() * x.element_size() + y.numel() * y.element_size(), note=note))
+        del y
+
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    # the FIR that follows G's up-sampling conv (conv2d_resample.py:119-126): [B,128,513,513] -> 512^2, fp32, channel-minor
+    add('upfirdn2d pad1 gain4 f32 cl [B,128,513,513]', lambda t: up.upfirdn2d(t, f4, padding=1, gain=4), cl(torch.randn(B, 128, 513, 513, device=dev)))
+    add('upfirdn2d pad1 gain4 f32 cl [B,512,129,129]', lambda t: up.upfirdn2d(t, f4, padding=1, gain=4), cl(torch.randn(B, 512, 129, 129, device=dev)))
+    # skip-image up-sampling of the tri-plane decoder (networks_stylegan2.py:268): 96 channels
+    add('upsample2d x2 f32 cl [B,96,256,256]', lambda t: up.upsample2d(t, f4), cl(torch.randn(B, 96, 256, 256, device=dev)))
+    # config 4 proper: fp16 NCHW, r: 64 -> 128 -> 256, C in {512, 256, 128}
+    for C, r in ((512, 64), (256, 128), (128, 256)):
+        add(f'upsample2d x2 f16 nchw [B,{C},{r},{r}]', lambda t: up.upsample2d(t, f4), torch.randn(B, C, r, r, device=dev).half())
+        add(f'downsample2d x2 f16 nchw [B,{C},{2 * r},{2 * r}]', lambda t: up.downsample2d(t, f4), torch.randn(B, C, 2 * r, 2 * r, device=dev).half())
+    bias = torch.randn(512, device=dev)
+    add('bias_act lrelu f16 nchw [B,512,128,128]', lambda t: ba.bias_act(t, bias.half(), act='lrelu', clamp=256), torch.randn(B, 512, 128, 128, device=dev).half())
+    add('bias_act lrelu f32 cl [B,128,512,512]', lambda t: ba.bias_act(t, bias[:128], act='lrelu'), cl(torch.randn(B, 128, 512, 512, device=dev)))
+    add('filtered_lrelu up2 down2 12-tap f16 [B,256,128,128]', lambda t: fl.filtered_lrelu(t, fu=f12, fd=f12, b=bias[:256].half(), up=2, down=2, padding=[11, 10, 11, 10]),
+        torch.randn(B, 256, 128, 128, device=dev).half(), note='composed: upfirdn2d -> bias/lrelu/clamp (+sign bits) -> upfirdn2d')
+    peaks = measured_peaks()
+    c0 = gp._lib.launch_count
+    W_, K_ = max(args.warmup, 3), args.steps
+    tot_b = tot_ms = 0.0
+    rows = []
+    clocks_mon = ClockSampler(local); clocks_mon.start()
+    for c_ in cases:
+        for _ in range(W_):
+            c_['fn'](c_['x'])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(K_):
+            c_['fn'](c_['x'])
+        ev[1].record(); torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / K_
+        gbs = c_['bytes'] / (ms * 1e-3) / 1e9
+        rows.append(dict(op=c_['name'], ms=round(ms, 4), gbs=round(gbs, 1), frac=round(gbs / peaks['hbm_gbs'], 3), **({'note': c_['note']} if c_['note'] else {})))
+        tot_b += c_['bytes']; tot_ms += ms
+    launches = gp._lib.launch_count - c0
+    clocks = clocks_mon.stop()
+    agg = tot_b / (tot_ms * 1e-3) / 1e9
+    return dict(metric='plugin ops aggregate GB/s (algorithmic bytes of all cases / total time)', value=agg * world, unit='GB/s', ms_per_step=tot_ms, dtype='f16 / f32',
+                config=dict(workload='ops (BASELINE configs[3]: op-level upfirdn2d / bias_act / filtered_lrelu)', batch_per_gpu=B,
+                            l2='every case moves >= 130 MB (> the 126 MB L2)', cases=rows, parallelism=f'replicas x{world}'),
+                roofline=dict(bound='hbm', achieved=agg, peak=peaks['hbm_gbs'], unit='GB/s', frac=agg / peaks['hbm_gbs'], traffic=None,
+                              kernel='upfirdn2d / bias_act kernels (byte-weighted aggregate)', peak_source=peaks['source']),
+                e2e=dict(value=agg * world, unit='GB/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0, note='device-resident microbench: no host leg'),
+                gpu_launches=int(launches), clocks=clocks)
+
+
 def cpu_train_step(small=False, budget_s=25.0):
     """Reference algorithm on the host cores (oracle port, torch-CPU / numpy, all threads) for the training-step metric.
     Bounded sample: ONE image through the generator forward (mapping + tri-plane decoder + ray-march at the training patch
@@ -482,7 +549,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default=os.environ.get('GP3D_BENCH_WORKLOAD', 'train_step'), choices=['train_step', 'raymarch', 'ginfer'])
+    ap.add_argument('--workload', default=os.environ.get('GP3D_BENCH_WORKLOAD', 'train_step'), choices=['train_step', 'raymarch', 'ginfer', 'ops'])
     ap.add_argument('--batch-gpu', type=int, default=0)
     ap.add_argument('--mlp-mode', type=int, default=2, help='tri-plane MLP arithmetic: 0 fp32 SIMT (v1 kernel), 1 TF32 mma, 2 3xTF32 mma (default)')
     ap.add_argument('--planes-fp16', action='store_true')
@@ -517,7 +584,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl')
-    res = {'train_step': run_train_step, 'raymarch': run_raymarch, 'ginfer': run_ginfer}[args.workload](args, rank, world, local)
+    res = {'train_step': run_train_step, 'raymarch': run_raymarch, 'ginfer': run_ginfer, 'ops': run_ops}[args.workload](args, rank, world, local)
     if rank == 0:
         line = dict(metric=res['metric'], value=res['value'], unit=res['unit'], n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
@@ -527,7 +594,7 @@ def main():
         if 'forward_backward' in res:
             line['forward_backward'] = res['forward_backward']
         if world == 1 and not args.no_cpu_baseline:
-            if args.workload != 'ginfer':
+            if args.workload not in ('ginfer', 'ops'):
                 line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)
         print(json.dumps(line))
     if world > 1:

@@ -161,6 +161,11 @@ int gp3d_demod_act(const void* x, const void* d, const void* noise, int noise_pe
  */
 int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample, const float* b,
                        float* dc, float* g_d, float* g_b, float* g_ns, int N, int HW, int C, int act, float alpha, float gain, void* stream);
+/* gp3d_demod_act_bwd writing dc either as float32 (dc != NULL) or directly as the bf16 (hi, lo) operand pair of the tensor-core
+ * input-gradient / weight-gradient kernels (dc_hi, dc_lo != NULL, [N][HW][C_pad] with channels [C, C_pad) zero-filled; C_pad - C <= C). */
+int gp3d_demod_act_bwd_split(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample,
+                             const float* b, float* dc, void* dc_hi, void* dc_lo, int C_pad, float* g_d, float* g_b, float* g_ns,
+                             int N, int HW, int C, int act, float alpha, float gain, void* stream);
 int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* dx, float* g_s, int N, int HW, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -208,6 +213,22 @@ int gp3d_conv2d_nhwc_bf16(const void* x, const void* w, float* y, int N, int H, 
  */
 int gp3d_conv2d_nhwc_bf16x3(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                             int Cin, int Cout, int ksize, int accumulate, void* stream);
+
+/* bf16x3 'same' convolution with the rest of the modulated-conv layer fused into the TMEM -> HBM epilogue
+ * (reference networks_stylegan2.py:71 `fma(x, dcoefs, noise)` and :144 `bias_act(x, b, act, gain)`, no clamp):
+ *   y[n][oy][ox][co] = act(conv * dcoef[n][co] + noise[n?][oy][ox] + bias[co]) * gain
+ * dcoef / noise / bias may each be NULL; noise is already multiplied by noise_strength, [N][H][W] if noise_per_sample else [H][W].
+ */
+typedef struct gp3d_conv_epilogue {
+    const float* dcoef;
+    const float* noise;
+    const float* bias;
+    int noise_per_sample;
+    int act;            /* 1 linear, 3 lrelu */
+    float alpha, gain;
+} gp3d_conv_epilogue;
+int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                                int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
 
 /* General tap convolution on the same tcgen05 pipeline -- the building block of the strided forms:
  *   y[n][iy*osy+oy0][ix*osx+ox0][co] (+)= sum_t sum_ci x[n][iy*in_stride+dy_t][ix*in_stride+dx_t][ci] * w[co][slab_t][ci]

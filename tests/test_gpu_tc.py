@@ -134,7 +134,7 @@ def test_transposed_conv_stride2_polyphase_and_its_gradients(N, Cin, Cout, H):
         assert rel(outs[0][i], outs[1][i]) < 1e-4, (i, rel(outs[0][i], outs[1][i]))
 
 
-@pytest.mark.parametrize('N,Cin,Cout,H,dtype', [(2, 128, 128, 36, torch.float32), (4, 64, 256, 12, torch.float32), (2, 128, 128, 20, torch.float16)])
+@pytest.mark.parametrize('N,Cin,Cout,H,dtype', [(2, 128, 128, 36, torch.float32), (4, 64, 256, 12, torch.float32), (2, 128, 128, 20, torch.float16), (3, 64, 512, 12, torch.float16)])
 def test_strided_conv_and_its_transposed_gradient(N, Cin, Cout, H, dtype):
     """D's down-sampling conv1 (FIR-padded input, stride-2 conv, conv2d_resample.py:106-109) and its input gradient (polyphase with output padding)."""
     cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
@@ -280,3 +280,50 @@ def test_fused_modconv_layer_at_the_coarsest_resolutions(res, up):
     assert rel(out[0][0], out[1][0]) < 1e-4
     for a, b in zip(out[0][1], out[1][1]):
         assert rel(a, b) < 3e-4, rel(a, b)
+
+
+@pytest.mark.parametrize('Cout,act,with_d,nps', [(128, 3, True, 1), (96, 1, False, 0), (256, 3, True, 0)])
+def test_conv_fused_epilogue_matches_conv_then_demod_act(Cout, act, with_d, nps):
+    """gp3d_conv2d_nhwc_bf16x3_act == gp3d_conv2d_nhwc_bf16x3 followed by gp3d_demod_act (bit-for-bit: same fma order)."""
+    import ctypes
+    tc = _tc()
+    _lib = importlib.import_module('3dgp_b200._lib')
+    L = _lib.lib()
+    torch.manual_seed(7)
+    N, H, W, Cin, k = 3, 20, 24, 64, 3
+    x = torch.randn(N, H, W, Cin, device='cuda'); w = torch.randn(Cout, k, k, Cin, device='cuda') / (Cin * 9) ** 0.5
+    xh, xl = tc.split_bf16(x); wh, wl = tc.split_bf16(w)
+    d = (torch.rand(N, Cout, device='cuda') + 0.5) if with_d else None
+    nz = torch.randn(N if nps else 1, H, W, device='cuda') * 0.3
+    b = torch.randn(Cout, device='cuda') * 0.1
+    c = torch.empty(N, H, W, Cout, device='cuda'); y_ref = torch.empty_like(c); y = torch.empty_like(c)
+    s = _lib.stream_ptr()
+    _lib.check(L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), c.data_ptr(), N, H, W, Cin, Cout, k, 0, s), 'conv')
+    _lib.check(L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), nz.data_ptr(), nps, b.data_ptr(), y_ref.data_ptr(), 0, N, Cout, H * W, 1, act, 0.2, 1.4142135, -1.0, s), 'demod_act')
+    epi = _lib.ConvEpilogue(_lib.ptr(d), nz.data_ptr(), b.data_ptr(), nps, act, 0.2, 1.4142135)
+    _lib.check(L.gp3d_conv2d_nhwc_bf16x3_act(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, ctypes.byref(epi), s), 'conv_act')
+    assert torch.equal(y, y_ref)
+
+
+def test_demod_act_bwd_split_outputs_equal_split_of_float_outputs():
+    tc = _tc()
+    _lib = importlib.import_module('3dgp_b200._lib')
+    L = _lib.lib()
+    torch.manual_seed(8)
+    N, HW, C, Cp = 2, 37, 96, 128
+    dy = torch.randn(N, HW, C, device='cuda'); y = torch.randn(N, HW, C, device='cuda'); d = torch.rand(N, C, device='cuda') + 0.5
+    b = torch.randn(C, device='cuda') * 0.1
+    dc = torch.empty_like(dy)
+    outs = []
+    for split in (False, True):
+        g_d = torch.zeros_like(d); g_b = torch.zeros(C, device='cuda')
+        hi = torch.full([N, HW, Cp], 7.0, dtype=torch.bfloat16, device='cuda'); lo = torch.full_like(hi, 7.0)
+        rc = L.gp3d_demod_act_bwd_split(dy.data_ptr(), y.data_ptr(), d.data_ptr(), None, None, 0, b.data_ptr(), None if split else dc.data_ptr(),
+                                        hi.data_ptr() if split else None, lo.data_ptr() if split else None, Cp, g_d.data_ptr(), g_b.data_ptr(), None,
+                                        N, HW, C, 3, 0.2, 1.4142135, _lib.stream_ptr())
+        _lib.check(rc, 'demod_act_bwd_split')
+        outs.append((g_d, g_b, hi, lo))
+    rh, rl = tc.split_bf16(dc, pad_to=Cp)
+    assert torch.equal(outs[1][2], rh) and torch.equal(outs[1][3], rl)
+    assert torch.equal(outs[0][0], outs[1][0]) or torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)
