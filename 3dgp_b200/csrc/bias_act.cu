@@ -74,36 +74,67 @@ __device__ __forceinline__ float bias_act_one(int G, float x, float b, float xre
     return y;
 }
 
-// BMODE: 0 = no bias, 1 = one bias value per 16B vector (stepB % VEC == 0), 2 = per element.
-template <class T, int A, int BMODE>
-__global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
+// BMODE: 0 = no bias, 1 = one bias value per 16B vector (stepB % VEC == 0), 2 = per element (generic),
+//        3 = channel-minor (stepB == 1, sizeB % VEC == 0): the vector's bias values are VEC consecutive entries of b.
+// IDX: uint32_t when numel < 2^32 (the per-vector bias index costs one 32-bit division instead of two 64-bit ones).
+// Each thread keeps kUnroll independent 16-byte vectors of every input stream in flight: one vector per thread leaves a B200 SM
+// (2048 threads, ~1 us HBM latency, 44 B/ns per SM) short of the bytes in flight the roofline needs.
+// FWD: only x (and b) are read (xref, yref, dy absent: the grad == 0 call) -- four vectors in flight at 4 CTAs / SM; the general form
+// carries up to four input streams and keeps two vectors of each in flight.
+template <bool FWD> struct ba_unroll { static constexpr int value = FWD ? 4 : 2; };
+
+template <class T, int A, int BMODE, class IDX, bool FWD>
+__global__ void __launch_bounds__(256, FWD ? 4 : 3) bias_act_vec_kernel(BiasActParams p) {
     constexpr int VEC = vec16<T>::N;
-    const int64_t nvec = p.numel / VEC;
-    const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = (const T*)p.xref;
-    const T* yr = (const T*)p.yref; const T* dyp = (const T*)p.dy; T* y = (T*)p.y;
+    constexpr int kUnroll = ba_unroll<FWD>::value;
+    const IDX nvec = (IDX)(p.numel / VEC);
+    const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = FWD ? nullptr : (const T*)p.xref;
+    const T* yr = FWD ? nullptr : (const T*)p.yref; const T* dyp = FWD ? nullptr : (const T*)p.dy; T* y = (T*)p.y;
     const int G = p.grad;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i0 = v * VEC;
-        vec16<T> vx, vxr, vyr, vdy, vy;
-        float fx[VEC], fxr[VEC], fyr[VEC], fdy[VEC], fy[VEC];
-        vx.load(x + i0); vx.unpack(fx);
-        if (xr) { vxr.load(xr + i0); vxr.unpack(fxr); }
-        if (yr) { vyr.load(yr + i0); vyr.unpack(fyr); }
-        if (dyp) { vdy.load(dyp + i0); vdy.unpack(fdy); }
-        float bv = 0.f;
-        if (BMODE == 1) bv = io_traits<T>::ld(b + (i0 / p.stepB) % p.sizeB);
+    const IDX stride = (IDX)gridDim.x * blockDim.x;
+    const IDX stepB = (IDX)p.stepB, sizeB = (IDX)p.sizeB;
+    for (IDX v0 = (IDX)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * kUnroll) {
+        vec16<T> vx[kUnroll], vxr[kUnroll], vyr[kUnroll], vdy[kUnroll], vb[kUnroll];
+        float bs[kUnroll];
 #pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            float bb = bv;
-            if (BMODE == 2) bb = io_traits<T>::ld(b + ((i0 + k) / p.stepB) % p.sizeB);
-            fy[k] = bias_act_one<A>(G, fx[k], bb, xr ? fxr[k] : 0.f, yr ? fyr[k] : 0.f, dyp ? fdy[k] : 1.f,
-                                    p.alpha, p.gain, p.clamp);
+        for (int u = 0; u < kUnroll; u++) {                    // all loads first
+            const IDX v = v0 + (IDX)u * stride;
+            if (v < nvec) {
+                const IDX i0 = v * VEC;
+                vx[u].load(x + i0);
+                if (xr) vxr[u].load(xr + i0);
+                if (yr) vyr[u].load(yr + i0);
+                if (dyp) vdy[u].load(dyp + i0);
+                if (BMODE == 1) bs[u] = io_traits<T>::ld(b + (i0 / stepB) % sizeB);
+                if (BMODE == 3) vb[u].load(b + i0 % sizeB);
+            }
         }
-        vy.pack(fy); vy.store(y + i0);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const IDX v = v0 + (IDX)u * stride;
+            if (v < nvec) {
+                const IDX i0 = v * VEC;
+                float fx[VEC], fxr[VEC], fyr[VEC], fdy[VEC], fy[VEC], fb[VEC];
+                vx[u].unpack(fx);
+                if (xr) vxr[u].unpack(fxr);
+                if (yr) vyr[u].unpack(fyr);
+                if (dyp) vdy[u].unpack(fdy);
+                if (BMODE == 3) vb[u].unpack(fb);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    float bb = 0.f;
+                    if (BMODE == 1) bb = bs[u];
+                    if (BMODE == 2) bb = io_traits<T>::ld(b + ((i0 + k) / stepB) % sizeB);
+                    if (BMODE == 3) bb = fb[k];
+                    fy[k] = bias_act_one<A>(G, fx[k], bb, xr ? fxr[k] : 0.f, yr ? fyr[k] : 0.f, dyp ? fdy[k] : 1.f, p.alpha, p.gain, p.clamp);
+                }
+                vec16<T> vy; vy.pack(fy); vy.store(y + i0);
+            }
+        }
     }
     // scalar tail (numel % VEC elements), handled by the first few threads of block 0
     if (blockIdx.x == 0) {
-        int64_t i = nvec * VEC + threadIdx.x;
+        int64_t i = (int64_t)nvec * VEC + threadIdx.x;
         if (i < p.numel) {
             float bb = (BMODE != 0) ? io_traits<T>::ld(b + (i / p.stepB) % p.sizeB) : 0.f;
             float r = bias_act_one<A>(G, io_traits<T>::ld(x + i), bb, xr ? io_traits<T>::ld(xr + i) : 0.f,
@@ -139,11 +170,16 @@ int launch_bias_act(const BiasActParams& p, cudaStream_t stream) {
         return 0;
     }
     int64_t nvec = p.numel / VEC;
-    int grid = gp3d_grid_for(nvec > 0 ? nvec : 1, 256, 8);
-    int bmode = (!p.b) ? 0 : ((p.stepB % VEC == 0) ? 1 : 2);
-    if (bmode == 0) bias_act_vec_kernel<T, A, 0><<<grid, 256, 0, stream>>>(p);
-    else if (bmode == 1) bias_act_vec_kernel<T, A, 1><<<grid, 256, 0, stream>>>(p);
-    else bias_act_vec_kernel<T, A, 2><<<grid, 256, 0, stream>>>(p);
+    const bool fwd = !p.xref && !p.yref && !p.dy;
+    const int kUnroll = fwd ? 4 : 2;
+    int grid = gp3d_grid_for(nvec > 0 ? (nvec + kUnroll - 1) / kUnroll : 1, 256, fwd ? 4 : 3);
+    int bmode = (!p.b) ? 0 : (p.stepB % VEC == 0) ? 1 : (p.stepB == 1 && p.sizeB % VEC == 0 && gp3d_aligned16(p.b)) ? 3 : 2;
+    const bool small = p.numel < (int64_t)4294967295LL - (int64_t)VEC * 256 * 8 * GP3D_NUM_SMS * 4;   // v0 + u*stride stays below 2^32
+#define GP3D_BA(M) do { if (small && fwd) bias_act_vec_kernel<T, A, M, uint32_t, true><<<grid, 256, 0, stream>>>(p); \
+                        else if (small) bias_act_vec_kernel<T, A, M, uint32_t, false><<<grid, 256, 0, stream>>>(p); \
+                        else bias_act_vec_kernel<T, A, M, int64_t, false><<<grid, 256, 0, stream>>>(p); } while (0)
+    if (bmode == 0) GP3D_BA(0); else if (bmode == 1) GP3D_BA(1); else if (bmode == 3) GP3D_BA(3); else GP3D_BA(2);
+#undef GP3D_BA
     return 0;
 }
 

@@ -51,6 +51,7 @@ template <> struct vec16<float> {
     static constexpr int N = 4;
     float4 v;
     __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
     __device__ __forceinline__ void unpack(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
     __device__ __forceinline__ void pack(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
@@ -59,6 +60,7 @@ template <> struct vec16<__half> {
     static constexpr int N = 8;
     uint4 v;
     __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
     __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = v; }
     __device__ __forceinline__ void unpack(float* f) const {
         const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -75,6 +77,7 @@ template <> struct vec16<__nv_bfloat16> {
     static constexpr int N = 8;
     uint4 v;
     __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
     __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
     __device__ __forceinline__ void unpack(float* f) const {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);

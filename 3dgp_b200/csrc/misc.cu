@@ -207,6 +207,61 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x
     }
 }
 
+// Division-free form for the common channel counts (C_out / 8 divides 256): grid (pixel blocks, N); a thread keeps ONE 8-channel group
+// (its styles stay in registers) and walks the pixels of image blockIdx.y, four independent pixels in flight.
+template <class T>
+__global__ void __launch_bounds__(256) split_bf16_cm_kernel(const T* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
+                                                            __nv_bfloat16* __restrict__ lo, int HW, int C, int Cp) {
+    constexpr int U = 4;
+    const int CV = Cp >> 3, PL = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int n = blockIdx.y, c0 = cv * 8;
+    const bool pad = c0 >= C;
+    float sv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sv[k] = 1.f;
+    if (s && !pad) {
+        const float4 sa = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0), sb = *reinterpret_cast<const float4*>(s + (int64_t)n * C + c0 + 4);
+        sv[0] = sa.x; sv[1] = sa.y; sv[2] = sa.z; sv[3] = sa.w; sv[4] = sb.x; sv[5] = sb.y; sv[6] = sb.z; sv[7] = sb.w;
+    }
+    const T* xb = x + (int64_t)n * HW * C + c0;
+    __nv_bfloat16* hb = hi + (int64_t)n * HW * Cp + c0;
+    __nv_bfloat16* lb = lo ? lo + (int64_t)n * HW * Cp + c0 : nullptr;
+    for (int px0 = blockIdx.x * PL * U + pl; px0 < HW; px0 += gridDim.x * PL * U) {
+        float f[U][8];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int px = px0 + u * PL;
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[u][k] = 0.f;
+            if (px < HW && !pad) {
+                if (sizeof(T) == 4) {
+                    const float* xp = reinterpret_cast<const float*>(xb) + (int64_t)px * C;
+                    const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
+                    f[u][0] = a.x; f[u][1] = a.y; f[u][2] = a.z; f[u][3] = a.w; f[u][4] = b.x; f[u][5] = b.y; f[u][6] = b.z; f[u][7] = b.w;
+                } else {
+                    vec16<__half> t; t.load(reinterpret_cast<const __half*>(xb) + (int64_t)px * C); t.unpack(f[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int px = px0 + u * PL;
+            if (px < HW) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) f[u][k] *= sv[k];
+                vec16<__nv_bfloat16> h; h.pack(f[u]); h.store(hb + (int64_t)px * Cp);
+                if (lb) {
+                    float hf[8], r[8]; h.unpack(hf);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) r[k] = f[u][k] - hf[k];
+                    vec16<__nv_bfloat16> l; l.pack(r); l.store(lb + (int64_t)px * Cp);
+                }
+            }
+        }
+    }
+}
+
 template <class T>
 int launch_modulate(const void* x, const void* s, void* y, int N, int C, int HW, int cl, cudaStream_t st) {
     constexpr int VEC = vec16<T>::N;
@@ -218,6 +273,46 @@ int launch_modulate(const void* x, const void* s, void* y, int N, int C, int HW,
     return 0;
 }
 
+// Channel-minor float32 fast path of demod_act (C / 4 divides 256): no index divisions, demodulation / bias vectors in registers,
+// four independent pixels in flight per thread.  Same arithmetic (fma order) as demod_act_kernel.
+template <int ACT>
+__global__ void __launch_bounds__(256) demod_act_cm_kernel(const float* __restrict__ x, const float* __restrict__ d, const float* __restrict__ noise,
+                                                           int noise_per_sample, const float* __restrict__ b, float* __restrict__ y,
+                                                           int C, int HW, float alpha, float gain, float clamp) {
+    constexpr int U = 4;
+    const int CV = C >> 2, PL = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int n = blockIdx.y;
+    const float4 dv = d ? *reinterpret_cast<const float4*>(d + (int64_t)n * C + 4 * cv) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 bv = b ? *reinterpret_cast<const float4*>(b + 4 * cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xb = x + (int64_t)n * HW * C + 4 * cv;
+    float* yb = y + (int64_t)n * HW * C + 4 * cv;
+    const float* nb = noise ? noise + (noise_per_sample ? (int64_t)n * HW : 0) : nullptr;
+    for (int px0 = blockIdx.x * PL * U + pl; px0 < HW; px0 += gridDim.x * PL * U) {
+        float4 v[U]; float nz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int px = px0 + u * PL;
+            nz[u] = 0.f;
+            if (px < HW) { v[u] = *reinterpret_cast<const float4*>(xb + (int64_t)px * C); if (nb) nz[u] = nb[px]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int px = px0 + u * PL;
+            if (px < HW) {
+                float t[4] = {fmaf(v[u].x, dv.x, nz[u]) + bv.x, fmaf(v[u].y, dv.y, nz[u]) + bv.y, fmaf(v[u].z, dv.z, nz[u]) + bv.z, fmaf(v[u].w, dv.w, nz[u]) + bv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (ACT == 3) t[k] = (t[k] > 0.f) ? t[k] : t[k] * alpha;
+                    t[k] *= gain;
+                    if (clamp >= 0.f) t[k] = fminf(fmaxf(t[k], -clamp), clamp);
+                }
+                *reinterpret_cast<float4*>(yb + (int64_t)px * C) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    }
+}
+
 template <class T>
 int launch_demod(const void* x, const void* d, const void* noise, int nps, const void* b, void* y, int N, int C, int HW,
                  int cl, int act, float alpha, float gain, float clamp, cudaStream_t st) {
@@ -225,6 +320,17 @@ int launch_demod(const void* x, const void* d, const void* noise, int nps, const
     const int64_t total = (int64_t)N * C * HW;
     if (total % VEC || (!cl && HW % VEC) || (cl && C % VEC) || !gp3d_aligned16(x) || !gp3d_aligned16(y)) return GP3D_E_UNSUPPORTED;
     const int grid = gp3d_grid_for(total / VEC, 256, 8);
+    if (sizeof(T) == 4 && cl && C % 4 == 0 && (C / 4) <= 256 && 256 % (C / 4) == 0 && N <= 65535 && (!d || gp3d_aligned16(d)) && (!b || gp3d_aligned16(b))) {
+        const int PL = 256 / (C / 4);
+        int64_t gx = ((int64_t)HW + PL * 4 - 1) / (PL * 4);
+        const int64_t cap = ((int64_t)GP3D_NUM_SMS * 8 + N - 1) / N;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        const dim3 g2((unsigned)gx, (unsigned)N);
+        if (act == 3) demod_act_cm_kernel<3><<<g2, 256, 0, st>>>((const float*)x, (const float*)d, (const float*)noise, nps, (const float*)b, (float*)y, C, HW, alpha, gain, clamp);
+        else demod_act_cm_kernel<1><<<g2, 256, 0, st>>>((const float*)x, (const float*)d, (const float*)noise, nps, (const float*)b, (float*)y, C, HW, alpha, gain, clamp);
+        return 0;
+    }
 #define GP3D_DEMOD(CLV, ACTV) demod_act_kernel<T, CLV, ACTV><<<grid, 256, 0, st>>>((const T*)x, (const T*)d, (const T*)noise, nps, (const T*)b, (T*)y, N, C, HW, alpha, gain, clamp)
     if (cl) { if (act == 3) GP3D_DEMOD(true, 3); else GP3D_DEMOD(true, 1); }
     else    { if (act == 3) GP3D_DEMOD(false, 3); else GP3D_DEMOD(false, 1); }
@@ -289,6 +395,19 @@ extern "C" int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s,
     const int64_t nvec = (int64_t)N * HW * C_out / 8;
     const int grid = gp3d_grid_for(nvec, 256, 8);
     cudaStream_t st = (cudaStream_t)stream;
+    GP3D_CHECK_ARG(src_dtype == GP3D_F32 || src_dtype == GP3D_F16, "split_bf16: source must be float32 or float16");
+    const int CV = C_out / 8;
+    if (CV <= 256 && 256 % CV == 0 && N <= 65535) {
+        const int PL = 256 / CV;
+        int64_t gx = ((int64_t)HW + PL * 4 - 1) / (PL * 4);
+        const int64_t cap = ((int64_t)GP3D_NUM_SMS * 8 + N - 1) / N;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        const dim3 g2((unsigned)gx, (unsigned)N);
+        if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float><<<g2, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
+        else split_bf16_cm_kernel<__half><<<g2, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
+        GP3D_RETURN_LAUNCH();
+    }
     if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     else if (src_dtype == GP3D_F16) split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     else { gp3d_set_error("split_bf16: source must be float32 or float16"); return GP3D_E_BADARG; }
@@ -407,12 +526,20 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pl < PL && cv < CV_all) {
             const float4 sv = *reinterpret_cast<const float4*>(s + (int64_t)n * C + 4 * cv);
-            for (int px = p0 + pl; px < p1; px += PL) {
-                const int64_t off = ((int64_t)n * HW + px) * C + 4 * cv;
-                const float4 g = *reinterpret_cast<const float4*>(dxs + off);
-                const float4 xv = *reinterpret_cast<const float4*>(x + off);
-                acc.x += g.x * xv.x; acc.y += g.y * xv.y; acc.z += g.z * xv.z; acc.w += g.w * xv.w;
-                *reinterpret_cast<float4*>(dx + off) = make_float4(g.x * sv.x, g.y * sv.y, g.z * sv.z, g.w * sv.w);
+            for (int px0 = p0 + pl; px0 < p1; px0 += 2 * PL) {      // two independent pixels in flight
+                const int px1 = px0 + PL;
+                const bool two = px1 < p1;
+                const int64_t off0 = ((int64_t)n * HW + px0) * C + 4 * cv, off1 = ((int64_t)n * HW + px1) * C + 4 * cv;
+                const float4 g0 = *reinterpret_cast<const float4*>(dxs + off0);
+                const float4 x0 = *reinterpret_cast<const float4*>(x + off0);
+                float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = g1;
+                if (two) { g1 = *reinterpret_cast<const float4*>(dxs + off1); x1 = *reinterpret_cast<const float4*>(x + off1); }
+                acc.x += g0.x * x0.x; acc.y += g0.y * x0.y; acc.z += g0.z * x0.z; acc.w += g0.w * x0.w;
+                *reinterpret_cast<float4*>(dx + off0) = make_float4(g0.x * sv.x, g0.y * sv.y, g0.z * sv.z, g0.w * sv.w);
+                if (two) {
+                    acc.x += g1.x * x1.x; acc.y += g1.y * x1.y; acc.z += g1.z * x1.z; acc.w += g1.w * x1.w;
+                    *reinterpret_cast<float4*>(dx + off1) = make_float4(g1.x * sv.x, g1.y * sv.y, g1.z * sv.z, g1.w * sv.w);
+                }
             }
         }
         block_channel_reduce_add(acc, red_smem, cvl, CV, PL, pl, g_s + (int64_t)n * C + 4 * cbase);
@@ -420,7 +547,7 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
 }
 
 static int reduce_chunks(int N, int HW) {
-    int chunks = (GP3D_NUM_SMS * 4 + N - 1) / N;
+    int chunks = (GP3D_NUM_SMS * 8 + N - 1) / N;      // 8 CTAs of 256 threads per SM: enough loads in flight for the HBM roofline
     if (chunks > HW) chunks = HW;
     if (chunks < 1) chunks = 1;
     return chunks;

@@ -16,6 +16,7 @@
 //   * C-minor (channels-last): each thread produces one 16-byte channel vector of one pixel; every tap is a
 //     coalesced 16-byte load.
 //   * any-stride scalar fallback.
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -110,6 +111,64 @@ __global__ void __launch_bounds__(256) upfirdn2d_wminor_kernel(UpfirdnParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// W-minor tiled kernel (NCHW planes, any dtype / up / down / filter): a CTA stages the input window of a 64 x 16 output tile of one
+// (n, c) plane in shared memory as float (coalesced row loads, zero-filled outside the image = the padding rule), then every thread
+// evaluates four outputs of one column from shared memory.  The window is read from HBM once (halo excepted) instead of once per tap.
+constexpr int kTOW = 64, kTOH = 16;
+
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_wminor_tiled_kernel(UpfirdnParams p, int TIW, int TIH) {
+    extern __shared__ float tsm[];
+    const int taps = p.fh * p.fw;
+    float* sf = tsm;
+    float* st = tsm + ((taps + 3) & ~3);
+    stage_filter(sf, p);
+    int64_t tile = blockIdx.x;
+    const int tx = (int)(tile % p.tilesX); tile /= p.tilesX;
+    const int ty = (int)(tile % p.tilesY); tile /= p.tilesY;
+    const int nc = (int)tile;
+    const int n = nc / p.C, c = nc - n * p.C;
+    const int ox_t0 = tx * kTOW, oy_t0 = ty * kTOH;
+    const int ix_t0 = ceil_div_s(ox_t0 * p.downx - p.padx0, p.upx), iy_t0 = ceil_div_s(oy_t0 * p.downy - p.pady0, p.upy);
+    const T* xb = (const T*)p.x + n * p.xsN + c * p.xsC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < TIH; r += 8) {
+        const int iy = iy_t0 + r;
+        const bool rowin = (iy >= 0 && iy < p.inH);
+        const T* xr = xb + (int64_t)iy * p.xsH;
+        for (int cc = lane; cc < TIW; cc += 32) {
+            const int ix = ix_t0 + cc;
+            st[r * TIW + cc] = (rowin && ix >= 0 && ix < p.inW) ? io_traits<T>::ld(xr + ix) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & (kTOW - 1), ly0 = threadIdx.x >> 6;
+    const int ox = ox_t0 + lx;
+    if (ox >= p.outW) return;
+    const int bx = ox * p.downx - p.padx0;
+    const int ixa = ceil_div_s(bx, p.upx);
+    const int kx0 = ixa * p.upx - bx;
+    const int cx = ixa - ix_t0;
+    T* yb = (T*)p.y + n * p.ysN + c * p.ysC + ox;
+#pragma unroll
+    for (int rr = 0; rr < kTOH / 4; rr++) {
+        const int oy = oy_t0 + ly0 + 4 * rr;
+        if (oy >= p.outH) continue;
+        const int by = oy * p.downy - p.pady0;
+        const int iya = ceil_div_s(by, p.upy);
+        float acc = 0.f;
+        int ry = iya - iy_t0;
+        for (int ky = iya * p.upy - by; ky < p.fh; ky += p.upy, ry++) {
+            const float* row = st + ry * TIW + cx;
+            const float* fr = sf + ky * p.fw;
+            int q = 0;
+            for (int kx = kx0; kx < p.fw; kx += p.upx, q++) acc = fmaf(row[q], fr[kx], acc);
+        }
+        io_traits<T>::st(yb + (int64_t)oy * p.ysH, acc * p.gain);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // C-minor (channels-last) kernel: one 16-byte channel vector per thread.
 template <class T>
 __global__ void __launch_bounds__(256) upfirdn2d_cminor_kernel(UpfirdnParams p) {
@@ -151,57 +210,82 @@ __global__ void __launch_bounds__(256) upfirdn2d_cminor_kernel(UpfirdnParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// C-minor register-tiled kernel for the 4x4 [1,3,3,1] cases that dominate G and D (fp32): each thread produces PX consecutive
-// output pixels of one row for one 16-byte channel vector, loading every needed input vector ONCE (7 x 4 loads for 4 outputs of the
-// up=1 FIR instead of 64).  Grid: (x-groups, 1, N*outH); threads: channel vector fastest -> 512 contiguous bytes per warp and pixel.
-template <int UP, int DOWN, int PX>
+// C-minor register-tiled kernel for the 4x4 [1,3,3,1] cases that dominate G and D (fp32): each thread produces a PX x PY patch of output
+// pixels for one 16-byte channel vector and walks the input rows the patch touches ONCE (up=1: 7 x 7 loads for 16 outputs, i.e. 3 loads
+// per output instead of the 16 of a tap-by-tap kernel); the NIX loads of a row are independent, which is what keeps enough bytes in
+// flight for the HBM roofline.  Grid: (x-groups, 1, N * ceil(outH / PY)); threads: channel vector fastest -> 512 contiguous bytes per
+// warp and pixel.
+template <class T, int UP, int DOWN, int PX, int PY>
 __global__ void __launch_bounds__(256) upfirdn2d_cminor4_kernel(UpfirdnParams p) {
     constexpr int FS = 4;
+    constexpr int VEC = vec16<T>::N;                                 // 4 float / 8 half channels per thread
     constexpr int NIX = ((PX - 1) * DOWN + FS - 1) / UP + 2;       // input columns that can touch PX outputs
     __shared__ float sf[FS * FS];
     stage_filter(sf, p);
-    const int CV = p.C / 4;
+    const int CV = p.C / VEC;
     const int cv_per = CV < 256 ? CV : 256;
     const int groups = 256 / cv_per;                                 // x-groups per block
     const int cvl = threadIdx.x % cv_per, xg = threadIdx.x / cv_per;
-    const int n = blockIdx.z / p.outH, oy = blockIdx.z - n * p.outH;
+    const int rows = (p.outH + PY - 1) / PY;
+    const int n = blockIdx.z / rows, oy0 = (blockIdx.z - n * rows) * PY;
     const int ox0 = (blockIdx.x * groups + xg) * PX;
     if (xg >= groups || ox0 >= p.outW) return;
-    const int by = oy * DOWN - p.pady0;
-    int iy0 = ceil_div_s(by, UP); if (iy0 < 0) iy0 = 0;
-    int iy1 = floor_div(by + FS - 1, UP); if (iy1 > p.inH - 1) iy1 = p.inH - 1;
+    const int by0 = oy0 * DOWN - p.pady0;
+    int iy0 = ceil_div_s(by0, UP); if (iy0 < 0) iy0 = 0;
+    int iy1 = floor_div(by0 + (PY - 1) * DOWN + FS - 1, UP); if (iy1 > p.inH - 1) iy1 = p.inH - 1;
     const int bx0 = ox0 * DOWN - p.padx0;
     const int ixb = ceil_div_s(bx0, UP);                             // first input column that can contribute to output ox0
     for (int cv = cvl; cv < CV; cv += cv_per) {
-        const float* xb = (const float*)p.x + (int64_t)n * p.xsN + 4 * cv;
-        float4 acc[PX];
+        const T* xb = (const T*)p.x + (int64_t)n * p.xsN + VEC * cv;
+        float acc[PY][PX][VEC];
 #pragma unroll
-        for (int j = 0; j < PX; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < PY; i++)
+#pragma unroll
+            for (int j = 0; j < PX; j++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) acc[i][j][k] = 0.f;
         for (int iy = iy0; iy <= iy1; iy++) {
-            const float* fr = sf + (iy * UP - by) * FS;
-            const float* xr = xb + (int64_t)iy * p.xsH;
+            const T* xr = xb + (int64_t)iy * p.xsH;
+            vec16<T> v[NIX];
 #pragma unroll
             for (int t = 0; t < NIX; t++) {
                 const int ix = ixb + t;
-                if (ix < 0 || ix >= p.inW) continue;
-                const float4 v = *reinterpret_cast<const float4*>(xr + (int64_t)ix * p.xsW);
+                if (ix >= 0 && ix < p.inW) v[t].load(xr + (int64_t)ix * p.xsW);
+                else v[t].zero();
+            }
 #pragma unroll
-                for (int j = 0; j < PX; j++) {
-                    const int kx = ix * UP - (bx0 + j * DOWN);
-                    if (kx >= 0 && kx < FS) {
-                        const float w = fr[kx];
-                        acc[j].x = fmaf(v.x, w, acc[j].x); acc[j].y = fmaf(v.y, w, acc[j].y);
-                        acc[j].z = fmaf(v.z, w, acc[j].z); acc[j].w = fmaf(v.w, w, acc[j].w);
+            for (int i = 0; i < PY; i++) {
+                const int ky = iy * UP - (by0 + i * DOWN);
+                if (ky < 0 || ky >= FS) continue;
+                const float* fr = sf + ky * FS;
+#pragma unroll
+                for (int t = 0; t < NIX; t++) {
+                    float fv[VEC];
+                    v[t].unpack(fv);
+#pragma unroll
+                    for (int j = 0; j < PX; j++) {
+                        const int kx = (ixb + t) * UP - (bx0 + j * DOWN);
+                        if (kx >= 0 && kx < FS) {
+                            const float w = fr[kx];
+#pragma unroll
+                            for (int k = 0; k < VEC; k++) acc[i][j][k] = fmaf(fv[k], w, acc[i][j][k]);
+                        }
                     }
                 }
             }
         }
-        float* yo = (float*)p.y + (int64_t)n * p.ysN + (int64_t)oy * p.ysH + 4 * cv;
 #pragma unroll
-        for (int j = 0; j < PX; j++)
-            if (ox0 + j < p.outW)
-                *reinterpret_cast<float4*>(yo + (int64_t)(ox0 + j) * p.ysW) =
-                    make_float4(acc[j].x * p.gain, acc[j].y * p.gain, acc[j].z * p.gain, acc[j].w * p.gain);
+        for (int i = 0; i < PY; i++) {
+            if (oy0 + i >= p.outH) continue;
+            T* yo = (T*)p.y + (int64_t)n * p.ysN + (int64_t)(oy0 + i) * p.ysH + VEC * cv;
+#pragma unroll
+            for (int j = 0; j < PX; j++)
+                if (ox0 + j < p.outW) {
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) acc[i][j][k] *= p.gain;
+                    vec16<T> o; o.pack(acc[i][j]); o.store(yo + (int64_t)(ox0 + j) * p.ysW);
+                }
+        }
     }
 }
 
@@ -241,14 +325,16 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
     const bool cminor = (p.xsC == 1 && p.ysC == 1 && p.C % VEC == 0 && gp3d_aligned16(p.x) && gp3d_aligned16(p.y) &&
                          p.xsW % VEC == 0 && p.xsH % VEC == 0 && p.xsN % VEC == 0 &&
                          p.ysW % VEC == 0 && p.ysH % VEC == 0 && p.ysN % VEC == 0);
-    if (cminor && !(wminor && p.C == 1) && sizeof(T) == 4 && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
-        ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2)) && (int64_t)p.N * p.outH <= 65535) {
-        constexpr int PX = 4;
-        const int CV = p.C / 4, cv_per = CV < 256 ? CV : 256, groups = 256 / cv_per;
-        dim3 grid((p.outW + groups * PX - 1) / (groups * PX), 1, p.N * p.outH);
-        if (p.upx == 1 && p.downx == 1) upfirdn2d_cminor4_kernel<1, 1, PX><<<grid, 256, 0, s>>>(p);
-        else if (p.upx == 2) upfirdn2d_cminor4_kernel<2, 1, PX><<<grid, 256, 0, s>>>(p);
-        else upfirdn2d_cminor4_kernel<1, 2, PX><<<grid, 256, 0, s>>>(p);
+    if (cminor && !(wminor && p.C == 1) && (sizeof(T) == 4 || sizeof(T) == 2) && !std::is_same<T, __nv_bfloat16>::value && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
+        ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2)) && (int64_t)p.N * ((p.outH + 1) / 2) <= 65535) {
+        constexpr int PX = (sizeof(T) == 4) ? 4 : 2;       // half: 8 channels per thread, so a 2 x 2 patch for the same register budget
+        constexpr int PYA = (sizeof(T) == 4) ? 4 : 2;
+        const int CV = p.C / VEC, cv_per = CV < 256 ? CV : 256, groups = 256 / cv_per;
+        const unsigned gx = (p.outW + groups * PX - 1) / (groups * PX);
+        auto gridz = [&](int PY) { return dim3(gx, 1, (unsigned)(p.N * ((p.outH + PY - 1) / PY))); };
+        if (p.upx == 1 && p.downx == 1) upfirdn2d_cminor4_kernel<T, 1, 1, PX, PYA><<<gridz(PYA), 256, 0, s>>>(p);
+        else if (p.upx == 2) upfirdn2d_cminor4_kernel<T, 2, 1, PX, PYA><<<gridz(PYA), 256, 0, s>>>(p);
+        else upfirdn2d_cminor4_kernel<T, 1, 2, PX, 2><<<gridz(2), 256, 0, s>>>(p);     // decimating: 11 input columns per 4 outputs, keep the patch 4 x 2
         return 0;
     }
     if (cminor && !(wminor && p.C == 1)) {
@@ -257,6 +343,19 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
         return 0;
     }
     if (wminor) {
+        const int TIW = ((kTOW - 1) * p.downx + p.fw - 1) / p.upx + 2, TIH = ((kTOH - 1) * p.downy + p.fh - 1) / p.upy + 2;
+        const size_t tsmem = ((size_t)((p.fh * p.fw + 3) & ~3) + (size_t)TIW * TIH) * sizeof(float);
+        const bool small4 = (p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy && p.upx <= 2 && p.downx <= 2);   // unrolled per-tap kernels below
+        if (tsmem <= 96 * 1024 && !small4) {
+            p.tilesX = (p.outW + kTOW - 1) / kTOW;
+            p.tilesY = (p.outH + kTOH - 1) / kTOH;
+            const int64_t tblocks = (int64_t)p.N * p.C * p.tilesX * p.tilesY;
+            if (tblocks > 2147483647LL) return GP3D_E_TOOLARGE;
+            auto kern = upfirdn2d_wminor_tiled_kernel<T>;
+            if (tsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+            kern<<<(unsigned)tblocks, 256, tsmem, s>>>(p, TIW, TIH);
+            return 0;
+        }
         p.tilesX = (p.outW + 127) / 128;
         p.tilesY = (p.outH + 7) / 8;
         int64_t blocks = (int64_t)p.N * p.C * p.tilesX * p.tilesY;
