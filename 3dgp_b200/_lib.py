@@ -46,6 +46,7 @@ PROTOTYPES = {
     'gp3d_demod_act': (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 6 + [c_float] * 3 + [c_void_p]),
     'gp3d_demod_act_bwd': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
     'gp3d_demod_act_bwd_split': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
+    'gp3d_fir4_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_float] + [c_int] * 8 + [c_void_p] * 3 + [ctypes.POINTER(ConvEpilogue), c_void_p]),
     'gp3d_conv2d_nhwc_bf16x3_act': (c_int, [c_void_p] * 5 + [c_int] * 6 + [ctypes.POINTER(ConvEpilogue), c_void_p]),
     'gp3d_modulate_bwd': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     'gp3d_grad_epilogue': (c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),

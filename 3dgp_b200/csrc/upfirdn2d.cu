@@ -19,6 +19,9 @@
 #include <type_traits>
 #include "common.cuh"
 
+int gp3d_fir4_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int padx1, int pady0, int pady1,
+                     float* y, void* hi, void* lo, const gp3d_conv_epilogue* epi, cudaStream_t st);   // fir_tma.cu
+
 namespace {
 
 struct UpfirdnParams {
@@ -325,6 +328,15 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
     const bool cminor = (p.xsC == 1 && p.ysC == 1 && p.C % VEC == 0 && gp3d_aligned16(p.x) && gp3d_aligned16(p.y) &&
                          p.xsW % VEC == 0 && p.xsH % VEC == 0 && p.xsN % VEC == 0 &&
                          p.ysW % VEC == 0 && p.ysH % VEC == 0 && p.ysN % VEC == 0);
+    // dense channel-minor float32, 4x4, no resampling, C % 32 == 0: the TMA-staged kernel of fir_tma.cu (bit-identical taps order)
+    if (std::is_same<T, float>::value && p.fw == 4 && p.fh == 4 && p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.C % 32 == 0 && p.C >= 32 &&
+        p.xsC == 1 && p.xsW == p.C && p.xsH == (int64_t)p.inW * p.C && p.xsN == (int64_t)p.inH * p.inW * p.C &&
+        p.ysC == 1 && p.ysW == p.C && p.ysH == (int64_t)p.outW * p.C && p.ysN == (int64_t)p.outH * p.outW * p.C &&
+        (reinterpret_cast<uintptr_t>(p.x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0 &&
+        (int64_t)p.N * (p.C / 32) <= 65535 && (p.outH + 7) / 8 <= 65535) {
+        const int padx1 = p.outW - p.inW - p.padx0 + 3, pady1 = p.outH - p.inH - p.pady0 + 3;
+        return gp3d_fir4_launch((const float*)p.x, p.f, p.flip, p.gain, p.N, p.inH, p.inW, p.C, p.padx0, padx1, p.pady0, pady1, (float*)p.y, nullptr, nullptr, nullptr, s);
+    }
     if (cminor && !(wminor && p.C == 1) && (sizeof(T) == 4 || sizeof(T) == 2) && !std::is_same<T, __nv_bfloat16>::value && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
         ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2)) && (int64_t)p.N * ((p.outH + 1) / 2) <= 65535) {
         constexpr int PX = (sizeof(T) == 4) ? 4 : 2;       // half: 8 channels per thread, so a 2 x 2 patch for the same register budget

@@ -23,6 +23,10 @@ def eligible(x, weight, up, conv_clamp):
             and tc.channels_eligible(Cin, Cout) and Cin % 4 == 0 and Cout % 4 == 0)
 
 
+def _fir_tma_ok(C, fir):
+    return C % 32 == 0 and fir is not None and fir.dtype == torch.float32 and tuple(fir.shape) == (4, 4) and fir.is_contiguous()
+
+
 def _nhwc(t):
     return t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
@@ -77,13 +81,20 @@ class _ModConvLayer(torch.autograd.Function):
         else:
             c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
             # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
-            c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
-            Ho, Wo = c.shape[1], c.shape[2]
-            y = torch.empty_like(c)
-            with torch.cuda.device(dev):
-                rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
-                                      3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
-            _lib.check(rc, 'demod_act')
+            Ho, Wo = 2 * H, 2 * W
+            y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=dev)
+            if _fir_tma_ok(Cout, fir):    # TMA-staged FIR with demodulation / noise / bias / activation in its epilogue: the filtered tensor is never stored
+                epi = _lib.ConvEpilogue(_lib.ptr(d), _lib.ptr(nz), _lib.ptr(b), nps, 3 if act == 'lrelu' else 1, float(alpha), float(gain))
+                with torch.cuda.device(dev):
+                    rc = L.gp3d_fir4_nhwc(c.data_ptr(), fir.data_ptr(), 0, 4.0, N, 2 * H + 1, 2 * W + 1, Cout, 1, 1, 1, 1, y.data_ptr(), None, None,
+                                          ctypes.byref(epi), _lib.stream_ptr())
+                _lib.check(rc, 'fir4_nhwc')
+            else:
+                c = upfirdn2d._plugin.upfirdn2d(c.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0).permute(0, 2, 3, 1)
+                with torch.cuda.device(dev):
+                    rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
+                                          3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
+                _lib.check(rc, 'demod_act')
         ctx.save_for_backward(xn, xh, xl, weight, st, d if d is not None else torch.empty(0, device=dev), y,
                               noise if noise is not None else torch.empty(0, device=dev),
                               noise_strength if noise is not None else torch.empty(0, device=dev),
@@ -121,8 +132,16 @@ class _ModConvLayer(torch.autograd.Function):
         if g_ns is not None:
             g_ns = g_ns.reshape(noise_strength.shape)
         if up == 2:   # adjoint of the FIR (upfirdn2d.py:250-269): same filter, flipped, padding p = fw - pad - 1 = 2
-            dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
-            dch, dcl = tc.split_bf16(dc, pad_to=Cp)
+            if _fir_tma_ok(Cout, fir) and Cp == Cout:   # TMA-staged adjoint FIR that writes the bf16 (hi, lo) operand pair directly
+                dch = torch.empty([N, Ho + 1, Wo + 1, Cp], dtype=torch.bfloat16, device=dev)
+                dcl = torch.empty_like(dch)
+                with torch.cuda.device(dev):
+                    rc = L.gp3d_fir4_nhwc(dc.data_ptr(), fir.data_ptr(), 1, 4.0, N, Ho, Wo, Cout, 2, 2, 2, 2, None, dch.data_ptr(), dcl.data_ptr(),
+                                          None, _lib.stream_ptr())
+                _lib.check(rc, 'fir4_nhwc')
+            else:
+                dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
+                dch, dcl = tc.split_bf16(dc, pad_to=Cp)
         # input gradient
         dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
         assert tc.channels_eligible(Cp, Cin)

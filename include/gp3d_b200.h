@@ -230,6 +230,15 @@ typedef struct gp3d_conv_epilogue {
 int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                                 int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
 
+/* 4x4 FIR, up = down = 1, dense channel-minor float32 [N][H][W][C] (C % 32 == 0), input window staged by TMA: the filter after the
+ * up-sampling convolution (conv2d_resample.py:119-126) and its adjoint.  out = (H + pady0 + pady1 - 3) x (W + padx0 + padx1 - 3).
+ * f: DEVICE pointer to the 4x4 filter as upfirdn2d.setup_filter stores it; flip / gain as in gp3d_upfirdn2d.
+ * Exactly one output form:  y (float32; with epi != NULL the modulated-conv epilogue act(v*dcoef + noise + bias)*gain is applied to the
+ * filtered value v, networks_stylegan2.py:71,144)  or  (hi, lo) = bf16 pair of v for the tensor-core gradient kernels. */
+int gp3d_fir4_nhwc(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C,
+                   int padx0, int padx1, int pady0, int pady1, float* y, void* hi, void* lo,
+                   const gp3d_conv_epilogue* epi, void* stream);
+
 /* General tap convolution on the same tcgen05 pipeline -- the building block of the strided forms:
  *   y[n][iy*osy+oy0][ix*osx+ox0][co] (+)= sum_t sum_ci x[n][iy*in_stride+dy_t][ix*in_stride+dx_t][ci] * w[co][slab_t][ci]
  * for (iy, ix) in [0,HoP) x [0,WoP); out-of-range input pixels read as zero.  h_taps is a HOST array of ntaps x (dy, dx, slab).

@@ -160,3 +160,44 @@ def test_upfirdn2d_register_tiled_channels_last_kernel(kw, shape):
     assert torch.equal(y_cl.contiguous(), y_nchw)
     yo = R.upfirdn2d(x, f, **kw)
     assert maxrel(y_nchw.cpu().numpy(), yo) < TOL
+
+
+@pytest.mark.parametrize('shape,pad,flip', [((2, 64, 37, 41), (1, 1, 1, 1), False), ((3, 32, 16, 16), (2, 2, 2, 2), True), ((1, 128, 65, 9), (1, 2, 0, 3), False)])
+def test_fir4_tma_kernel_matches_generic_upfirdn2d_bit_for_bit(shape, pad, flip):
+    """gp3d_fir4_nhwc (TMA-staged window, csrc/fir_tma.cu) against the register-tiled / generic kernels behind gp3d_upfirdn2d on the same
+    channel-minor float32 tensors, plus its two fused output forms (demodulation epilogue, bf16 operand pair)."""
+    import ctypes
+    import importlib
+    _lib = importlib.import_module('3dgp_b200._lib')
+    up = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    tcm = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    L = _lib.lib()
+    torch.manual_seed(11)
+    N, C, H, W = shape
+    x = torch.randn(N, H, W, C, device='cuda')
+    f = up.setup_filter([1, 3, 3, 1], device='cuda') * torch.linspace(0.5, 1.5, 16, device='cuda').view(4, 4)    # not symmetric: flip matters
+    px0, px1, py0, py1 = pad
+    oh, ow = H + py0 + py1 - 3, W + px0 + px1 - 3
+    y = torch.empty(N, oh, ow, C, device='cuda')
+    s = _lib.stream_ptr()
+    _lib.check(L.gp3d_fir4_nhwc(x.data_ptr(), f.data_ptr(), int(flip), 4.0, N, H, W, C, px0, px1, py0, py1, y.data_ptr(), None, None, None, s), 'fir4')
+    # reference: the same op on a tensor whose strides keep it off the TMA route (channel count padded in memory)
+    xs = torch.zeros(N, H, W, C + 4, device='cuda')[..., :C]
+    xs.copy_(x)
+    ref = up._plugin.upfirdn2d(xs.permute(0, 3, 1, 2), f, 1, 1, 1, 1, px0, px1, py0, py1, flip, 4.0).permute(0, 2, 3, 1)
+    assert ref.shape == y.shape and torch.equal(y, ref.contiguous())
+    # routed automatically for dense tensors
+    y2 = up._plugin.upfirdn2d(x.permute(0, 3, 1, 2), f, 1, 1, 1, 1, px0, px1, py0, py1, flip, 4.0).permute(0, 2, 3, 1)
+    assert torch.equal(y2.contiguous(), y)
+    # fused epilogue == demod_act on the filtered tensor
+    d = torch.rand(N, C, device='cuda') + 0.5; nz = torch.randn(N, oh, ow, device='cuda') * 0.2; b = torch.randn(C, device='cuda') * 0.1
+    y_ref = torch.empty_like(y); y_f = torch.empty_like(y)
+    _lib.check(L.gp3d_demod_act(y.data_ptr(), d.data_ptr(), nz.data_ptr(), 1, b.data_ptr(), y_ref.data_ptr(), 0, N, C, oh * ow, 1, 3, 0.2, 1.4142135, -1.0, s), 'demod_act')
+    epi = _lib.ConvEpilogue(d.data_ptr(), nz.data_ptr(), b.data_ptr(), 1, 3, 0.2, 1.4142135)
+    _lib.check(L.gp3d_fir4_nhwc(x.data_ptr(), f.data_ptr(), int(flip), 4.0, N, H, W, C, px0, px1, py0, py1, y_f.data_ptr(), None, None, ctypes.byref(epi), s), 'fir4 epi')
+    assert torch.equal(y_f, y_ref)
+    # bf16 pair == split of the filtered tensor
+    hi = torch.empty(N, oh, ow, C, dtype=torch.bfloat16, device='cuda'); lo = torch.empty_like(hi)
+    _lib.check(L.gp3d_fir4_nhwc(x.data_ptr(), f.data_ptr(), int(flip), 4.0, N, H, W, C, px0, px1, py0, py1, None, hi.data_ptr(), lo.data_ptr(), None, s), 'fir4 split')
+    rh, rl = tcm.split_bf16(y)
+    assert torch.equal(hi, rh) and torch.equal(lo, rl)
