@@ -115,7 +115,106 @@ __global__ void __launch_bounds__(256, 3) fir4_tma_kernel(const __grid_constant_
     }
 }
 
+// ---- up = 2 (zero-stuffing) form: the skip-image up-sampling of the tri-plane decoder (upsample2d, networks_stylegan2.py:268).
+// Output tile 32 x 8; the input window is at most 18 x 6 pixels (13.8 KB); a thread's 4 x 2 patch touches 4 x 3 input pixels, 4 taps per output.
+constexpr int UIW = 18, UIH = 6;
+constexpr uint32_t kUpTileBytes = UIH * UIW * FCB * 4;
+
+__global__ void __launch_bounds__(256, 4) fir4_up2_tma_kernel(const __grid_constant__ CUtensorMap tmX, Fir4Params p) {
+    extern __shared__ unsigned char fsm_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fsm_raw) + 127) & ~(uintptr_t)127);
+    float* tile = reinterpret_cast<float*>(base);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + kUpTileBytes);
+    float* sf = reinterpret_cast<float*>(bar + 1);
+    const int tid = threadIdx.x;
+    const int cblocks = p.C / FCB;
+    const int n = blockIdx.z / cblocks, cb = blockIdx.z - n * cblocks;
+    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * FTH;
+    auto cdiv2 = [](int a) { return (a >= 0) ? (a + 1) / 2 : -((-a) / 2); };          // ceil(a / 2)
+    const int ix_t0 = cdiv2(ox0 - p.padx0), iy_t0 = cdiv2(oy0 - p.pady0);
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (tid < 16) {
+        const int ky = tid >> 2, kx = tid & 3;
+        const int sy = p.flip ? ky : 3 - ky, sx = p.flip ? kx : 3 - kx;
+        sf[tid] = p.f[sy * 4 + sx];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, kUpTileBytes);
+        tma_load_4d(tile, &tmX, bar, cb * FCB, ix_t0, iy_t0, n);
+    }
+    const int cv = tid & 7, xg = (tid >> 3) & 7, yg = tid >> 6;
+    const int oyb = oy0 + 2 * yg, oxb = ox0 + 4 * xg;
+    const int iyb = cdiv2(oyb - p.pady0), ixb = cdiv2(oxb - p.padx0);
+    float4 acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_wait(bar, 0);
+    const float* tb = tile + ((iyb - iy_t0) * UIW + (ixb - ix_t0)) * FCB + 4 * cv;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float4 v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) v[t] = *reinterpret_cast<const float4*>(tb + (r * UIW + t) * FCB);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int ky = 2 * (iyb + r) - (oyb + i - p.pady0);
+            if (ky < 0 || ky >= 4) continue;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int kx = 2 * (ixb + t) - (oxb + j - p.padx0);
+                    if (kx >= 0 && kx < 4) {
+                        const float w = sf[ky * 4 + kx];
+                        acc[i][j].x = fmaf(v[t].x, w, acc[i][j].x); acc[i][j].y = fmaf(v[t].y, w, acc[i][j].y);
+                        acc[i][j].z = fmaf(v[t].z, w, acc[i][j].z); acc[i][j].w = fmaf(v[t].w, w, acc[i][j].w);
+                    }
+                }
+            }
+        }
+    }
+    const int c0 = cb * FCB + 4 * cv;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int oy = oyb + i;
+        if (oy >= p.outH) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int ox = oxb + j;
+            if (ox >= p.outW) continue;
+            const size_t pix = ((size_t)n * p.outH + oy) * p.outW + ox;
+            *reinterpret_cast<float4*>(p.y + pix * p.C + c0) = make_float4(acc[i][j].x * p.gain, acc[i][j].y * p.gain, acc[i][j].z * p.gain, acc[i][j].w * p.gain);
+        }
+    }
+}
+
 }  // namespace
+
+// up = 2, down = 1, 4x4 filter, dense [N][H][W][C] float32 -> [N][outH][outW][C] (called by upfirdn2d.cu's dispatcher)
+int gp3d_fir4_up2_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int pady0, int outH, int outW,
+                         float* y, cudaStream_t st) {
+    GP3D_CHECK_ARG(x && f && y && N >= 1 && H >= 1 && W >= 1 && C >= FCB && C % FCB == 0 && outH >= 1 && outW >= 1, "fir4_up2: bad shape (C must be a multiple of 32)");
+    GP3D_CHECK_ARG((int64_t)N * (C / FCB) <= 65535 && (outH + FTH - 1) / FTH <= 65535, "fir4_up2: grid too large");
+    gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
+    if (!enc) { gp3d_set_error("cuTensorMapEncodeTiled is not available from this driver"); return GP3D_E_UNSUPPORTED; }
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {FCB, UIW, UIH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { gp3d_set_error("fir4_up2: tensor map encode failed (CUresult %d)", (int)r); return GP3D_E_BADARG; }
+    Fir4Params p{};
+    p.y = y; p.f = f; p.flip = flip; p.gain = gain; p.N = N; p.C = C; p.outH = outH; p.outW = outW; p.padx0 = padx0; p.pady0 = pady0;
+    const size_t smem = 128 + kUpTileBytes + 8 + 64;
+    const dim3 grid((outW + FTW - 1) / FTW, (outH + FTH - 1) / FTH, N * (C / FCB));
+    fir4_up2_tma_kernel<<<grid, 256, smem, st>>>(tm, p);
+    return 0;
+}
 
 // Internal launcher shared with upfirdn2d.cu's dispatcher.  x: dense [N][H][W][C] float32.
 int gp3d_fir4_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int padx1, int pady0, int pady1,

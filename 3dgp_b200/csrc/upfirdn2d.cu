@@ -22,6 +22,9 @@
 int gp3d_fir4_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int padx1, int pady0, int pady1,
                      float* y, void* hi, void* lo, const gp3d_conv_epilogue* epi, cudaStream_t st);   // fir_tma.cu
 
+int gp3d_fir4_up2_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int pady0, int outH, int outW,
+                         float* y, cudaStream_t st);   // fir_tma.cu
+
 namespace {
 
 struct UpfirdnParams {
@@ -336,6 +339,13 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
         (int64_t)p.N * (p.C / 32) <= 65535 && (p.outH + 7) / 8 <= 65535) {
         const int padx1 = p.outW - p.inW - p.padx0 + 3, pady1 = p.outH - p.inH - p.pady0 + 3;
         return gp3d_fir4_launch((const float*)p.x, p.f, p.flip, p.gain, p.N, p.inH, p.inW, p.C, p.padx0, padx1, p.pady0, pady1, (float*)p.y, nullptr, nullptr, nullptr, s);
+    }
+    if (std::is_same<T, float>::value && p.fw == 4 && p.fh == 4 && p.upx == 2 && p.upy == 2 && p.downx == 1 && p.downy == 1 && p.C % 32 == 0 && p.C >= 32 &&
+        p.xsC == 1 && p.xsW == p.C && p.xsH == (int64_t)p.inW * p.C && p.xsN == (int64_t)p.inH * p.inW * p.C &&
+        p.ysC == 1 && p.ysW == p.C && p.ysH == (int64_t)p.outW * p.C && p.ysN == (int64_t)p.outH * p.outW * p.C &&
+        (reinterpret_cast<uintptr_t>(p.x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0 &&
+        (int64_t)p.N * (p.C / 32) <= 65535 && (p.outH + 7) / 8 <= 65535) {
+        return gp3d_fir4_up2_launch((const float*)p.x, p.f, p.flip, p.gain, p.N, p.inH, p.inW, p.C, p.padx0, p.pady0, p.outH, p.outW, (float*)p.y, s);
     }
     if (cminor && !(wminor && p.C == 1) && (sizeof(T) == 4 || sizeof(T) == 2) && !std::is_same<T, __nv_bfloat16>::value && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
         ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2)) && (int64_t)p.N * ((p.outH + 1) / 2) <= 65535) {

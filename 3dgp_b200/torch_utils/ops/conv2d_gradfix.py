@@ -152,10 +152,17 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
             use_tc = (tc_enabled and groups == 1 and tuple(dilation) == (1, 1) and weight_shape[2] == weight_shape[3] and k in (1, 3, 5)
                       and input.dtype in (torch.float32, torch.float16) and tc.wgrad_eligible(cin_op, cout_op)
                       and ((not transpose and ((tuple(stride) == (1, 1) and tuple(padding) == (k // 2, k // 2)) or (tuple(stride) == (2, 2) and k == 3 and padding[0] == padding[1])))
-                           or (transpose and tuple(stride) == (2, 2) and tuple(padding) == (0, 0) and k == 3)))
+                           or (transpose and tuple(stride) == (2, 2) and tuple(padding) == (0, 0) and k == 3)
+                           or (transpose and tuple(stride) == (1, 1) and tuple(padding) == (k // 2, k // 2) and tuple(output_padding) == (0, 0))))
             if use_tc:
                 tc_stats['tc'] += 1
-                gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], terms)
+                if transpose and tuple(stride) == (1, 1):
+                    # stride-1 transposed conv == conv with the flipped, transposed kernel and padding k-1-p (= k//2 here): take that conv's
+                    # weight gradient and undo the flip / transpose.  This is the weight-gradient of an input-gradient op, i.e. the second-order
+                    # term of the R1 penalty (loss.py:238-253).
+                    gw = tc.conv_wgrad(grad_output, input, k, 'conv', 1, k // 2, terms).flip([2, 3]).transpose(0, 1)
+                else:
+                    gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], terms)
                 ctx.save_for_backward(grad_output, input)
                 return gw
             tc_stats['aten'] += 1

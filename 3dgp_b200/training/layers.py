@@ -146,6 +146,38 @@ class MappingNetwork(torch.nn.Module):
         return x
 
 
+fused_hyper_mod = True     # first-order fused backward of the hyper-modulation; the loss switches it off around the R1 (double-backward) forward
+
+
+class _ChannelScale(torch.autograd.Function):
+    """y = x * s[n, c] (hyper-modulation of Conv2dLayer, layers.py:231-232) with a one-pass backward: dx = dy * s and
+    g_s[n, c] = sum_hw dy * x come out of ONE kernel (gp3d_modulate_bwd) instead of mul + mul + sum.  First-order only."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(x, s)
+        return x * s.to(x.dtype).unsqueeze(2).unsqueeze(3)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        N, C, H, W = x.shape
+        if (x.dtype == torch.float32 and dy.dtype == torch.float32 and C % 4 == 0 and x.stride(1) == 1 and x.stride(3) == C and x.stride(2) == W * C
+                and x.stride(0) == H * W * C and (x.data_ptr() % 16 == 0)):
+            from .. import _lib
+            dyn = dy.contiguous(memory_format=torch.channels_last)
+            st = s.to(torch.float32).contiguous()
+            dx = torch.empty_like(x)                      # preserves the channel-minor strides
+            g_s = torch.zeros_like(st)
+            with torch.cuda.device(x.device):
+                rc = _lib.lib().gp3d_modulate_bwd(dyn.data_ptr(), x.data_ptr(), st.data_ptr(), dx.data_ptr(), g_s.data_ptr(), N, H * W, C, _lib.stream_ptr())
+            _lib.check(rc, 'modulate_bwd')
+            return dx, g_s.to(s.dtype)
+        sb = s.to(x.dtype).unsqueeze(2).unsqueeze(3)
+        return dy * sb, (dy.to(torch.float32) * x.to(torch.float32)).sum([2, 3]).to(s.dtype)
+
+
 class Conv2dLayer(torch.nn.Module):
     """conv (+FIR resampling) + bias + activation, optional hyper-modulation x * (1 + tanh(affine(c)))
     (layers.py:182-246)."""
@@ -177,7 +209,10 @@ class Conv2dLayer(torch.nn.Module):
     def forward(self, x, c=None, gain=1):
         w = self.weight * self.weight_gain
         if self.affine is not None:
-            x = (x * (1.0 + self.affine(c).tanh().unsqueeze(2).unsqueeze(3)).to(x.dtype)).to(x.dtype)
+            if fused_hyper_mod and x.is_cuda:
+                x = _ChannelScale.apply(x, 1.0 + self.affine(c).tanh())
+            else:
+                x = (x * (1.0 + self.affine(c).tanh().unsqueeze(2).unsqueeze(3)).to(x.dtype)).to(x.dtype)
         w = w.to(x.dtype)
         if x.is_cuda and isinstance(self.weight, torch.nn.Parameter):
             tc.tag_weight_source(w, self.weight, self.weight_gain)     # lets the tensor-core wrappers reuse this parameter's bf16 operands

@@ -201,3 +201,25 @@ def test_fir4_tma_kernel_matches_generic_upfirdn2d_bit_for_bit(shape, pad, flip)
     _lib.check(L.gp3d_fir4_nhwc(x.data_ptr(), f.data_ptr(), int(flip), 4.0, N, H, W, C, px0, px1, py0, py1, None, hi.data_ptr(), lo.data_ptr(), None, s), 'fir4 split')
     rh, rl = tcm.split_bf16(y)
     assert torch.equal(hi, rh) and torch.equal(lo, rl)
+
+
+@pytest.mark.parametrize('shape,pad,flip', [((2, 96, 16, 16), (2, 1, 2, 1), False), ((1, 32, 37, 21), (1, 2, 2, 1), True), ((3, 64, 5, 70), (2, 1, 1, 2), False)])
+def test_fir4_up2_tma_kernel_matches_register_tiled_kernel_bit_for_bit(shape, pad, flip):
+    """up = 2 form (upsample2d of the skip image): dense channel-minor float32 tensors take the TMA-staged kernel, tensors with a padded
+    channel stride the register-tiled one; both must agree exactly, and with the oracle's zero-stuffing definition."""
+    import importlib
+    up = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    from oracle import restated as R
+    torch.manual_seed(12)
+    N, C, H, W = shape
+    x = torch.randn(N, H, W, C, device='cuda')
+    f = up.setup_filter([1, 3, 3, 1], device='cuda') * torch.linspace(0.5, 1.5, 16, device='cuda').view(4, 4)
+    px0, px1, py0, py1 = pad
+    y = up._plugin.upfirdn2d(x.permute(0, 3, 1, 2), f, 2, 2, 1, 1, px0, px1, py0, py1, flip, 4.0)
+    xs = torch.zeros(N, H, W, C + 4, device='cuda')[..., :C]
+    xs.copy_(x)
+    ref = up._plugin.upfirdn2d(xs.permute(0, 3, 1, 2), f, 2, 2, 1, 1, px0, px1, py0, py1, flip, 4.0)
+    assert y.shape == ref.shape == (N, C, 2 * H + py0 + py1 - 3, 2 * W + px0 + px1 - 3)
+    assert torch.equal(y.contiguous(), ref.contiguous())
+    o = R.upfirdn2d(x.permute(0, 3, 1, 2).cpu().numpy(), f.cpu().numpy(), up=2, padding=[px0, px1, py0, py1], flip_filter=flip, gain=4)
+    assert np.abs(y.cpu().numpy() - o).max() <= 2e-5 * np.abs(o).max()

@@ -93,7 +93,10 @@ def test_conv2d_gradfix_tc_double_backward_r1_style():
             gx = torch.autograd.grad(y.tanh().sum(), x, create_graph=True)[0]
         (gw,) = torch.autograd.grad(gx.square().sum(), w)
         return gw
-    a, b = r1(True), r1(False)
+    n_aten = cg.tc_stats['aten']
+    a = r1(True)
+    assert cg.tc_stats['aten'] == n_aten          # every conv of the second-order graph (incl. the weight gradient of the input-gradient op) ran on tcgen05
+    b = r1(False)
     cg.tc_enabled = True
     assert (a - b).abs().max().item() / b.abs().max().item() < 2e-4
 
@@ -327,3 +330,21 @@ def test_demod_act_bwd_split_outputs_equal_split_of_float_outputs():
     assert torch.equal(outs[1][2], rh) and torch.equal(outs[1][3], rl)
     assert torch.equal(outs[0][0], outs[1][0]) or torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('cl', [True, False])
+def test_channel_scale_fused_backward_matches_autograd(cl):
+    """Hyper-modulation x * s[n, c] of Conv2dLayer (layers.py:231-232): one-kernel backward against plain autograd."""
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    torch.manual_seed(9)
+    x = torch.randn(3, 64, 10, 12, device='cuda')
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    s = (1 + torch.randn(3, 64, device='cuda').tanh()).requires_grad_(True)
+    dy = torch.randn(3, 64, 10, 12, device='cuda')
+    y = layers._ChannelScale.apply(x, s)
+    gx, gs = torch.autograd.grad(y, [x, s], dy)
+    yr = x * s.unsqueeze(2).unsqueeze(3)
+    rx, rs = torch.autograd.grad(yr, [x, s], dy)
+    assert torch.equal(y, yr) and torch.allclose(gx, rx, rtol=1e-6, atol=1e-6) and torch.allclose(gs, rs, rtol=1e-4, atol=1e-4)

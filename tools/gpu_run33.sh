@@ -1,9 +1,9 @@
 cd /root/repo
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q --tb=short 2>&1 | tail -8
-timeout 300 python bench.py --workload ops --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ops_v6.json | python -c "
+timeout 300 python bench.py --workload ops --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ops_v7.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 for c in d['config']['cases'][:3]: print(c)
 print(d['value'])"
-timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_b32_v14.json | cut -c1-300
+timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_b32_v15.json | cut -c1-300
