@@ -9,7 +9,7 @@ from .dnnlib import EasyDict
 
 def make_config(cmax=1024, cbase=65536, tri_res=512, feat_dim=32, num_ray_steps=48, patch_res=64, img_resolution=256, c_dim=1000,
                 use_depth=True, hid_dim=64, d_fmaps=1.0, w_dim=512, z_dim=512, depth_hid=64, embedding_dim=2048, kd_weight=1.0,
-                batch_size=64):
+                batch_size=64, learn_camera_dist=False):
     camera = dict(
         ray=dict(start=0.75, end=1.25), fov=dict(dist='uniform', min=10.0, max=45.0),
         origin=dict(radius=dict(dist='normal', mean=1.0, std=0.0),
@@ -29,7 +29,10 @@ def make_config(cmax=1024, cbase=65536, tri_res=512, feat_dim=32, num_ray_steps=
         tri_plane=dict(res=tri_res, feat_dim=feat_dim, mlp=dict(n_layers=2, hid_dim=hid_dim)),
         depth_adaptor=dict(enabled=use_depth, kernel_size=5, hid_dim=depth_hid, num_hid_layers=3, out_strategy='random', selection_start_p=0.1,
                            anneal_kimg=10000, near_plane_offset_max_fraction=0.25, near_plane_offset_bias=-3.0, w_dim=w_dim, camera=camera),
-        camera_adaptor=dict(enabled=False),
+        camera_adaptor=dict(enabled=learn_camera_dist, camera=camera, residual=False, lipschitz_weights=dict(enabled=False),
+                            emd=dict(enabled=True, anneal_kimg=10000, num_samples=64, origin=2.0, radius=0.0, fov=0.0001, look_at=0.0001),
+                            lr_multiplier=0.1, z_dim=z_dim, c_dim=c_dim, hid_dim=256, embed_dim=16,
+                            adjust=dict(angles=True, radius=False, fov=True, look_at=True), force_mean_weight=10.0),
         optim=dict(kwargs=dict(lr=0.0025, betas=[0.0, 0.99], eps=1e-8, weight_decay=0.0)))
     discriminator = dict(fp32_only=False, c_dim=c_dim, cmax=cmax, cbase=cbase, fmaps=d_fmaps, patch=patch,
                          num_additional_start_blocks=int(np.log2(img_resolution // patch_res)), logits_clamp_val=1e7, mbstd_group_size=4,
@@ -39,7 +42,7 @@ def make_config(cmax=1024, cbase=65536, tri_res=512, feat_dim=32, num_ray_steps=
                        kd=dict(discr=dict(weight=kd_weight, anneal_kimg=100000, loss_type='l2')))
     cfg = dict(camera=camera, dataset=dataset,
                model=dict(name='3dgp', generator=generator, discriminator=discriminator, loss_kwargs=loss_kwargs),
-               training=dict(batch_size=batch_size, use_depth=use_depth, learn_camera_dist=False, patch=patch, blur_real_depth_sigma=0.0))
+               training=dict(batch_size=batch_size, use_depth=use_depth, learn_camera_dist=learn_camera_dist, patch=patch, blur_real_depth_sigma=0.0))
     return EasyDict.init_recursively(cfg)
 
 

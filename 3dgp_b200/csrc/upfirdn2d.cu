@@ -117,6 +117,91 @@ __global__ void __launch_bounds__(256) upfirdn2d_wminor_kernel(UpfirdnParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// W-minor 4x4 kernel for NCHW planes with up / down in {(1,1), (2,1), (1,2)} (upsample2d / downsample2d / filter2d of the reference with
+// the [1,3,3,1] filter; BASELINE configs[3]).  A CTA stages the input window of a 128 x 16 output tile of one (n, c) plane in shared
+// memory as float; a thread then produces 8 consecutive outputs of one row from registers (every staged value is read once per thread,
+// the valid (column, output) tap pairs are resolved at compile time) and stores them as one 16-byte vector when aligned.
+template <class T, int UP, int DOWN, int KX0>
+__device__ __forceinline__ void wminor4_row(const float* __restrict__ row, const float* __restrict__ fr, float (&acc)[8]) {
+    constexpr int NC = (7 * DOWN + 3) / UP + 2;
+    float v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) v[c] = row[c];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int kx = KX0 + c * UP - j * DOWN;          // compile-time after unrolling
+            if (kx >= 0 && kx < 4) acc[j] = fmaf(v[c], fr[kx], acc[j]);
+        }
+    }
+}
+
+template <class T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_wminor4_kernel(UpfirdnParams p) {
+    constexpr int FS = 4, TOW = 128, TOH = 16;
+    constexpr int IW = ((TOW - 1) * DOWN + FS - 1) / UP + 2, IH = ((TOH - 1) * DOWN + FS - 1) / UP + 2;
+    constexpr int IWP = IW | 1;
+    constexpr int NC = (7 * DOWN + 3) / UP + 2;
+    __shared__ float sf[FS * FS];
+    __shared__ float st[IH * IWP + NC];
+    stage_filter(sf, p);
+    int64_t tile = blockIdx.x;
+    const int tx = (int)(tile % p.tilesX); tile /= p.tilesX;
+    const int ty = (int)(tile % p.tilesY); tile /= p.tilesY;
+    const int nc = (int)tile;
+    const int n = nc / p.C, c = nc - n * p.C;
+    const int ox_t0 = tx * TOW, oy_t0 = ty * TOH;
+    const int ix_t0 = ceil_div_s(ox_t0 * DOWN - p.padx0, UP), iy_t0 = ceil_div_s(oy_t0 * DOWN - p.pady0, UP);
+    const T* xb = (const T*)p.x + n * p.xsN + c * p.xsC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < IH; r += 8) {
+        const int iy = iy_t0 + r;
+        const bool rowin = (iy >= 0 && iy < p.inH);
+        const T* xr = xb + (int64_t)iy * p.xsH;
+        for (int cc = lane; cc < IWP; cc += 32) {
+            const int ix = ix_t0 + cc;
+            st[r * IWP + cc] = (rowin && cc < IW && ix >= 0 && ix < p.inW) ? io_traits<T>::ld(xr + ix) : 0.f;
+        }
+    }
+    if (threadIdx.x < NC) st[IH * IWP + threadIdx.x] = 0.f;
+    __syncthreads();
+    const int xg = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int oy = oy_t0 + ly, ox = ox_t0 + 8 * xg;
+    if (oy >= p.outH || ox >= p.outW) return;
+    const int by = oy * DOWN - p.pady0, bx0 = ox * DOWN - p.padx0;
+    const int iya = ceil_div_s(by, UP), ixa = ceil_div_s(bx0, UP);
+    const int ky0 = iya * UP - by, kx0 = ixa * UP - bx0;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    const float* base = st + (iya - iy_t0) * IWP + (ixa - ix_t0);
+#pragma unroll
+    for (int r = 0; r < (FS + UP - 1) / UP; r++) {
+        const int ky = ky0 + r * UP;
+        if (ky < FS) {
+            if (UP == 1 || kx0 == 0) wminor4_row<T, UP, DOWN, 0>(base + r * IWP, sf + ky * FS, acc);
+            else wminor4_row<T, UP, DOWN, 1>(base + r * IWP, sf + ky * FS, acc);
+        }
+    }
+    T* yo = (T*)p.y + n * p.ysN + c * p.ysC + (int64_t)oy * p.ysH + ox;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] *= p.gain;
+    if (ox + 8 <= p.outW && (reinterpret_cast<uintptr_t>(yo) & 15u) == 0) {
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(yo) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(yo) + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+            vec16<T> o; o.pack(acc); o.store(yo);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (ox + j < p.outW) io_traits<T>::st(yo + j, acc[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // W-minor tiled kernel (NCHW planes, any dtype / up / down / filter): a CTA stages the input window of a 64 x 16 output tile of one
 // (n, c) plane in shared memory as float (coalesced row loads, zero-filled outside the image = the padding rule), then every thread
 // evaluates four outputs of one column from shared memory.  The window is read from HBM once (halo excepted) instead of once per tap.
@@ -376,6 +461,16 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
             auto kern = upfirdn2d_wminor_tiled_kernel<T>;
             if (tsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
             kern<<<(unsigned)tblocks, 256, tsmem, s>>>(p, TIW, TIH);
+            return 0;
+        }
+        if (small4 && ((p.upx == 1 && p.downx == 1) || (p.upx == 2 && p.downx == 1) || (p.upx == 1 && p.downx == 2))) {
+            p.tilesX = (p.outW + 127) / 128;
+            p.tilesY = (p.outH + 15) / 16;
+            const int64_t b4 = (int64_t)p.N * p.C * p.tilesX * p.tilesY;
+            if (b4 > 2147483647LL) return GP3D_E_TOOLARGE;
+            if (p.upx == 2) upfirdn2d_wminor4_kernel<T, 2, 1><<<(unsigned)b4, 256, 0, s>>>(p);
+            else if (p.downx == 2) upfirdn2d_wminor4_kernel<T, 1, 2><<<(unsigned)b4, 256, 0, s>>>(p);
+            else upfirdn2d_wminor4_kernel<T, 1, 1><<<(unsigned)b4, 256, 0, s>>>(p);
             return 0;
         }
         p.tilesX = (p.outW + 127) / 128;

@@ -1,7 +1,12 @@
 """Non-saturating GAN loss with R1, patch-wise training and discriminator knowledge distillation
-(reference src/training/loss.py:33-339), for the configuration on the hot path: `training.learn_camera_dist=false`
-(the camera adaptor and its POT/EMD regulariser are outside the scope table), `pl_weight=0` (3dgp.yaml / base.yaml:77).
-Phases: Gmain, Dmain, Dreg (lazy R1) exactly as training_loop.py:321-331 drives them."""
+(reference src/training/loss.py:33-339), `pl_weight=0` (3dgp.yaml / base.yaml:77).
+Phases: Gmain, Dmain, Dreg (lazy R1) exactly as training_loop.py:321-331 drives them.
+`training.learn_camera_dist=true`: the camera adaptor maps the prior camera before rendering (:78-79) and Gmain adds its regularisers
+(:142-232): Lipschitz (off in 3dgp.yaml), earth-mover distance between prior and posterior per camera coordinate, and the pull of the mean
+origin angles to the prior mean.  The reference calls POT (`ot.dist` + `ot.emd2`, environment.yml:38, unpinned version) for the EMD; POT is not
+installed here, so the term is restated: for two equally weighted 1-D samples of the same size and a convex cost the optimal plan matches
+order statistics, hence emd2 == mean((sort(a) - sort(b))^2), differentiated with the plan held fixed exactly as `ot.emd2` does.
+PARITY UNPINNED for this one term (no POT to compare against)."""
 import numpy as np
 import torch
 
@@ -9,7 +14,8 @@ from . import layers
 
 from ..dnnlib import EasyDict
 from ..torch_utils.ops import conv2d_gradfix, upfirdn2d
-from .training_utils import extract_patches, linear_schedule, sample_patch_params
+from .rendering_utils import get_mean_angles_values
+from .training_utils import extract_patches, linear_schedule, sample_patch_params, sample_random_c
 
 
 def maybe_blur(img, blur_sigma):
@@ -40,17 +46,59 @@ class StyleGAN2Loss:
                 pc.min_scale = linear_schedule(cur_kimg, pc.max_scale, pc.min_scale_trg, pc.anneal_kimg)
         kd = self.cfg.model.loss_kwargs.kd.discr
         self.D_kd_weight = linear_schedule(cur_kimg, kd.weight, 0.0, period=kd.anneal_kimg, start_step=0)
+        self.learn_camera = bool(self.cfg.training.get('learn_camera_dist', False))
+        self.emd_multiplier = linear_schedule(cur_kimg, 0.0, 1.0, period=self.cfg.model.generator.camera_adaptor.emd.anneal_kimg, start_step=0) if self.learn_camera else 0.0
 
     def run_G(self, z, c, camera_params, update_emas=False, patch_params=None, render_opts=None):
         ws = self.G.mapping(z=z, c=c, update_emas=update_emas)
         if patch_params is None:
             patch_params = sample_patch_params(len(z), self.patch_cfg, device=z.device) if self.patch_cfg.enabled else {}
         kw = dict(patch_params=patch_params) if self.patch_cfg.enabled else {}
+        if self.learn_camera:
+            camera_params = self.G.synthesis.camera_adaptor(camera_params, z, c)                      # loss.py:78-79
         ro = dict(concat_depth=self.cfg.training.use_depth, return_depth=True)
         ro.update(render_opts or {})
         out = self.G.synthesis(ws, camera_params, update_emas=update_emas, render_opts=ro, **kw)
         out.ws = ws
+        out.camera_params = camera_params
         return out, patch_params
+
+    def camera_regularisers(self, stats):
+        """Gmain's extra terms for the learned camera distribution (loss.py:142-232); returns their sum."""
+        ca, ccfg = self.G.synthesis.camera_adaptor, self.cfg.model.generator.camera_adaptor
+        total = 0.0
+
+        def prior_posterior(n):
+            z = torch.randn(n, self.G.z_dim, device=self.device)
+            c = sample_random_c(n, self.G.c_dim, self.device)
+            prior_raw = ca.unroll_camera_params(ca.sample_from_prior(n, device=self.device)).requires_grad_(True)      # [n, 8]
+            post_raw = ca.unroll_camera_params(ca(ca.roll_camera_params(prior_raw), z, c))
+            return prior_raw, post_raw
+
+        def weighted(t, w):        # t [1, 8] in unrolled order; only yaw, pitch, radius, fov and the look-at triple count (:175, :214)
+            g = ca.roll_camera_params(t)
+            return (g.angles * w[0])[:, :2].sum() + (g.radius * w[1]).sum() + (g.fov * w[2]).sum() + (g.look_at * w[3]).sum()
+
+        if ccfg.lipschitz_weights.enabled:                                                                             # :143-177
+            prior_raw, post_raw = prior_posterior(256)
+            grads = torch.stack([torch.autograd.grad(post_raw[:, i].sum(), prior_raw, create_graph=True)[0][:, i] for i in range(8)], dim=1).abs()
+            lw = ccfg.lipschitz_weights
+            lip = weighted((grads + 1.0 / (grads + 1e-4)).mean(dim=0, keepdim=True), (lw.angles, lw.radius, lw.fov, lw.look_at))
+            stats['Loss/camera_dist/lipschitz_loss'] = lip.detach()
+            total = total + lip
+        if ccfg.emd.enabled and self.emd_multiplier > 0.0:                                                             # :182-216
+            prior_raw, post_raw = prior_posterior(ccfg.emd.num_samples)
+            emd = (post_raw.sort(dim=0).values - prior_raw.detach().sort(dim=0).values).square().mean(dim=0, keepdim=True)   # [1, 8], see the module docstring
+            emd = self.emd_multiplier * weighted(emd, (ccfg.emd.origin, ccfg.emd.radius, ccfg.emd.fov, ccfg.emd.look_at))
+            stats['Loss/camera_dist/emd_loss'] = emd.detach()
+            total = total + emd
+        if ccfg.adjust.angles and ccfg.force_mean_weight > 0:                                                          # :221-230
+            mean_angles = torch.tensor(get_mean_angles_values(self.cfg.camera.origin.angles), device=self.device)
+            _, post_raw = prior_posterior(256)
+            fm = ccfg.force_mean_weight * (post_raw[:, :3].mean(dim=0) - mean_angles + 1e-8).square().sum().sqrt()
+            stats['Loss/camera_dist/force_mean'] = fm.detach()
+            total = total + fm
+        return total
 
     def run_D(self, img, c, blur_sigma=0, update_emas=False, **kwargs):
         img = maybe_blur(img, blur_sigma)
@@ -76,16 +124,17 @@ class StyleGAN2Loss:
 
         if phase == 'Gmain':
             gen_out, pp = self.run_G(gen_data.z, gen_data.c, gen_data.camera_params, render_opts=render_opts)
-            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=gen_data.camera_params.angles)
+            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=gen_out.camera_params.angles)
             loss = torch.nn.functional.softplus(-logits)
-            loss.mean().mul(gain).backward()
+            reg = self.camera_regularisers(stats) if self.learn_camera else 0.0
+            (loss.mean() + reg).mul(gain).backward()
             stats['Loss/G/loss'] = loss.detach().mean()
 
         loss_Dgen = 0
         if phase in ['Dmain', 'Dall']:
             with torch.no_grad():
                 gen_out, pp = self.run_G(gen_data.z, gen_data.c, gen_data.camera_params, update_emas=True, render_opts=render_opts)
-            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, update_emas=True, patch_params=pp, camera_angles=gen_data.camera_params.angles)
+            logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, update_emas=True, patch_params=pp, camera_angles=gen_out.camera_params.angles)
             loss_Dgen = torch.nn.functional.softplus(logits.clamp(min=-lk.discriminator.logits_clamp_val))
             loss_Dgen = loss_Dgen + 0.0 * logits.max()
             loss_Dgen.mean().mul(gain).backward()

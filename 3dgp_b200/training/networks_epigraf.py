@@ -12,6 +12,7 @@ import torch
 from ..dnnlib import EasyDict, TensorGroup
 from .layers import FullyConnectedLayer, MappingNetwork
 from .networks_depth_adaptor import DepthAdaptor
+from .networks_camera_adaptor import CameraAdaptor
 from .networks_stylegan2 import SynthesisBlock
 from .rendering_utils import compute_cam2world_matrix
 from .training_utils import linear_schedule
@@ -94,9 +95,7 @@ class SynthesisNetwork(torch.nn.Module):
         self.test_resolution = img_resolution
         self.renderer = ImportanceRenderer(ray_marcher_type=cfg.ray_marcher_type)
         self.depth_adaptor = DepthAdaptor(cfg.depth_adaptor, min_depth=cfg.camera.ray.start, max_depth=cfg.camera.ray.end) if cfg.depth_adaptor.enabled else None
-        if cfg.camera_adaptor.enabled:
-            raise NotImplementedError('camera adaptor (training.learn_camera_dist) is a "next" row of the scope table; run with learn_camera_dist=false')
-        self.camera_adaptor = None
+        self.camera_adaptor = CameraAdaptor(cfg.camera_adaptor) if cfg.camera_adaptor.enabled else None        # networks_epigraf.py:174-177
         self._default_render_options = EasyDict(max_batch_res=cfg.max_batch_res, return_depth=False, return_depth_adapted=False,
                                                 return_weights=False, concat_depth=False, cut_quantile=0.0, density_bias=cfg.density_bias)
 

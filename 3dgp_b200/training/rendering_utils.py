@@ -69,3 +69,12 @@ def sample_camera_params(cfg, batch_size, device='cpu', origin_angles=None):
     la = _angles(cfg.look_at.angles, batch_size, device)
     look_at = torch.cat([la[:, [0, 1]], _scalar(cfg.look_at.radius, batch_size, device).unsqueeze(1)], dim=1)
     return TensorGroup(angles=angles, fov=fov, radius=radius, look_at=look_at)
+
+
+def get_mean_angles_values(angles_cfg):
+    """Mean (yaw, pitch, roll) of an origin-angle prior (rendering_utils.py:180-190)."""
+    if angles_cfg.dist == 'normal':
+        return [angles_cfg.yaw.mean, angles_cfg.pitch.mean, 0.0]
+    if angles_cfg.dist in ('spherical_uniform', 'truncnorm', 'uniform'):
+        return [(angles_cfg.yaw.max + angles_cfg.yaw.min) * 0.5, (angles_cfg.pitch.max + angles_cfg.pitch.min) * 0.5, 0.0]
+    raise NotImplementedError(f'mean of camera angle distribution `{angles_cfg.dist}`')

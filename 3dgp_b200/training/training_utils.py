@@ -53,3 +53,11 @@ def sample_patch_params(batch_size, patch_cfg, device='cpu'):
     scales = torch.stack([sx, sx], dim=1)
     offsets = torch.rand(scales.shape, device=device) * (1.0 - scales)
     return {'scales': scales.repeat_interleave(g, dim=0), 'offsets': offsets.repeat_interleave(g, dim=0)}
+
+
+def sample_random_c(batch_size, c_dim, device):
+    """Uniform one-hot class labels (training_utils.py:207-214)."""
+    c = torch.zeros(batch_size, c_dim, device=device)
+    if c_dim > 0:
+        c[torch.arange(batch_size, device=device), torch.randint(0, c_dim, (batch_size,), device=device)] = 1.0
+    return c

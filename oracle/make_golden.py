@@ -242,6 +242,43 @@ def gen_networks(ns, report):
         json.dump(meta, f, indent=1, sort_keys=True)
 
 
+def gen_camera_adaptor(ns, report):
+    """Learned camera distribution (networks_camera_adaptor.py:54-134) of the UNMODIFIED reference on CPU: seeded weights (stored), prior
+    cameras / z / c from numpy seeds; outputs + gradients of a fixed cotangent w.r.t. z and two weight tensors."""
+    import importlib
+    ca_mod = importlib.import_module('src.training.networks_camera_adaptor')
+    G_cfg, _, _ = rh.make_cfg(learn_camera_dist=True, z_dim=16, c_dim=6)
+    cfg = ns.dnnlib.EasyDict.init_recursively(G_cfg['camera_adaptor'])
+    cfg.hid_dim = 32; cfg.embed_dim = 8
+    torch.manual_seed(3)
+    ca = ca_mod.CameraAdaptor(cfg)
+    with torch.no_grad():                      # biases start at 0 in the reference; give them values so that they are exercised
+        for n_, p_ in ca.named_parameters():
+            if n_.endswith('bias'):
+                p_.normal_(0, 1.0)
+    rs = np.random.RandomState(7)
+    B = 9
+    cam = ns.dnnlib.TensorGroup(
+        angles=torch.from_numpy(np.stack([rs.uniform(-1.5, 1.5, B), rs.uniform(0.8, 2.3, B), np.zeros(B)], 1).astype(np.float32)),
+        fov=torch.from_numpy(rs.uniform(10, 45, B).astype(np.float32)), radius=torch.ones(B),
+        look_at=torch.from_numpy(np.stack([rs.uniform(-3, 3, B), rs.uniform(0.1, 3.0, B), rs.uniform(0, 0.2, B)], 1).astype(np.float32)))
+    z = torch.from_numpy(rs.randn(B, 16).astype(np.float32)).requires_grad_(True)
+    c = torch.zeros(B, 6); c[torch.arange(B), torch.from_numpy(rs.randint(0, 6, B))] = 1.0
+    out = ca(cam, z, c)
+    raw = ca.unroll_camera_params(out)
+    cot = torch.from_numpy(rs.randn(B, 8).astype(np.float32))
+    names = ['origin_adaptor.main.0.weight', 'look_at_adaptor.project_z.weight', 'look_at_adaptor.main.1.bias']
+    pars = dict(ca.named_parameters())
+    grads = torch.autograd.grad((raw * cot).sum(), [z] + [pars[n_] for n_ in names])
+    res = {'in/angles': cam.angles.numpy(), 'in/fov': cam.fov.numpy(), 'in/radius': cam.radius.numpy(), 'in/look_at': cam.look_at.numpy(),
+           'in/z': z.detach().numpy(), 'in/c': c.numpy(), 'in/cot': cot.numpy(), 'out/raw': raw.detach().numpy(), 'grad/z': grads[0].numpy()}
+    for n_, g_ in zip(names, grads[1:]):
+        res['grad/' + n_] = g_.numpy()
+    for k, v in ca.state_dict().items():
+        res['sd/' + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, 'camera_adaptor.npz'), **res)
+
+
 def main():
     assert rh.available(), 'reference not found'
     os.makedirs(GOLD, exist_ok=True)
@@ -249,7 +286,8 @@ def main():
     ns = rh.load()
     report = {}
     only = sys.argv[1:]
-    gens = dict(upfirdn2d=gen_upfirdn2d, bias_act=gen_bias_act, filtered_lrelu=gen_filtered_lrelu, render=gen_render, networks=gen_networks)
+    gens = dict(upfirdn2d=gen_upfirdn2d, bias_act=gen_bias_act, filtered_lrelu=gen_filtered_lrelu, render=gen_render, networks=gen_networks,
+                camera_adaptor=gen_camera_adaptor)
     for name, fn in gens.items():
         if only and name not in only:
             continue

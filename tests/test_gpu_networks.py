@@ -119,3 +119,66 @@ def test_training_step_runs_and_updates():
     assert not torch.equal(w0, G.synthesis.tri_plane_decoder.b8.conv0.weight) and not torch.equal(d0, D.b16.conv0.weight)
     stats = tr.step(real, gen)
     assert 'Loss/D/r1_penalty' not in stats     # lazy regularisation: Dreg only every 16th iteration
+
+
+def test_camera_adaptor_vs_golden(golden):
+    """Learned camera distribution (networks_camera_adaptor.py): the reference's weights, prior cameras, z, c -> posterior camera and gradients."""
+    ca_mod = importlib.import_module('3dgp_b200.training.networks_camera_adaptor')
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    g = golden('camera_adaptor')
+    cfg = cfgm.make_config(learn_camera_dist=True, z_dim=16, c_dim=6).model.generator.camera_adaptor
+    cfg.hid_dim = 32; cfg.embed_dim = 8
+    ca = ca_mod.CameraAdaptor(cfg).cuda()
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd/')}
+    assert set(sd) == set(ca.state_dict())                      # same module / parameter names as the reference
+    ca.load_state_dict(sd)
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    cam = dn.TensorGroup(angles=cu('in/angles'), fov=cu('in/fov'), radius=cu('in/radius'), look_at=cu('in/look_at'))
+    z = cu('in/z').requires_grad_(True)
+    out = ca(cam, z, cu('in/c'))
+    raw = ca.unroll_camera_params(out)
+    assert maxrel(raw.detach().cpu().numpy(), g['out/raw']) < 1e-5
+    names = [k[5:] for k in g.files if k.startswith('grad/') and k != 'grad/z']
+    pars = dict(ca.named_parameters())
+    grads = torch.autograd.grad((raw * cu('in/cot')).sum(), [z] + [pars[n] for n in names])
+    assert maxrel(grads[0].cpu().numpy(), g['grad/z']) < 1e-4
+    for n, gr in zip(names, grads[1:]):
+        assert maxrel(gr.cpu().numpy(), g['grad/' + n]) < 1e-4, n
+
+
+def test_training_step_with_learned_camera_distribution():
+    """training.learn_camera_dist=true on the small config: the camera adaptor sits in front of the renderer, its weights receive gradient
+    through d(ray_o), d(ray_d) of the fused ray-march backward plus the EMD / force-mean regularisers, and move."""
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0, learn_camera_dist=True)
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = cfgm.build_networks(cfg, 'cuda', fp32_D=True)
+    assert G.synthesis.camera_adaptor is not None
+    inp = cases.net_inputs(meta['net_kwargs'])
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    B = t['z'].shape[0]
+    loss = lossm.StyleGAN2Loss(cfg, 'cuda', G, D, r1_gamma=1.0)
+    loss.progressive_update(5000)                      # EMD weight ramps in from 0 (loss.py:64-65)
+    assert loss.emd_multiplier > 0
+    # gradient reaches the adaptor through the renderer alone
+    G.requires_grad_(True); D.requires_grad_(False)
+    out, pp = loss.run_G(t['z'], t['c'], cam)
+    ca = G.synthesis.camera_adaptor
+    gw = torch.autograd.grad(out.img.square().mean(), [ca.origin_adaptor.main[0].weight, ca.look_at_adaptor.main[1].weight], allow_unused=False)
+    assert all(torch.isfinite(x).all() and x.abs().max() > 0 for x in gw)
+    tr = stepm.Trainer(G, D, loss, cfg, D_reg_interval=16)
+    real = dn.EasyDict(img=torch.rand(B, 3, 64, 64, device='cuda') * 2 - 1, depth=torch.rand(B, 1, 64, 64, device='cuda') * 2 - 1, c=t['c'],
+                       embs=torch.randn(B, kw['embedding_dim'], device='cuda'), camera_angles=t['angles'])
+    gen = dn.EasyDict(z=t['z'], c=t['c'], camera_params=cam)
+    w0 = ca.look_at_adaptor.main[0].weight.detach().clone()
+    stats = tr.step(real, gen)
+    assert all(torch.isfinite(v).all() for v in stats.values())
+    assert 'Loss/camera_dist/emd_loss' in stats and 'Loss/camera_dist/force_mean' in stats
+    assert not torch.equal(w0, ca.look_at_adaptor.main[0].weight)
