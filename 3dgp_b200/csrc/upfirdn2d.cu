@@ -121,12 +121,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_wminor_kernel(UpfirdnParams p) 
 // the [1,3,3,1] filter; BASELINE configs[3]).  A CTA stages the input window of a 128 x 16 output tile of one (n, c) plane in shared
 // memory as float; a thread then produces 8 consecutive outputs of one row from registers (every staged value is read once per thread,
 // the valid (column, output) tap pairs are resolved at compile time) and stores them as one 16-byte vector when aligned.
-template <class T, int UP, int DOWN, int KX0>
-__device__ __forceinline__ void wminor4_row(const float* __restrict__ row, const float* __restrict__ fr, float (&acc)[8]) {
+// Shared-memory column index with one pad float every S = 8 * DOWN / UP columns (the distance between the windows of neighbouring threads):
+// the 16 threads of a row then start on 16 different banks instead of 2 (down = 2), 4 (no resampling) or 8 (up = 2).
+template <int LOGS> __device__ __forceinline__ int wm4_col(int c) { return c + (c >> LOGS); }
+
+template <class T, int UP, int DOWN, int KX0, int LOGS>
+__device__ __forceinline__ void wminor4_row(const float* __restrict__ row, int w0, const float* __restrict__ fr, float (&acc)[8]) {
     constexpr int NC = (7 * DOWN + 3) / UP + 2;
     float v[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) v[c] = row[c];
+    for (int c = 0; c < NC; c++) v[c] = row[wm4_col<LOGS>(w0 + c)];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
 #pragma unroll
@@ -141,10 +145,12 @@ template <class T, int UP, int DOWN>
 __global__ void __launch_bounds__(256) upfirdn2d_wminor4_kernel(UpfirdnParams p) {
     constexpr int FS = 4, TOW = 128, TOH = 16;
     constexpr int IW = ((TOW - 1) * DOWN + FS - 1) / UP + 2, IH = ((TOH - 1) * DOWN + FS - 1) / UP + 2;
-    constexpr int IWP = IW | 1;
     constexpr int NC = (7 * DOWN + 3) / UP + 2;
+    constexpr int LOGS = (DOWN == 2) ? 4 : (UP == 2) ? 2 : 3;        // log2(8 * DOWN / UP)
+    constexpr int IWT = IW + NC;                                       // columns staged per row (tail: zero slack for the last thread's window)
+    constexpr int IWP = (IWT + (IWT >> LOGS) + 1) | 1;
     __shared__ float sf[FS * FS];
-    __shared__ float st[IH * IWP + NC];
+    __shared__ float st[IH * IWP];
     stage_filter(sf, p);
     int64_t tile = blockIdx.x;
     const int tx = (int)(tile % p.tilesX); tile /= p.tilesX;
@@ -159,12 +165,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_wminor4_kernel(UpfirdnParams p)
         const int iy = iy_t0 + r;
         const bool rowin = (iy >= 0 && iy < p.inH);
         const T* xr = xb + (int64_t)iy * p.xsH;
-        for (int cc = lane; cc < IWP; cc += 32) {
+        for (int cc = lane; cc < IWT; cc += 32) {
             const int ix = ix_t0 + cc;
-            st[r * IWP + cc] = (rowin && cc < IW && ix >= 0 && ix < p.inW) ? io_traits<T>::ld(xr + ix) : 0.f;
+            st[r * IWP + wm4_col<LOGS>(cc)] = (rowin && cc < IW && ix >= 0 && ix < p.inW) ? io_traits<T>::ld(xr + ix) : 0.f;
         }
     }
-    if (threadIdx.x < NC) st[IH * IWP + threadIdx.x] = 0.f;
     __syncthreads();
     const int xg = threadIdx.x & 15, ly = threadIdx.x >> 4;
     const int oy = oy_t0 + ly, ox = ox_t0 + 8 * xg;
@@ -175,13 +180,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_wminor4_kernel(UpfirdnParams p)
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
-    const float* base = st + (iya - iy_t0) * IWP + (ixa - ix_t0);
+    const float* base = st + (iya - iy_t0) * IWP;
+    const int w0 = ixa - ix_t0;
 #pragma unroll
     for (int r = 0; r < (FS + UP - 1) / UP; r++) {
         const int ky = ky0 + r * UP;
         if (ky < FS) {
-            if (UP == 1 || kx0 == 0) wminor4_row<T, UP, DOWN, 0>(base + r * IWP, sf + ky * FS, acc);
-            else wminor4_row<T, UP, DOWN, 1>(base + r * IWP, sf + ky * FS, acc);
+            if (UP == 1 || kx0 == 0) wminor4_row<T, UP, DOWN, 0, LOGS>(base + r * IWP, w0, sf + ky * FS, acc);
+            else wminor4_row<T, UP, DOWN, 1, LOGS>(base + r * IWP, w0, sf + ky * FS, acc);
         }
     }
     T* yo = (T*)p.y + n * p.ysN + c * p.ysC + (int64_t)oy * p.ysH + ox;
