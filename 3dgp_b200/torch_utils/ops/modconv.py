@@ -75,8 +75,8 @@ class _ModConvLayer(torch.autograd.Function):
             y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=dev)
             epi = _lib.ConvEpilogue(_lib.ptr(d), _lib.ptr(nz), _lib.ptr(b), nps, 3 if act == 'lrelu' else 1, float(alpha), float(gain))
             with torch.cuda.device(dev):
-                rc = L.gp3d_conv2d_nhwc_bf16x3_act(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k,
-                                                   ctypes.byref(epi), _lib.stream_ptr())
+                rc = tc.timed(2.0 * N * H * W * Cin * Cout * k * k, lambda: L.gp3d_conv2d_nhwc_bf16x3_act(
+                    xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, ctypes.byref(epi), _lib.stream_ptr()))
             _lib.check(rc, 'conv2d_nhwc_bf16x3_act')
         else:
             c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
@@ -148,7 +148,8 @@ class _ModConvLayer(torch.autograd.Function):
         if up == 1:
             wdh, wdl = tc.weight_operands(weight, 'dgrad1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), pad_to=Cp)    # [Cin,k,k,Cout(+pad)]
             with torch.cuda.device(dev):
-                rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cp, Cin, k, 0, _lib.stream_ptr())
+                rc = tc.timed(2.0 * N * H * W * Cp * Cin * k * k, lambda: L.gp3d_conv2d_nhwc_bf16x3(
+                    dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cp, Cin, k, 0, _lib.stream_ptr()))
             _lib.check(rc, 'conv2d_nhwc_bf16x3')
         else:   # dx[i,j] = sum dc1[2i+ky, 2j+kx] w[co][ci][ky][kx]: strided gather over the (2H+1)^2 gradient
             wdh, wdl = tc.weight_operands(weight, 'dgrad2', lambda w_: w_.permute(1, 2, 3, 0), pad_to=Cp)                 # [Cin,ky,kx,Cout]

@@ -63,6 +63,19 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None):
 
 
 _weight_cache = {}
+CONV_TIMING = None   # set to a list to collect (start_event, end_event, algorithmic_flops) of the stride-1 bf16x3 conv launches (bench.py roofline)
+
+
+def timed(flops, launch):
+    """Runs `launch()`; when CONV_TIMING is a list, brackets it with CUDA events on the current stream."""
+    if CONV_TIMING is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = launch()
+    e1.record()
+    CONV_TIMING.append((e0, e1, flops))
+    return r
 
 
 def invalidate_weight_cache(param_ids=None):

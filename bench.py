@@ -200,7 +200,9 @@ def run_raymarch(args, rank, world, local):
         config=dict(workload='raymarch (BASELINE configs[2])', batch_per_gpu=B, rays=R_, samples_per_ray=2 * RM['N'], plane_res=RM['P'],
                     l2='inputs (%.2f GB of planes per GPU) larger than the 126 MB L2' % (B * 3 * RM['C'] * RM['P'] ** 2 * pb / 1e9),
                     rng='in-kernel Philox', mlp_mode=args.mlp_mode, parallelism=f'replicas x{world} (render does not shard)'),
-        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
+        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'],
+                      # dram__bytes_read + dram__bytes_write of one launch at this configuration (ncu --set full, profiles/r1_raymarch_fwd_v2_raw.csv)
+                      traffic=468696320 if (B == 16 and args.mlp_mode == 2 and not args.planes_fp16) else None,
                       kernel='raymarch_fwd2_kernel' if args.mlp_mode else 'raymarch_fwd_kernel', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg),
         e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(2 * B * R_ * 12), d2h_bytes_per_step=int(B * R_ * 20)),
         gpu_launches=args.steps, clocks=clocks,
@@ -325,10 +327,15 @@ def run_train_step(args, rank, world, local):
     # same steps, collecting the fused ray-march forward kernel's duration with events on the launching stream
     c0 = gp._lib.launch_count
     rmod.TIMING = []
+    tcm = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    tcm.CONV_TIMING = []
     ms2, _ = timed_region(step, args.steps, 0, world)
     launches = (gp._lib.launch_count - c0) // max(args.steps + 3, 1)
     ev = rmod.TIMING; rmod.TIMING = None
+    cev = tcm.CONV_TIMING; tcm.CONV_TIMING = None
     torch.cuda.synchronize()
+    conv_ms = float(sum(a.elapsed_time(b) for a, b, _ in cev)) or 1e-9
+    conv_flops = float(sum(f_ for _, _, f_ in cev))
     kms = [a.elapsed_time(b) for (a, b, *_rest) in ev]
     _, _, Bk, Rk, Nk, Pk, Ck, esz = ev[0]
     alg = raymarch_algorithmic_bytes(Bk, Rk, Nk, Pk, Ck, plane_bytes=esz)
@@ -358,9 +365,17 @@ def run_train_step(args, rank, world, local):
                     l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
                     parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)', conv_engine=args.conv_engine,
                     conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9)),
-        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
-                      kernel='raymarch_fwd2_kernel (3xTF32 MLP, inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
-                      launches_timed=len(kms), mean_ms=float(np.mean(kms))),
+        # dominant kernel of the step (~1/3 of its GPU time): the stride-1 bf16x3 tcgen05 convolution of the tri-plane decoder (forward + input gradient)
+        roofline=dict(bound='tensor', achieved=3.0 * conv_flops / (conv_ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
+                      frac=3.0 * conv_flops / (conv_ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'], traffic=None,
+                      kernel='conv_nhwc_bf16_kernel<128,3> (bf16x3: three bf16 MMAs per fp32-grade product; `achieved` counts the executed MMA FLOPs, '
+                             '`achieved_algorithmic` the convolution FLOPs)', achieved_algorithmic=conv_flops / (conv_ms * 1e-3) / 1e12,
+                      peak_source=peaks['source'], launches_timed=len(cev), mean_ms=conv_ms / max(len(cev), 1),
+                      algorithmic_flops_per_launch=conv_flops / max(len(cev), 1),
+                      traffic_note='ncu (profiles/r1_hot_kernels_summary.txt): DRAM bytes = operands + output once (0.54 GB read / 0.49 GB written for the 256->256 @256^2 B=8 launch)'),
+        roofline_raymarch=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
+                               kernel='raymarch_fwd2_kernel (3xTF32 MLP, inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
+                               launches_timed=len(kms), mean_ms=float(np.mean(kms))),
         roofline_step_tensor=dict(bound='tensor', achieved=flops_step / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
                                   frac=flops_step / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
                                   note='dense-contraction FLOPs of the whole step / step time, against the measured sustained bf16 GEMM peak'),
@@ -591,6 +606,8 @@ def main():
                     config=res['config'], roofline=res['roofline'], e2e=res['e2e'], gpu_launches=res['gpu_launches'], clocks=res['clocks'])
         if 'roofline_step_tensor' in res:
             line['roofline_step_tensor'] = res['roofline_step_tensor']
+        if 'roofline_raymarch' in res:
+            line['roofline_raymarch'] = res['roofline_raymarch']
         if 'forward_backward' in res:
             line['forward_backward'] = res['forward_backward']
         if world == 1 and not args.no_cpu_baseline:
