@@ -46,6 +46,8 @@ cl = lambda t: t.contiguous(memory_format=torch.channels_last)
 up.upfirdn2d(cl(torch.randn(B, 128, 513, 513, device=dev)), f4, padding=1, gain=4)
 up.upsample2d(cl(torch.randn(B, 96, 256, 256, device=dev)), f4)
 up.upfirdn2d(xd, f4, padding=2)
+up.upsample2d(torch.randn(B, 256, 128, 128, device=dev).half(), f4)          # NCHW fp16 (BASELINE configs[3] shape)
+up.downsample2d(torch.randn(B, 256, 256, 256, device=dev).half(), f4)
 ba.bias_act(cl(torch.randn(B, 128, 512, 512, device=dev)), torch.zeros(128, device=dev), act='lrelu')
 ba.bias_act(xd, torch.zeros(1024, device=dev).half(), act='lrelu', clamp=256)
 # optimiser: 64 M parameters
