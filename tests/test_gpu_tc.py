@@ -348,3 +348,41 @@ def test_channel_scale_fused_backward_matches_autograd(cl):
     yr = x * s.unsqueeze(2).unsqueeze(3)
     rx, rs = torch.autograd.grad(yr, [x, s], dy)
     assert torch.equal(y, yr) and torch.allclose(gx, rx, rtol=1e-6, atol=1e-6) and torch.allclose(gs, rs, rtol=1e-4, atol=1e-4)
+
+
+def test_conv_and_fir_at_baseline_size_exact_properties():
+    """BASELINE layer shape (b512.conv1: 128 -> 128 channels at 512^2; the FIR of b512.conv0 on 513^2): size-independent exact properties.
+    Scaling the input by 2 scales every bf16 (hi, lo) operand by exactly 2, so the convolution must double bit-for-bit; the fused
+    epilogue must equal conv followed by demod_act; the TMA-staged FIR must equal the register-tiled kernel (reached through a padded stride)."""
+    import ctypes
+    tc = _tc()
+    _lib = importlib.import_module('3dgp_b200._lib')
+    up = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    L = _lib.lib()
+    s = _lib.stream_ptr()
+    torch.manual_seed(21)
+    N, H, C = 2, 512, 128
+    x = torch.randn(N, H, H, C, device='cuda'); w = torch.randn(C, 3, 3, C, device='cuda') / 34
+    wh, wl = tc.split_bf16(w)
+    ys = []
+    for scale in (1.0, 2.0):
+        xh, xl = tc.split_bf16(x * scale)
+        y = torch.empty(N, H, H, C, device='cuda')
+        _lib.check(L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, H, C, C, 3, 0, s), 'conv')
+        ys.append(y)
+    assert torch.isfinite(ys[0]).all() and torch.equal(ys[1], ys[0] * 2)
+    d = torch.rand(N, C, device='cuda') + 0.5; nz = torch.randn(H, H, device='cuda') * 0.1; b = torch.randn(C, device='cuda') * 0.1
+    ref = torch.empty_like(ys[0]); got = torch.empty_like(ys[0])
+    _lib.check(L.gp3d_demod_act(ys[0].data_ptr(), d.data_ptr(), nz.data_ptr(), 0, b.data_ptr(), ref.data_ptr(), 0, N, C, H * H, 1, 3, 0.2, 1.4142135, -1.0, s), 'demod')
+    xh, xl = tc.split_bf16(x)
+    epi = _lib.ConvEpilogue(d.data_ptr(), nz.data_ptr(), b.data_ptr(), 0, 3, 0.2, 1.4142135)
+    _lib.check(L.gp3d_conv2d_nhwc_bf16x3_act(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), got.data_ptr(), N, H, H, C, C, 3, ctypes.byref(epi), s), 'conv_act')
+    assert torch.equal(got, ref)
+    del ys, ref, got, xh, xl
+    f = up.setup_filter([1, 3, 3, 1], device='cuda')
+    c1 = torch.randn(N, 513, 513, C, device='cuda')
+    a = up._plugin.upfirdn2d(c1.permute(0, 3, 1, 2), f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)
+    c1s = torch.zeros(N, 513, 513, C + 4, device='cuda')[..., :C]
+    c1s.copy_(c1)
+    b2 = up._plugin.upfirdn2d(c1s.permute(0, 3, 1, 2), f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)
+    assert a.shape == (N, C, 512, 512) and torch.equal(a.contiguous(), b2.contiguous())
