@@ -17,7 +17,7 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 
 class ConvEpilogue(ctypes.Structure):
     """gp3d_conv_epilogue (include/gp3d_b200.h)."""
-    _fields_ = [('dcoef', c_void_p), ('noise', c_void_p), ('bias', c_void_p), ('noise_per_sample', c_int), ('act', c_int), ('alpha', c_float), ('gain', c_float)]
+    _fields_ = [('dcoef', c_void_p), ('noise', c_void_p), ('bias', c_void_p), ('noise_per_sample', c_int), ('act', c_int), ('alpha', c_float), ('gain', c_float), ('clamp', c_float)]
 
 
 class RaymarchOpts(ctypes.Structure):
@@ -47,6 +47,8 @@ PROTOTYPES = {
     'gp3d_demod_act_bwd': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
     'gp3d_demod_act_bwd_split': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
     'gp3d_fir4_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_float] + [c_int] * 8 + [c_void_p] * 3 + [ctypes.POINTER(ConvEpilogue), c_void_p]),
+    'gp3d_conv2d_nhwc_act': (c_int, [c_void_p] * 5 + [c_int] * 6 + [ctypes.POINTER(ConvEpilogue), c_void_p]),
+    'gp3d_act_bwd_split': (c_int, [c_void_p] * 5 + [c_int, c_void_p] + [c_int] * 4 + [c_float] * 3 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16x3_act': (c_int, [c_void_p] * 5 + [c_int] * 6 + [ctypes.POINTER(ConvEpilogue), c_void_p]),
     'gp3d_modulate_bwd': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     'gp3d_grad_epilogue': (c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),

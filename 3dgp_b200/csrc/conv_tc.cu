@@ -33,7 +33,7 @@ struct ConvGeom {
 struct ConvEpi {
     const float* dcoef; const float* noise; const float* bias;
     int enabled, noise_per_sample, act;
-    float alpha, gain;
+    float alpha, gain, clamp;      // clamp <= 0: none
 };
 
 // TERMS == 1: y += xh * wh.   TERMS == 3 (error-compensated "bf16x3", ~2^-16 relative): y += xh*wh + xh*wl + xl*wh with
@@ -172,6 +172,10 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             o.z = (o.z > 0.f) ? o.z : o.z * ep.alpha; o.w = (o.w > 0.f) ? o.w : o.w * ep.alpha;
                         }
                         o.x *= ep.gain; o.y *= ep.gain; o.z *= ep.gain; o.w *= ep.gain;
+                        if (ep.clamp > 0.f) {
+                            o.x = fminf(fmaxf(o.x, -ep.clamp), ep.clamp); o.y = fminf(fmaxf(o.y, -ep.clamp), ep.clamp);
+                            o.z = fminf(fmaxf(o.z, -ep.clamp), ep.clamp); o.w = fminf(fmaxf(o.w, -ep.clamp), ep.clamp);
+                        }
                     }
                     float4* dst = reinterpret_cast<float4*>(yrow + c + j);
                     if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
@@ -220,7 +224,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         GP3D_CHECK_ARG(epi->act == 1 || epi->act == 3, "%s: fused epilogue activation must be linear (1) or lrelu (3), got %d", who, epi->act);
         GP3D_CHECK_ARG((!epi->dcoef || gp3d_aligned16(epi->dcoef)) && (!epi->bias || gp3d_aligned16(epi->bias)), "%s: epilogue vectors must be 16-byte aligned", who);
         ep.dcoef = epi->dcoef; ep.noise = epi->noise; ep.bias = epi->bias; ep.enabled = 1; ep.noise_per_sample = epi->noise_per_sample;
-        ep.act = epi->act; ep.alpha = epi->alpha; ep.gain = epi->gain;
+        ep.act = epi->act; ep.alpha = epi->alpha; ep.gain = epi->gain; ep.clamp = epi->clamp;
     }
     GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "%s: both low-order operands are required", who);
     GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && HoP > 0 && WoP > 0, "%s: empty tensor", who);
@@ -310,6 +314,12 @@ extern "C" int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const
     GP3D_CHECK_ARG(xl && wl, "conv2d_nhwc_bf16x3_act: null low-order operand");
     GP3D_CHECK_ARG(epi != nullptr, "conv2d_nhwc_bf16x3_act: null epilogue description");
     return conv_same(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, 0, stream, "conv2d_nhwc_bf16x3_act", epi);
+}
+
+extern "C" int gp3d_conv2d_nhwc_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                                    int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream) {
+    GP3D_CHECK_ARG(epi != nullptr, "conv2d_nhwc_act: null epilogue description");
+    return conv_same(xh, xl, wh, wl, y, N, H, W, Cin, Cout, ksize, 0, stream, "conv2d_nhwc_act", epi);
 }
 
 extern "C" int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, float* y,

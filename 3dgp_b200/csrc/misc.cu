@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restr
                                                             int noise_per_sample, const float* __restrict__ b,
                                                             float* __restrict__ dc, float* __restrict__ g_d, float* __restrict__ g_b,
                                                             float* __restrict__ g_ns, int N, int HW, int C, float alpha, float gain, int chunks,
-                                                            __nv_bfloat16* __restrict__ dc_hi, __nv_bfloat16* __restrict__ dc_lo, int Cp) {
+                                                            __nv_bfloat16* __restrict__ dc_hi, __nv_bfloat16* __restrict__ dc_lo, int Cp, float clamp) {
     extern __shared__ float red_smem[];
     const float nscale = (noise && noise_scale) ? *noise_scale : 1.f;
     const int CV_all = C / 4;
@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restr
                 for (int k = 0; k < 4; k++) {
                     const float slope = (ACT == 3 && yv[k] < 0.f) ? alpha : 1.f;
                     dt[k] = gy[k] * gain * slope;
+                    if (clamp > 0.f && !(yv[k] > -clamp && yv[k] < clamp)) dt[k] = 0.f;      // bias_act.cu: clamped outputs pass no gradient
                     const float t = yv[k] / (gain * slope);               // pre-activation: c * d + noise + b
                     const float c = (t - nz - bb[k]) / dd[k];
                     o[k] = dt[k] * dd[k];
@@ -490,10 +491,10 @@ __global__ void __launch_bounds__(256) demod_act_bwd_kernel(const float* __restr
 #pragma unroll
                     for (int k = 0; k < 4; k++) { h[k] = __float2bfloat16_rn(o[k]); l[k] = __float2bfloat16_rn(o[k] - __bfloat162float(h[k])); }
                     *reinterpret_cast<uint2*>(dc_hi + offp) = *reinterpret_cast<const uint2*>(h);
-                    *reinterpret_cast<uint2*>(dc_lo + offp) = *reinterpret_cast<const uint2*>(l);
+                    if (dc_lo) *reinterpret_cast<uint2*>(dc_lo + offp) = *reinterpret_cast<const uint2*>(l);
                     if (4 * cv < Cp - C) {     // Cp - C <= C: the first (Cp-C)/4 channel lanes also clear the padding
                         *reinterpret_cast<uint2*>(dc_hi + ((int64_t)n * HW + px) * Cp + C + 4 * cv) = make_uint2(0u, 0u);
-                        *reinterpret_cast<uint2*>(dc_lo + ((int64_t)n * HW + px) * Cp + C + 4 * cv) = make_uint2(0u, 0u);
+                        if (dc_lo) *reinterpret_cast<uint2*>(dc_lo + ((int64_t)n * HW + px) * Cp + C + 4 * cv) = make_uint2(0u, 0u);
                     }
                 } else {
                     *reinterpret_cast<float4*>(dc + off) = make_float4(o[0], o[1], o[2], o[3]);
@@ -569,8 +570,26 @@ extern "C" int gp3d_demod_act_bwd_split(const float* dy, const float* y, const f
     const size_t smem = 256 * sizeof(float4);
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* hi = (__nv_bfloat16*)dc_hi; __nv_bfloat16* lo = (__nv_bfloat16*)dc_lo;
-    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad);
-    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad);
+    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad, -1.f);
+    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, d, noise, noise_scale, noise_per_sample, b, dc, g_d, g_b, g_ns, N, HW, C, alpha, gain, chunks, hi, lo, C_pad, -1.f);
+    GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_act_bwd_split(const float* dy, const float* y, float* dc, void* dc_hi, void* dc_lo, int C_pad, float* g_b,
+                                  int N, int HW, int C, int act, float alpha, float gain, float clamp, void* stream) {
+    GP3D_CHECK_ARG(dy && y && N >= 1 && HW >= 1 && C >= 4 && C % 4 == 0, "act_bwd_split: bad arguments (C must be a multiple of 4)");
+    GP3D_CHECK_ARG((dc != nullptr) != (dc_hi != nullptr) && !(dc_lo && !dc_hi), "act_bwd_split: give either dc (float32) or dc_hi (+ optional dc_lo)");
+    GP3D_CHECK_ARG(!dc_hi || (C_pad >= C && C_pad % 4 == 0 && C_pad - C <= C), "act_bwd_split: padded channel count %d incompatible with C=%d", C_pad, C);
+    GP3D_CHECK_ARG(act == 1 || act == 3, "act_bwd_split: only linear (1) and lrelu (3) are fused, got %d", act);
+    GP3D_CHECK_ARG(gain != 0.f, "act_bwd_split: gain must be non-zero");
+    GP3D_CHECK_ARG(gp3d_aligned16(dy) && gp3d_aligned16(y) && (!dc || gp3d_aligned16(dc)) && (!dc_hi || gp3d_aligned16(dc_hi)) && (!dc_lo || gp3d_aligned16(dc_lo)),
+                   "act_bwd_split: pointers must be 16-byte aligned");
+    const int chunks = reduce_chunks(N, HW);
+    const size_t smem = 256 * sizeof(float4);
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* hi = (__nv_bfloat16*)dc_hi; __nv_bfloat16* lo = (__nv_bfloat16*)dc_lo;
+    if (act == 3) demod_act_bwd_kernel<3><<<N * chunks, 256, smem, st>>>(dy, y, nullptr, nullptr, nullptr, 0, nullptr, dc, nullptr, g_b, nullptr, N, HW, C, alpha, gain, chunks, hi, lo, C_pad, clamp);
+    else demod_act_bwd_kernel<1><<<N * chunks, 256, smem, st>>>(dy, y, nullptr, nullptr, nullptr, 0, nullptr, dc, nullptr, g_b, nullptr, N, HW, C, alpha, gain, chunks, hi, lo, C_pad, clamp);
     GP3D_RETURN_LAUNCH();
 }
 

@@ -186,3 +186,94 @@ def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=Non
     if noise is not None and not torch.is_tensor(noise_strength):
         noise_strength = torch.as_tensor(float(noise_strength if noise_strength is not None else 1.0), device=x.device)
     return _ModConvLayer.apply(x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Conv2dLayer of the discriminator / depth adaptor (layers.py:228-241) as one first-order autograd node:
+#   y = clamp( act( conv( x * s[n, ci]?, w * wgain ) + b ) * gain )
+# forward : split (hyper-modulation fused) -> tcgen05 conv whose epilogue applies bias / activation / gain / clamp
+# backward: act backward (clamp mask, bias gradient) emitting the bf16 operand -> tcgen05 input-gradient conv (+ modulate_bwd) + weight gradient.
+# terms = 1 (single bf16 product: the blocks the reference runs in fp16) or 3 (bf16x3).  Stride-1 'same' shapes only.
+
+def conv_act_eligible(x, weight, k, up, down, padding, act, cin, cout):
+    return (x.is_cuda and x.dtype == torch.float32 and up == 1 and down == 1 and k in (1, 3) and padding == k // 2 and act in ('linear', 'lrelu')
+            and cin % 64 == 0 and cout % 64 == 0 and tc.channels_eligible(cin, cout) and tc.channels_eligible(cout, cin))
+
+
+class _ConvBiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, s, wgain, act, alpha, gain, clamp, terms):
+        L = _lib.lib()
+        N, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        dev = x.device
+        xn = _nhwc(x)
+        st = s.to(torch.float32).contiguous() if s is not None else None
+        xh, xl = tc.split_bf16(xn, styles=st, want_lo=(terms == 3))
+        wh, wl = tc.weight_operands(weight, ('cfwd', float(wgain)), lambda w_: (w_ * wgain).permute(0, 2, 3, 1), terms)
+        b = bias.to(torch.float32).contiguous() if bias is not None else None
+        # channel-minor storage behind an ordinary NCHW-shaped tensor (not a view: DiscriminatorBlock adds into the skip output in place)
+        y = torch.empty([N, Cout, H, W], dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        epi = _lib.ConvEpilogue(None, None, _lib.ptr(b), 0, 3 if act == 'lrelu' else 1, float(alpha), float(gain), float(clamp) if clamp is not None else -1.0)
+        with torch.cuda.device(dev):
+            rc = L.gp3d_conv2d_nhwc_act(xh.data_ptr(), _lib.ptr(xl), wh.data_ptr(), _lib.ptr(wl), y.data_ptr(), N, H, W, Cin, Cout, k, ctypes.byref(epi), _lib.stream_ptr())
+        _lib.check(rc, 'conv2d_nhwc_act')
+        # linear, unclamped layers (the residual skip) do not need their output in the backward: callers may update it in place (y.add_(x))
+        keep_y = (act == 'lrelu') or (clamp is not None)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(xh, xl if xl is not None else empty, weight, st if st is not None else empty, xn if st is not None else empty,
+                              y if keep_y else empty)
+        ctx.cfg = (N, Cin, H, W, Cout, k, float(wgain), act, float(alpha), float(gain), clamp, terms, bias is not None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        from . import conv2d_gradfix
+        L = _lib.lib()
+        xh, xl, weight, st, xn, y = ctx.saved_tensors
+        N, Cin, H, W, Cout, k, wgain, act, alpha, gain, clamp, terms, has_b = ctx.cfg
+        dev = dy.device
+        xl = xl if xl.numel() else None
+        dyn = _nhwc(dy.to(torch.float32))
+        dch = torch.empty([N, H, W, Cout], dtype=torch.bfloat16, device=dev)
+        dcl = torch.empty_like(dch) if terms == 3 else None
+        g_b = torch.zeros([Cout], dtype=torch.float32, device=dev) if (has_b and ctx.needs_input_grad[2]) else None
+        yref = y if y.numel() else dyn            # linear / unclamped: the slope does not depend on y
+        with torch.cuda.device(dev):
+            rc = L.gp3d_act_bwd_split(dyn.data_ptr(), yref.data_ptr(), None, dch.data_ptr(), _lib.ptr(dcl), Cout, _lib.ptr(g_b), N, H * W, Cout,
+                                      3 if act == 'lrelu' else 1, alpha, gain, float(clamp) if clamp is not None else -1.0, _lib.stream_ptr())
+        _lib.check(rc, 'act_bwd_split')
+        dx = g_s = gw = None
+        if ctx.needs_input_grad[0] or (st.numel() and ctx.needs_input_grad[3]):
+            wdh, wdl = tc.weight_operands(weight, ('cadj', wgain), lambda w_: (w_ * wgain).flip([2, 3]).permute(1, 2, 3, 0), terms)      # [Cin,k,k,Cout]
+            dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                if terms == 3:
+                    rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
+                else:
+                    rc = L.gp3d_conv2d_nhwc_bf16(dch.data_ptr(), wdh.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
+            _lib.check(rc, 'conv2d_nhwc (input gradient)')
+            if st.numel():
+                dxo = torch.empty_like(dxs)
+                g_s = torch.zeros_like(st)
+                with torch.cuda.device(dev):
+                    rc = L.gp3d_modulate_bwd(dxs.data_ptr(), xn.data_ptr(), st.data_ptr(), dxo.data_ptr(), g_s.data_ptr(), N, H * W, Cin, _lib.stream_ptr())
+                _lib.check(rc, 'modulate_bwd')
+                dx = dxo.permute(0, 3, 1, 2)
+            else:
+                dx = dxs.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled:
+            taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
+            gwf = torch.zeros([Cout, k * k, Cin], dtype=torch.float32, device=dev)
+            arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
+            with torch.cuda.device(dev):
+                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), _lib.ptr(dcl), xh.data_ptr(), _lib.ptr(xl), gwf.data_ptr(), N, H, W, Cout, H, W, Cin, k * k,
+                                            len(taps), ctypes.cast(arr, ctypes.c_void_p), 1, 1, H, W, _lib.stream_ptr())
+            _lib.check(rc, 'wgrad_taps_nhwc')
+            gw = (gwf.view(Cout, k, k, Cin).permute(0, 3, 1, 2) * wgain).to(weight.dtype)
+        return dx, gw, g_b, g_s, None, None, None, None, None, None
+
+
+def conv_bias_act(x, weight, bias=None, s=None, wgain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, terms=3):
+    return _ConvBiasAct.apply(x, weight, bias, s, wgain, act, alpha, gain, clamp, terms)

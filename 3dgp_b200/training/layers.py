@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from ..torch_utils.ops import tc, bias_act, conv2d_resample, upfirdn2d
+from ..torch_utils.ops import tc, bias_act, conv2d_gradfix, conv2d_resample, modconv, upfirdn2d
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -207,6 +207,16 @@ class Conv2dLayer(torch.nn.Module):
             assert c_dim > 0
 
     def forward(self, x, c=None, gain=1):
+        k = self.weight.shape[2]
+        if (fused_hyper_mod and isinstance(self.weight, torch.nn.Parameter)
+                and modconv.conv_act_eligible(x, self.weight, k, self.up, self.down, self.padding, self.activation, self.in_channels, self.out_channels)):
+            # first-order fused node (ops/modconv.py::_ConvBiasAct): hyper-modulation in the operand split, bias / activation / gain / clamp in the
+            # conv epilogue; the loss switches this off around the R1 forward, which must stay twice differentiable
+            s = (1.0 + self.affine(c).tanh()) if self.affine is not None else None
+            alpha = bias_act.activation_funcs[self.activation].def_alpha
+            return modconv.conv_bias_act(x, self.weight, self.bias, s, self.weight_gain, self.activation, alpha if alpha is not None else 0.0,
+                                         self.act_gain * gain, self.conv_clamp * gain if self.conv_clamp is not None else None,
+                                         conv2d_gradfix._terms_for(x.dtype))
         w = self.weight * self.weight_gain
         if self.affine is not None:
             if fused_hyper_mod and x.is_cuda:

@@ -166,6 +166,10 @@ int gp3d_demod_act_bwd(const float* dy, const float* y, const float* d, const fl
 int gp3d_demod_act_bwd_split(const float* dy, const float* y, const float* d, const float* noise, const float* noise_scale, int noise_per_sample,
                              const float* b, float* dc, void* dc_hi, void* dc_lo, int C_pad, float* g_d, float* g_b, float* g_ns,
                              int N, int HW, int C, int act, float alpha, float gain, void* stream);
+/* same with bias_act's clamp (gradient passes only where |y| < clamp; clamp <= 0: none) and an optional low-order half
+ * (dc_lo == NULL: single-term bf16 operand) -- the backward of Conv2dLayer's bias_act in the discriminator. */
+int gp3d_act_bwd_split(const float* dy, const float* y, float* dc, void* dc_hi, void* dc_lo, int C_pad, float* g_b,
+                       int N, int HW, int C, int act, float alpha, float gain, float clamp, void* stream);
 int gp3d_modulate_bwd(const float* dxs, const float* x, const float* s, float* dx, float* g_s, int N, int HW, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -226,9 +230,14 @@ typedef struct gp3d_conv_epilogue {
     int noise_per_sample;
     int act;            /* 1 linear, 3 lrelu */
     float alpha, gain;
+    float clamp;        /* > 0: clamp the result to [-clamp, clamp] (bias_act's clamp, layers.py:239); <= 0: none */
 } gp3d_conv_epilogue;
 int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                                 int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
+/* same epilogue for either precision: xl / wl both NULL = single-term bf16 (the discriminator's low-precision blocks: Conv2dLayer's
+ * conv + bias_act, layers.py:228-241, dcoef / noise NULL), both given = bf16x3. */
+int gp3d_conv2d_nhwc_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
+                         int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
 
 /* 4x4 FIR, up = down = 1, dense channel-minor float32 [N][H][W][C] (C % 32 == 0), input window staged by TMA: the filter after the
  * up-sampling convolution (conv2d_resample.py:119-126) and its adjoint.  out = (H + pady0 + pady1 - 3) x (W + padx0 + padx1 - 3).

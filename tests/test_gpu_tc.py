@@ -386,3 +386,38 @@ def test_conv_and_fir_at_baseline_size_exact_properties():
     c1s.copy_(c1)
     b2 = up._plugin.upfirdn2d(c1s.permute(0, 3, 1, 2), f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)
     assert a.shape == (N, C, 512, 512) and torch.equal(a.contiguous(), b2.contiguous())
+
+
+@pytest.mark.parametrize('terms', [3, 1])
+@pytest.mark.parametrize('k,act,hyper,bias,clamp,gain', [(3, 'lrelu', True, True, 256, 1.0), (1, 'linear', False, False, None, 0.7071), (3, 'lrelu', False, True, 0.5, 1.0)])
+def test_fused_conv2d_layer_matches_unfused(terms, k, act, hyper, bias, clamp, gain):
+    """Conv2dLayer (layers.py:228-241) through ops/modconv.py::_ConvBiasAct against the reference-shaped composition
+    hyper-mod * x -> conv2d_gradfix -> bias_act on the same weights: output and every gradient, both precisions."""
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    torch.manual_seed(13)
+    layer = layers.Conv2dLayer(128, 256, kernel_size=k, bias=bias, activation=act, conv_clamp=clamp, c_dim=32 if hyper else 0, hyper_mod=hyper).cuda()
+    with torch.no_grad():
+        if bias:
+            layer.bias.normal_(0, 0.3)
+    x = torch.randn(3, 128, 20, 24, device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    c = torch.randn(3, 32, device='cuda') if hyper else None
+    dy = torch.randn(3, 256, 20, 24, device='cuda')
+    params = [x] + [p for p in layer.parameters()]
+    outs = []
+    for fused in (True, False):
+        layers.fused_hyper_mod = fused
+        with cg.tc_terms(terms):
+            y = layer(x, c=c, gain=gain)
+            gs = torch.autograd.grad(y, params, dy)
+        outs.append((y, gs))
+    layers.fused_hyper_mod = True
+    rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+    tol = 3e-4 if terms == 3 else 2e-3
+    assert outs[0][0].shape == outs[1][0].shape and rel(outs[0][0], outs[1][0]) < tol
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert a.shape == b.shape and rel(a, b) < tol, (a.shape, rel(a, b))
+    if clamp is not None and clamp < 1:
+        assert (outs[0][0].abs() <= clamp * gain + 1e-6).all() and (outs[0][0].abs() >= clamp * gain - 1e-6).any()     # the clamp is active in this case
+    y2 = layer(x, c=c, gain=gain)
+    y2.add_(1.0)                                             # in-place update of the output (DiscriminatorBlock: y.add_(x)) must be legal
