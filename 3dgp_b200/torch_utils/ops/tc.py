@@ -1,4 +1,6 @@
 """Tensor-core (tcgen05 / TMEM) contraction ops of lib3dgp_b200: plain TN GEMM and NHWC implicit-GEMM convolution."""
+import weakref
+
 import torch
 
 from ... import _lib
@@ -108,16 +110,20 @@ def _operands_of(w, tag, make_nhwc, terms):
 def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
     """bf16 (hi, lo) operand pair of a weight tensor in the layout `make_nhwc(weight)` produces ([rows][taps][cols], cols contiguous).
     Parameters are re-laid-out and split ONCE per optimiser step: the cache is keyed by (id, tag) and invalidated by the tensor's
-    autograd version counter (bumped by every in-place update)."""
+    autograd version counter (bumped by every in-place update).  Every entry holds a weak reference to its parameter: an id() reused by
+    a new tensor after the old one died (same address, version 0, same shape is entirely possible) can never produce a hit."""
     key = (id(weight), tag, terms, pad_to)
     ver = (weight._version, weight.data_ptr(), tuple(weight.shape))
     hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[3]() is weight:
         return hit[1], hit[2]
     wn = make_nhwc(weight.detach().to(torch.float32)).contiguous()
     wh, wl = split_bf16(wn, want_lo=(terms == 3), pad_to=pad_to)
     if isinstance(weight, torch.nn.Parameter):
-        _weight_cache[key] = (ver, wh, wl)
+        if len(_weight_cache) > 4096:          # dead entries of discarded networks
+            for k_ in [k_ for k_, v_ in _weight_cache.items() if v_[3]() is None]:
+                del _weight_cache[k_]
+        _weight_cache[key] = (ver, wh, wl, weakref.ref(weight))
     return wh, wl
 
 
