@@ -14,7 +14,7 @@ from . import tc
 enabled = False                     # kept for training_loop.py:78 (`conv2d_gradfix.enabled = True`)
 weight_gradients_disabled = False   # toggled by no_weight_gradients()
 tc_enabled = True                   # route eligible convs (and their input-gradient convs) to the tcgen05 kernels
-tc_stats = dict(tc=0, aten=0)       # how many primitive convolutions went where (bench.py / tests)
+tc_stats = tc.stats                 # how many primitive convolutions went where (bench.py / tests); same dict as ops.tc.stats
 
 
 _forced_terms = None

@@ -18,9 +18,12 @@ from . import tc, upfirdn2d
 
 
 def eligible(x, weight, up, conv_clamp):
+    """Forward (Cin -> Cout), input-gradient (Cout padded to whole 64-channel blocks -> Cin) and weight-gradient shapes must all be covered by the
+    tensor-core kernels; anything else (e.g. Cin = 192 from a non-power-of-two cbase) takes the unfused composition."""
     Cout, Cin, k, _ = weight.shape
+    Cp = ((Cout + 63) // 64) * 64
     return (x.is_cuda and x.dtype == torch.float32 and conv_clamp is None and up in (1, 2) and k in (1, 3) and (up == 1 or k == 3)
-            and tc.channels_eligible(Cin, Cout) and Cin % 4 == 0 and Cout % 4 == 0)
+            and tc.channels_eligible(Cin, Cout) and tc.channels_eligible(Cp, Cin) and tc.wgrad_eligible(Cin, Cp) and Cin % 4 == 0 and Cout % 4 == 0)
 
 
 def _fir_tma_ok(C, fir):
@@ -56,6 +59,7 @@ class _ModConvLayer(torch.autograd.Function):
     def forward(ctx, x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain):
         L = _lib.lib()
         upfirdn2d._init()
+        tc.stats['fused'] += 1
         N, Cin, H, W = x.shape
         Cout, _, k, _ = weight.shape
         dev = x.device
@@ -103,9 +107,13 @@ class _ModConvLayer(torch.autograd.Function):
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
+        from . import conv2d_gradfix
         L = _lib.lib()
         xn, xh, xl, weight, st, d, y, noise, noise_strength, b, fir = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        need_gw = ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled
         N, Cin, H, W, Cout, k, up, act, alpha, gain, nps, Ho, Wo = ctx.cfg
         dev = dy.device
         has_d, has_n, has_b = d.numel() > 0, noise.numel() > 0, b.numel() > 0
@@ -143,9 +151,11 @@ class _ModConvLayer(torch.autograd.Function):
                 dc = upfirdn2d._plugin.upfirdn2d(dc.permute(0, 3, 1, 2), fir, 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0).permute(0, 2, 3, 1).contiguous()
                 dch, dcl = tc.split_bf16(dc, pad_to=Cp)
         # input gradient
-        dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
+        dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev) if need_dx else None
         assert tc.channels_eligible(Cp, Cin)
-        if up == 1:
+        if not need_dx:
+            pass
+        elif up == 1:
             wdh, wdl = tc.weight_operands(weight, 'dgrad1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), pad_to=Cp)    # [Cin,k,k,Cout(+pad)]
             with torch.cuda.device(dev):
                 rc = tc.timed(2.0 * N * H * W * Cp * Cin * k * k, lambda: L.gp3d_conv2d_nhwc_bf16x3(
@@ -156,8 +166,10 @@ class _ModConvLayer(torch.autograd.Function):
             taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
             tc._taps_launch(dch, dcl, wdh, wdl, dxs, N, 2 * H + 1, 2 * W + 1, Cp, Cin, 9, taps, 2, H, W, H, W, 1, 1, 0, 0)
         # weight gradient
-        if tc.wgrad_eligible(Cin, Cp):
-            import ctypes
+        gw = None
+        if not need_gw:
+            pass
+        elif tc.wgrad_eligible(Cin, Cp):
             if up == 1:
                 taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
                 sa, sb, HoP, WoP, Hd, Wd = 1, 1, H, W, H, W
@@ -170,16 +182,19 @@ class _ModConvLayer(torch.autograd.Function):
                 rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), dcl.data_ptr(), xh.data_ptr(), xl.data_ptr(), gw.data_ptr(), N, Hd, Wd, Cp, H, W, Cin, k * k,
                                             len(taps), ctypes.cast(arr, ctypes.c_void_p), sa, sb, HoP, WoP, _lib.stream_ptr())
             _lib.check(rc, 'wgrad_taps_nhwc')
-            gw = gw[:Cout].view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+            gw = gw[:Cout].view(Cout, k, k, Cin).permute(0, 3, 1, 2).to(weight.dtype)
         else:
             raise RuntimeError('modconv: weight-gradient shape not covered by the tensor-core kernel (Cin %% 64 != 0)')
         # through the modulation
-        dx = torch.empty_like(dxs)
-        g_s = torch.zeros_like(st)
-        with torch.cuda.device(dev):
-            rc = L.gp3d_modulate_bwd(dxs.data_ptr(), xn.data_ptr(), st.data_ptr(), dx.data_ptr(), g_s.data_ptr(), N, H * W, Cin, _lib.stream_ptr())
-        _lib.check(rc, 'modulate_bwd')
-        return (dx.permute(0, 3, 1, 2), gw.to(weight.dtype), g_s, g_d, None, g_ns, g_b, None, None, None, None, None)
+        dx = g_s = None
+        if need_dx:
+            dx = torch.empty_like(dxs)
+            g_s = torch.zeros_like(st)
+            with torch.cuda.device(dev):
+                rc = L.gp3d_modulate_bwd(dxs.data_ptr(), xn.data_ptr(), st.data_ptr(), dx.data_ptr(), g_s.data_ptr(), N, H * W, Cin, _lib.stream_ptr())
+            _lib.check(rc, 'modulate_bwd')
+            dx = dx.permute(0, 3, 1, 2)
+        return (dx, gw, g_s, g_d, None, g_ns, g_b, None, None, None, None, None)
 
 
 def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=None, bias=None, up=1, fir=None, act='lrelu', alpha=0.2, gain=1.0):
@@ -204,6 +219,7 @@ class _ConvBiasAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, s, wgain, act, alpha, gain, clamp, terms):
         L = _lib.lib()
+        tc.stats['fused'] += 1
         N, Cin, H, W = x.shape
         Cout, _, k, _ = weight.shape
         dev = x.device

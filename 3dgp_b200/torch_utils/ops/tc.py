@@ -65,6 +65,7 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None):
 
 
 _weight_cache = {}
+stats = dict(tc=0, aten=0, fused=0)   # primitive convs on the tcgen05 kernels / on ATen, fused layer nodes (ops/modconv.py); read by tests and bench.py
 CONV_TIMING = None   # set to a list to collect (start_event, end_event, algorithmic_flops) of the stride-1 bf16x3 conv launches (bench.py roofline)
 
 
@@ -110,8 +111,8 @@ def _operands_of(w, tag, make_nhwc, terms):
 def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
     """bf16 (hi, lo) operand pair of a weight tensor in the layout `make_nhwc(weight)` produces ([rows][taps][cols], cols contiguous).
     Parameters are re-laid-out and split ONCE per optimiser step: the cache is keyed by (id, tag) and invalidated by the tensor's
-    autograd version counter (bumped by every in-place update).  Every entry holds a weak reference to its parameter: an id() reused by
-    a new tensor after the old one died (same address, version 0, same shape is entirely possible) can never produce a hit."""
+    autograd version counter (bumped by every in-place update).  Every entry holds a weak reference to its parameter whose callback removes
+    the entry: an id() reused by a new tensor after the old one died can never produce a hit, and no operand copy outlives its weight."""
     key = (id(weight), tag, terms, pad_to)
     ver = (weight._version, weight.data_ptr(), tuple(weight.shape))
     hit = _weight_cache.get(key)
@@ -120,10 +121,8 @@ def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
     wn = make_nhwc(weight.detach().to(torch.float32)).contiguous()
     wh, wl = split_bf16(wn, want_lo=(terms == 3), pad_to=pad_to)
     if isinstance(weight, torch.nn.Parameter):
-        if len(_weight_cache) > 4096:          # dead entries of discarded networks
-            for k_ in [k_ for k_, v_ in _weight_cache.items() if v_[3]() is None]:
-                del _weight_cache[k_]
-        _weight_cache[key] = (ver, wh, wl, weakref.ref(weight))
+        # the entry dies with its parameter (discarded networks, deep-copied snapshots): no operand copies outlive their weights on the device
+        _weight_cache[key] = (ver, wh, wl, weakref.ref(weight, lambda _r, key=key: _weight_cache.pop(key, None)))
     return wh, wl
 
 

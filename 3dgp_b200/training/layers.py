@@ -1,6 +1,8 @@
 """FC / mapping / conv building blocks with the reference's parameterisation and state-dict keys
 (reference src/training/layers.py).  Activations and resampling run on lib3dgp_b200's kernels through
 torch_utils.ops; dense contractions go through conv2d_gradfix / torch.addmm."""
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -146,7 +148,21 @@ class MappingNetwork(torch.nn.Module):
         return x
 
 
-fused_hyper_mod = True     # first-order fused backward of the hyper-modulation; the loss switches it off around the R1 (double-backward) forward
+_first_order = True     # Conv2dLayer may use first-order-only fused nodes (ops/modconv.py::_ConvBiasAct, _ChannelScale); see first_order_only()
+
+
+@contextlib.contextmanager
+def first_order_only(flag=True):
+    """Scope inside which Conv2dLayer forwards are (flag=True, the default state) / are not (flag=False) allowed to run as first-order-only fused
+    nodes.  Code that differentiates the discriminator TWICE (R1, loss.py:316-327; any gradient penalty) wraps its forward in
+    `first_order_only(False)`: that forward then stays on the twice-differentiable composition (conv2d_gradfix + bias_act)."""
+    global _first_order
+    old = _first_order
+    _first_order = bool(flag)
+    try:
+        yield
+    finally:
+        _first_order = old
 
 
 class _ChannelScale(torch.autograd.Function):
@@ -208,7 +224,7 @@ class Conv2dLayer(torch.nn.Module):
 
     def forward(self, x, c=None, gain=1):
         k = self.weight.shape[2]
-        if (fused_hyper_mod and isinstance(self.weight, torch.nn.Parameter)
+        if (_first_order and isinstance(self.weight, torch.nn.Parameter)
                 and modconv.conv_act_eligible(x, self.weight, k, self.up, self.down, self.padding, self.activation, self.in_channels, self.out_channels)):
             # first-order fused node (ops/modconv.py::_ConvBiasAct): hyper-modulation in the operand split, bias / activation / gain / clamp in the
             # conv epilogue; the loss switches this off around the R1 forward, which must stay twice differentiable
@@ -219,7 +235,7 @@ class Conv2dLayer(torch.nn.Module):
                                          conv2d_gradfix._terms_for(x.dtype))
         w = self.weight * self.weight_gain
         if self.affine is not None:
-            if fused_hyper_mod and x.is_cuda:
+            if _first_order and x.is_cuda:
                 x = _ChannelScale.apply(x, 1.0 + self.affine(c).tanh())
             else:
                 x = (x * (1.0 + self.affine(c).tanh().unsqueeze(2).unsqueeze(3)).to(x.dtype)).to(x.dtype)

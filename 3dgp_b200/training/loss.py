@@ -148,11 +148,8 @@ class StyleGAN2Loss:
             else:
                 pp, real_patch = None, real_img
             tmp = real_patch.detach().requires_grad_(phase in ['Dreg', 'Dall'])
-            layers.fused_hyper_mod = phase not in ['Dreg', 'Dall']      # R1 differentiates D twice: keep that forward on twice-differentiable ops
-            try:
+            with layers.first_order_only(phase not in ['Dreg', 'Dall']):      # R1 differentiates D twice: keep that forward on twice-differentiable ops
                 logits, feats = self.run_D(tmp, real_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=real_data.get('camera_angles'), predict_feat=do_kd)
-            finally:
-                layers.fused_hyper_mod = True
             loss_Dreal = loss_Dkd = loss_Dr1 = 0
             if phase in ['Dmain', 'Dall']:
                 loss_Dreal = torch.nn.functional.softplus(-logits.clamp(max=lk.discriminator.logits_clamp_val)) + 0.0 * logits.max()

@@ -68,8 +68,10 @@ class FlatAdam:
             v.copy_(p.data)
             p.data = v
             self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
+        self._ema_ids = set()
         if ema_module is not None:
             ema_params = [p for p in ema_module.parameters() if p.numel() > 0]
+            self._ema_ids = {id(p) for p in ema_params}
             assert [p.shape for p in ema_params] == [p.shape for p in self.params]
             for p, o in zip(ema_params, self.offsets):
                 v = self.flat_ema[o:o + p.numel()].view(p.shape)
@@ -118,7 +120,8 @@ class FlatAdam:
                                                float(ema_beta) if ema_beta is not None else 0.0,
                                                None if desc is None else self.blk_seg.data_ptr(), _lib.ptr(desc), _lib.stream_ptr())
         _lib.check(rc, 'adam_ema_step')
-        _tc.invalidate_weight_cache(self._param_ids)          # the kernel wrote the parameters behind autograd's version counters
+        # the kernel wrote the parameters (and the EMA copy) behind autograd's version counters: drop their cached bf16 conv operands
+        _tc.invalidate_weight_cache(self._param_ids | self._ema_ids if ema_beta is not None else self._param_ids)
         self.active.clear()
         return self.numel
 

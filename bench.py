@@ -8,8 +8,8 @@ Workloads (BASELINE.json `configs`):
                patch 64x64, batch/GPU from --batch-gpu, synthetic data, random-init weights.  metric = images/s.
   raymarch   : configs[2]  fused ray-march microbench, 64x64 rays, 48+48 samples/ray, 32-ch 512^2 tri-planes, batch 16.
   ginfer     : configs[4]  G-only inference at 256x256.
-`--impl reference` times the reference's CPU algorithm (the oracle port, torch-CPU/numpy, all host threads) on a
-bounded sample of the same workload; under torchrun only rank 0 runs it.
+`--impl reference` EXECUTES the reference's CPU algorithm (the oracle port, torch-CPU, all host threads: forward, backward and optimiser
+of every phase) for W + K steps on a bounded sample of the same workload; under torchrun only rank 0 runs it.
 
 Timing: W >= 3 warm-up steps, then exactly K steps between barrier + cuda synchronize, CUDA events on the launching
 (torch current) stream, max over ranks.  Inputs are larger than L2 (stated in config.l2).  Clocks are sampled with
@@ -122,19 +122,30 @@ RM = dict(B=16, P=512, C=32, H=64, res=64, N=48, ray_start=0.75, ray_end=1.25, b
 
 def raymarch_inputs(B, device, seed=0):
     """Synthetic tri-planes N(0,1) stored channel-minor (the layout the tri-plane decoder emits), full-frame 64x64 rays
-    from cameras ~ configs/camera/{base,uniform}.yaml, random-init MLP (layers.py:36: randn weights, zero bias)."""
-    from oracle import restated as R
+    from cameras ~ configs/camera/{base,uniform}.yaml through the product's own ray generator, random-init MLP (layers.py:36: randn weights, zero bias).
+    On a CUDA device nothing here touches oracle/; the CPU arm (device='cpu') generates the same rays with the oracle's restated ray generator."""
     g = torch.Generator(device='cpu').manual_seed(seed)
     P, C = RM['P'], RM['C']
-    planes = torch.randn([B, P, P, 3 * C], device=device, generator=torch.Generator(device=device).manual_seed(seed))
+    if torch.device(device).type == 'cuda':
+        planes = torch.randn([B, P, P, 3 * C], device=device, generator=torch.Generator(device=device).manual_seed(seed))
+    else:
+        planes = torch.randn([B, P, P, 3 * C], generator=torch.Generator().manual_seed(seed))
     planes = planes.permute(0, 3, 1, 2).view(B, 3, C, P, P)
     yaw = torch.rand(B, generator=g) * 3.14 - 1.57
     pitch = torch.rand(B, generator=g) * (2.35619449 - 0.785398163) + 0.785398163
     angles = torch.stack([yaw, pitch, torch.zeros(B)], 1)
     fov = torch.rand(B, generator=g) * 35 + 10
     look = torch.stack([torch.rand(B, generator=g) * 6.28 - 3.14, torch.acos(1 - 2 * torch.rand(B, generator=g).clamp(1e-5, 1 - 1e-5)), torch.rand(B, generator=g) * 0.2], 1)
-    c2w = R.compute_cam2world_matrix(angles, torch.ones(B), look)
-    ro, rd = R.sample_rays(c2w, fov, (RM['res'], RM['res']))
+    if torch.device(device).type == 'cuda':
+        dn = importlib.import_module('3dgp_b200.dnnlib')
+        ru = importlib.import_module('3dgp_b200.training.rendering_utils')
+        tpr = importlib.import_module('3dgp_b200.training.tri_plane_renderer')
+        c2w = ru.compute_cam2world_matrix(dn.TensorGroup(angles=angles, radius=torch.ones(B), look_at=look))
+        ro, rd = tpr.sample_rays(c2w, fov, (RM['res'], RM['res']))
+    else:
+        from oracle import restated as R
+        c2w = R.compute_cam2world_matrix(angles, torch.ones(B), look)
+        ro, rd = R.sample_rays(c2w, fov, (RM['res'], RM['res']))
     w1 = torch.randn(RM['H'], C, generator=g); w2 = torch.randn(4, RM['H'], generator=g)
     return dict(planes=planes, ray_o=ro, ray_d=rd, w1=w1, b1=torch.zeros(RM['H']), w2=w2, b2=torch.zeros(4))
 
@@ -291,6 +302,25 @@ def conv_flops_per_image(cfg):
     return fl, fd
 
 
+# ncu --set full capture of the step's dominant kernel (profiles/, see DESIGN.md "Measurement"): dram__bytes_read.sum + dram__bytes_write.sum per launch,
+# averaged over the launches of conv_nhwc_bf16_kernel<128,3> inside one training step at the benchmarked configuration; None until measured for a config.
+CONV_TRAFFIC_BYTES_PER_LAUNCH = {}
+try:
+    CONV_TRAFFIC_BYTES_PER_LAUNCH = json.load(open(os.path.join(ROOT, 'profiles', 'conv_traffic_per_launch.json')))
+except Exception:
+    pass
+
+TRAIN_WORKLOAD = 'train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64, learn_camera_dist=true)'
+
+
+def train_step_config(B, mb, world, small=False):
+    """The `config` object of the JSON line: static description of the workload, identical for the GPU arm and the `--impl reference` arm."""
+    return dict(workload=TRAIN_WORKLOAD if not small else 'train_step SMALL (debug)', batch_per_gpu=B, micro_batch=mb, global_batch=B * world,
+                phases='Gmain + Dmain every iteration, Dreg (R1) every 16th', learn_camera_dist=True,
+                l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
+                parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)')
+
+
 def run_train_step(args, rank, world, local):
     gp = importlib.import_module('3dgp_b200')
     cfgm = importlib.import_module('3dgp_b200.config')
@@ -298,12 +328,13 @@ def run_train_step(args, rank, world, local):
     lossm = importlib.import_module('3dgp_b200.training.loss')
     stepm = importlib.import_module('3dgp_b200.training.step')
     rmod = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
+    tcm = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
     dev = torch.device('cuda', local)
     B = args.batch_gpu or 32
     mb = args.micro_batch or min(B, 32)
     assert B % mb == 0 and mb % 4 == 0, 'micro-batch must divide batch-gpu and be a multiple of the minibatch-std group (4)'
     small = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if args.small else {}
-    cfg = cfgm.make_config(batch_size=B * world, **small)
+    cfg = cfgm.make_config(batch_size=B * world, learn_camera_dist=True, **small)        # configs/training/base.yaml:9 (the reference default)
     torch.manual_seed(1234 + rank); np.random.seed(1234 + rank)
     G, D = cfgm.build_networks(cfg, dev)
     with torch.no_grad():   # benchmark init: exercise the noise path
@@ -311,9 +342,10 @@ def run_train_step(args, rank, world, local):
             if n.endswith('noise_strength'):
                 p_.fill_(0.1)
     G.train(); D.train()
-    G.synthesis.nerf_noise_std = 0.5
     r1_gamma = 0.0002 * (cfg.dataset.resolution ** 2) / (B * world)      # train.py:173 'auto'
     loss = lossm.StyleGAN2Loss(cfg, dev, G, D, r1_gamma=r1_gamma)
+    # mid-training state (2500 kimg): density noise at half strength, EMD regulariser of the camera adaptor ramped in (loss.py:64-65)
+    G.progressive_update(2500); loss.progressive_update(2500)
     tr = stepm.Trainer(G, D, loss, cfg, rank=rank, world_size=world, D_reg_interval=16, batch_size=B * world, micro_batch=mb)
     host = synthetic_batch(cfg, B, dev, seed=rank)
     real, gen = to_step_inputs(host, dev, dn)
@@ -324,13 +356,14 @@ def run_train_step(args, rank, world, local):
 
     rmod.TIMING = None
     ms, clocks = timed_region(step, args.steps, args.warmup, world)
-    # same steps, collecting the fused ray-march forward kernel's duration with events on the launching stream
+    # same steps, collecting the durations of the dominant conv kernel and of the fused ray-march forward with events on the launching stream
     c0 = gp._lib.launch_count
     rmod.TIMING = []
-    tcm = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
     tcm.CONV_TIMING = []
+    s0 = dict(tcm.stats)
     ms2, _ = timed_region(step, args.steps, 0, world)
     launches = (gp._lib.launch_count - c0) // max(args.steps + 3, 1)
+    conv_routing = {k: (tcm.stats[k] - s0[k]) // max(args.steps + 3, 1) for k in s0}
     ev = rmod.TIMING; rmod.TIMING = None
     cev = tcm.CONV_TIMING; tcm.CONV_TIMING = None
     torch.cuda.synchronize()
@@ -353,35 +386,80 @@ def run_train_step(args, rank, world, local):
         stats_h.copy_(vals, non_blocking=True)
 
     ms_e2e, _ = timed_region(step_e2e, args.steps, 1, world)
+    peak_mem = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     fg, fd = conv_flops_per_image(cfg)
     # per iteration: Gmain = G fwd+bwd (3x) + D fwd + dgrad (2x); Dmain = G fwd (1x) + D fwd+bwd on fakes and reals (2 x 3x); Dreg/16 ~ D 2nd order
     flops_step = B * (4 * fg + 8 * fd + (1.0 / 16) * 6 * fd)
+    alg_tf = conv_flops / (conv_ms * 1e-3) / 1e12
+    n_l = max(len(cev), 1)
+    traffic = CONV_TRAFFIC_BYTES_PER_LAUNCH.get(f'B{mb}')
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline and not args.small:
+        gpu_base = gpu_baseline_step(tr, host, dev, dn, args)
     res = dict(
         metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
-        dtype='G fp32 (TF32 off) / D fp16+fp32, as the reference (configs/model/3dgp.yaml:8)',
-        config=dict(workload='train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64)' if not args.small else 'train_step SMALL (debug)',
-                    batch_per_gpu=B, micro_batch=mb, global_batch=B * world, peak_mem_gb=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1), phases='Gmain + Dmain every iteration, Dreg (R1) every 16th',
-                    l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
-                    parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)', conv_engine=args.conv_engine,
-                    conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9)),
-        # dominant kernel of the step (~1/3 of its GPU time): the stride-1 bf16x3 tcgen05 convolution of the tri-plane decoder (forward + input gradient)
-        roofline=dict(bound='tensor', achieved=3.0 * conv_flops / (conv_ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
-                      frac=3.0 * conv_flops / (conv_ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'], traffic=None,
-                      kernel='conv_nhwc_bf16_kernel<128,3> (bf16x3: three bf16 MMAs per fp32-grade product; `achieved` counts the executed MMA FLOPs, '
-                             '`achieved_algorithmic` the convolution FLOPs)', achieved_algorithmic=conv_flops / (conv_ms * 1e-3) / 1e12,
-                      peak_source=peaks['source'], launches_timed=len(cev), mean_ms=conv_ms / max(len(cev), 1),
-                      algorithmic_flops_per_launch=conv_flops / max(len(cev), 1),
-                      traffic_note='ncu (profiles/r1_hot_kernels_summary.txt): DRAM bytes = operands + output once (0.54 GB read / 0.49 GB written for the 256->256 @256^2 B=8 launch)'),
+        dtype='f32 storage; G convs bf16x3 on tcgen05 (three bf16 MMAs per product, fp32 accumulate: fp32-grade), tri-plane MLP 3xTF32; '
+              'D blocks the reference runs in fp16: %s tensor-core operands, fp32 accumulate' % D_LOW_PRECISION_NAME,
+        config=train_step_config(B, mb, world, args.small),
+        details=dict(peak_mem_gb=peak_mem, conv_gflop_per_image_fwd=dict(G=fg / 1e9, D=fd / 1e9), conv_routing_per_step=conv_routing,
+                     density_noise_std=float(G.synthesis.nerf_noise_std), emd_multiplier=float(loss.emd_multiplier)),
+        # dominant kernel of the step: the stride-1 bf16x3 tcgen05 convolution of the tri-plane decoder (forward + input gradient).
+        # `achieved` = ALGORITHMIC convolution FLOPs (2*B*Cout*Cin*k^2*H*W) / live-timed launch duration.
+        roofline=dict(bound='tensor', achieved=alg_tf, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s', frac=alg_tf / peaks['bf16_tflops_sustained'],
+                      traffic=traffic, kernel='conv_nhwc_bf16_kernel<128,3>', peak_source=peaks['source'] + ' (sustained bf16 GEMM: kernel timed inside a long step)',
+                      launches_timed=len(cev), mean_ms=conv_ms / n_l, algorithmic_flops_per_launch=conv_flops / n_l,
+                      # bf16x3 executes three bf16 MMAs per fp32-grade product: tensor-pipe occupancy, NOT the roofline fraction
+                      executed_mma_tflops=3.0 * alg_tf, executed_mma_frac_of_peak=3.0 * alg_tf / peaks['bf16_tflops_sustained'],
+                      traffic_source='profiles/conv_traffic_per_launch.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)' if traffic else None),
         roofline_raymarch=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=None,
-                               kernel='raymarch_fwd2_kernel (3xTF32 MLP, inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
+                               kernel='raymarch_fwd kernel (3xTF32 MLP, inside the step)', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg,
                                launches_timed=len(kms), mean_ms=float(np.mean(kms))),
         roofline_step_tensor=dict(bound='tensor', achieved=flops_step / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
                                   frac=flops_step / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
-                                  note='dense-contraction FLOPs of the whole step / step time, against the measured sustained bf16 GEMM peak'),
+                                  note='algorithmic dense-contraction FLOPs of the whole step / step time, against the measured sustained bf16 GEMM peak'),
         e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=16),
         gpu_launches=int(launches * args.steps), clocks=clocks)
+    if gpu_base is not None:
+        res['gpu_baseline'] = gpu_base
     return res
+
+
+D_LOW_PRECISION_NAME = 'bf16'
+
+
+def gpu_baseline_step(tr, host, dev, dn, args):
+    """Same modules, same weights, same step -- but every convolution on cuDNN fp32 with TF32 off (training_loop.py:76-77, the reference's own GPU
+    arithmetic for G) and every fused layer node switched off, i.e. the op-by-op composition the reference executes (x*styles -> conv -> FIR -> fma ->
+    bias_act; hyper-mod -> conv -> bias_act), on this repo's elementwise / FIR / ray-march kernels.  Timed in the same run on a reduced batch (the unfused
+    path keeps every intermediate alive for backward: 32 images do not fit comfortably)."""
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    sg = importlib.import_module('3dgp_b200.training.networks_stylegan2')
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    Bb = 8
+    sub = {k: v[:Bb] for k, v in host.items()}
+    real, gen = to_step_inputs(sub, dev, dn)
+    old_mb, old_bs = tr.micro_batch, tr.batch_size
+    tr.micro_batch, tr.batch_size = Bb, Bb
+    cg.tc_enabled = False; sg.fused_layer_enabled = False
+    try:
+        with layers.first_order_only(False):
+            for _ in range(2):
+                tr.step(real, gen)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            K = 3
+            e0.record()
+            for _ in range(K):
+                tr.step(real, gen)
+            e1.record(); torch.cuda.synchronize()
+        msb = e0.elapsed_time(e1) / K
+    finally:
+        cg.tc_enabled = True; sg.fused_layer_enabled = True
+        tr.micro_batch, tr.batch_size = old_mb, old_bs
+    return dict(value=Bb / (msb * 1e-3), unit='images/s', ms_per_step=msb, batch=Bb, steps=K,
+                kind='cuDNN fp32 (TF32 off) convolutions, unfused layer composition; same modules / weights / ray-march kernel',
+                note='first_order_only(False) forces the unfused D path for every phase; steps 2..4 of this leg contain no Dreg phase')
 
 
 def run_ginfer(args, rank, world, local):
@@ -502,59 +580,51 @@ def run_ops(args, rank, world, local):
                 gpu_launches=int(launches), clocks=clocks)
 
 
-def cpu_train_step(small=False, budget_s=25.0):
-    """Reference algorithm on the host cores (oracle port, torch-CPU / numpy, all threads) for the training-step metric.
-    Bounded sample: ONE image through the generator forward (mapping + tri-plane decoder + ray-march at the training patch
-    resolution + depth adaptor) and FOUR images (one minibatch-std group) through the discriminator forward, both at the
-    BASELINE widths.  Step cost is assembled with the same pass counts the GPU arm executes per iteration
-    (G: 1 differentiated pass = 3 forward-equivalents + 1 plain forward; D: 1 fwd + input-gradient pass (2) + 2 differentiated
-    passes (6)), i.e. images/s = 1 / (4 * tG + 8 * tD) -- an optimistic bound for the CPU since backward passes are costed at
-    forward speed x2."""
-    from oracle import ref_harness as rh, restated as R, shapes, cases
-    threads = min(os.cpu_count(), 32)      # beyond ~32 threads ATen's CPU convs stop scaling on these hosts
-    torch.set_num_threads(threads)
-    R.FAST_FIR = True                      # FIR through grouped F.conv2d, as the reference's CPU path does
-    kw = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if small else {}
-    Gc, Dc, m = rh.make_cfg(**kw)
-    gs, num_ws = shapes.generator_shapes(Gc)
-    ds, dres = shapes.discriminator_shapes(Dc, m['patch_res'], 4, m['embedding_dim'])
-    filt = torch.from_numpy(R.setup_filter([1, 3, 3, 1]))
+class CpuStep:
+    """Reference algorithm on the host cores (oracle port: oracle/restated.py with DIFFERENTIABLE = True, driven by oracle/train_step.py) for the
+    training-step metric.  One call of `run()` EXECUTES one optimisation step -- Gmain and Dmain forward + backward + Adam, Dreg (R1 double backward)
+    on the reference's schedule (every 16th step) -- at the BASELINE widths on a bounded sample of `sample_batch` images (default 1; the minibatch-std
+    group is then min(4, N) = 1 as in networks_discriminator.py:111).  Nothing is extrapolated."""
 
-    def fill(shp_table, seed):
-        g = torch.Generator().manual_seed(seed)
-        sd = {}
-        for k, shp in shp_table.items():
-            if k.endswith('resample_filter'):
-                sd[k] = filt.clone()
-            elif k.endswith('fourier_coefs'):
-                sd[k] = (2.0 ** torch.arange(shp[0]).float() / (2 ** shp[0])) * np.pi
-            elif k.endswith('.bias') or k.endswith('progress_coef') or k.endswith('w_avg'):
-                sd[k] = torch.zeros(shp) + (1.0 if (k.endswith('affine.bias') and 'synthesis' in k) else 0.0)
-            elif k.endswith('noise_strength'):
-                sd[k] = torch.tensor(0.1)
-            elif k.endswith('near_plane_offset_raw'):
-                sd[k] = torch.tensor([-3.0])
-            else:
-                sd[k] = torch.randn(shp, generator=g)
-        return sd
-    sdG, sdD = fill(gs, 0), fill(ds, 1)
-    g = torch.Generator().manual_seed(2)
-    pr, N = m['patch_res'], Gc['num_ray_steps']
-    z = torch.randn(1, Gc['z_dim'], generator=g); c = torch.zeros(1, Gc['c_dim']); c[0, 0] = 1
-    t0 = time.perf_counter()
-    ws = R.mapping_network(sdG, 'mapping.', z, c, num_ws)
-    R.generator_synthesis(sdG, Gc, ws, torch.tensor([[0.3, 1.4, 0.0]]), torch.tensor([25.0]), torch.ones(1), torch.tensor([[0.1, 1.5, 0.1]]), pr,
-                          torch.full((1, 2), 0.5), torch.full((1, 2), 0.25), torch.rand(1, pr * pr, N, generator=g), torch.rand(1, pr * pr, N, generator=g),
-                          noise_mode='const', fused_modconv=False)
-    tG = time.perf_counter() - t0
-    img = torch.rand(4, 4, pr, pr, generator=g) * 2 - 1
-    c4 = torch.zeros(4, Dc['c_dim']); c4[:, 0] = 1
-    t0 = time.perf_counter()
-    R.discriminator(sdD, img, c4, torch.full((4, 2), 0.5), torch.full((4, 2), 0.25), dres, Dc['num_additional_start_blocks'], predict_feat=False)
-    tD = (time.perf_counter() - t0) / 4
-    val = 1.0 / (4 * tG + 8 * tD)
-    return dict(value=val, unit='images/s', cores=threads, kind='port',
-                sample=f'G forward 1 image {tG:.2f} s + D forward 4 patches {4 * tD:.2f} s at the BASELINE widths; step = 4 G-forward-equivalents + 8 D-forward-equivalents per image')
+    def __init__(self, small=False, sample_batch=1):
+        from oracle import ref_harness as rh, train_step as ts
+        self.threads = min(os.cpu_count(), 32)      # beyond ~32 threads ATen's CPU convs stop scaling on these hosts
+        torch.set_num_threads(self.threads)
+        kw = dict(cmax=64, cbase=4096, tri_res=128, patch_res=32, img_resolution=128, c_dim=10, w_dim=128, z_dim=128, num_ray_steps=12) if small else {}
+        Gc, Dc, m = rh.make_cfg(**kw)
+        sdG, sdD = ts.random_state_dicts(Gc, Dc, m, seed=0)
+        Bs = sample_batch
+        r1_gamma = 0.0002 * (m['img_resolution'] ** 2) / 32
+        self.tr = ts.CpuTrainer(sdG, sdD, Gc, Dc, m, d_reg_interval=16, r1_gamma=r1_gamma)
+        g = torch.Generator().manual_seed(2)
+        res = m['img_resolution']
+        self.batch = dict(real_img=torch.randint(0, 256, (Bs, 3, res, res), generator=g).float() / 127.5 - 1,
+                          real_depth=torch.randint(0, 65536, (Bs, 1, res, res), generator=g).float() / 65536 * 2 - 1,
+                          c=torch.nn.functional.one_hot(torch.arange(Bs) % Gc['c_dim'], Gc['c_dim']).float(),
+                          embs=torch.randn(Bs, m['embedding_dim'], generator=g), z=torch.randn(Bs, Gc['z_dim'], generator=g),
+                          cam=dict(angles=torch.tensor([[0.3, 1.4, 0.0]]).repeat(Bs, 1), fov=torch.full((Bs,), 25.0), radius=torch.ones(Bs),
+                                   look_at=torch.tensor([[0.1, 1.5, 0.1]]).repeat(Bs, 1)))
+        self.Bs = Bs
+
+    def run(self):
+        t0 = time.perf_counter()
+        st = self.tr.step(**self.batch)
+        return time.perf_counter() - t0, st
+
+
+def cpu_train_step(small=False, steps=1, warmup=0, sample_batch=1):
+    """`steps` executed CPU optimisation steps after `warmup` untimed ones; returns the cpu_baseline object and the mean seconds per step."""
+    cs = CpuStep(small=small, sample_batch=sample_batch)
+    for _ in range(warmup):
+        cs.run()
+    ts_, had_reg = [], 0
+    for _ in range(steps):
+        dt, st = cs.run()
+        ts_.append(dt); had_reg += int('Loss/D/r1_penalty' in st)
+    mean_s = float(np.mean(ts_))
+    return dict(value=cs.Bs / mean_s, unit='images/s', cores=cs.threads, kind='port',
+                sample=f'{steps} executed optimisation step(s) (Gmain + Dmain forward/backward/Adam; {had_reg} with the lazy R1 phase) of {cs.Bs} image(s) at the '
+                       f'{"BASELINE widths (cmax=1024, 512^2 tri-planes, 64^2 patch, 48+48 samples/ray)" if not small else "SMALL debug widths"}, {mean_s:.2f} s/step, after {warmup} untimed step(s)'), mean_s
 
 
 # ----------------------------------------------------------------------------------------------
@@ -569,9 +639,10 @@ def main():
     ap.add_argument('--mlp-mode', type=int, default=2, help='tri-plane MLP arithmetic: 0 fp32 SIMT (v1 kernel), 1 TF32 mma, 2 3xTF32 mma (default)')
     ap.add_argument('--planes-fp16', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-baseline', action='store_true')
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--small', action='store_true')
-    ap.add_argument('--conv-engine', default='aten')
+    ap.add_argument('--cpu-sample-batch', type=int, default=1, help='images per executed CPU step of the reference arm / cpu_baseline leg')
     args = ap.parse_args()
     rank, world, local = dist_info()
 
@@ -579,16 +650,19 @@ def main():
         if rank != 0:
             return
         if args.workload == 'train_step':
-            cb = cpu_train_step(small=args.small)
+            B = args.batch_gpu or 32
+            cb, mean_s = cpu_train_step(small=args.small, steps=args.steps, warmup=args.warmup, sample_batch=args.cpu_sample_batch)
             metric = 'G+D training-step images/s at 256x256'
-            wl = 'train_step (BASELINE configs[1]: ImageNet-256 G+D step, cmax=1024, 48+48 samples/ray, patch 64x64)'
+            cfg_ = train_step_config(B, args.micro_batch or min(B, 32), args.gpus, args.small)
+            ms_step = mean_s * 1e3
         else:
-            cb = cpu_raymarch(sample_rays=4096, repeats=2)
+            cb = cpu_raymarch(sample_rays=4096, repeats=max(args.steps - 1, 1))
             metric = 'ray-march images/s (64x64 rays, 48+48 samples/ray, 32-ch 512^2 tri-planes)'
-            wl = 'raymarch (BASELINE configs[2])'
+            cfg_ = dict(workload='raymarch (BASELINE configs[2])')
+            ms_step = 1e3 / cb['value']
         line = dict(impl='reference', metric=metric, value=cb['value'], unit='images/s',
-                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 / cb['value'], higher_is_better=True, scaling='weak',
-                    vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload=wl),
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic', config=cfg_,
                     cpu_baseline=cb, e2e=dict(value=cb['value'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -604,15 +678,14 @@ def main():
         line = dict(metric=res['metric'], value=res['value'], unit=res['unit'], n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
                     config=res['config'], roofline=res['roofline'], e2e=res['e2e'], gpu_launches=res['gpu_launches'], clocks=res['clocks'])
-        if 'roofline_step_tensor' in res:
-            line['roofline_step_tensor'] = res['roofline_step_tensor']
-        if 'roofline_raymarch' in res:
-            line['roofline_raymarch'] = res['roofline_raymarch']
-        if 'forward_backward' in res:
-            line['forward_backward'] = res['forward_backward']
+        for k in ('details', 'roofline_step_tensor', 'roofline_raymarch', 'forward_backward', 'gpu_baseline'):
+            if k in res:
+                line[k] = res[k]
         if world == 1 and not args.no_cpu_baseline:
-            if args.workload not in ('ginfer', 'ops'):
-                line['cpu_baseline'] = cpu_train_step(small=args.small) if args.workload == 'train_step' else cpu_raymarch(sample_rays=4096, repeats=2)
+            if args.workload == 'train_step':
+                line['cpu_baseline'] = cpu_train_step(small=args.small, steps=1, warmup=0, sample_batch=args.cpu_sample_batch)[0]
+            elif args.workload == 'raymarch':
+                line['cpu_baseline'] = cpu_raymarch(sample_rays=4096, repeats=2)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

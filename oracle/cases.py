@@ -162,6 +162,18 @@ def small_net_kwargs():
                 use_depth=True, learn_camera_dist=False, hid_dim=64, w_dim=64, z_dim=64, depth_hid=8, embedding_dim=16)
 
 
+def wide_net_kwargs():
+    """Same topology at widths where EVERY hot convolution is eligible for the tcgen05 path (Cin % 64 == 0, Cout in {64, 96} or % 128 == 0):
+    G decoder 128-128-128-128-64 channels up to 64^2 tri-planes (incl. a 128->64 up-sampling layer, 64->96 and 128->96 toRGB), depth adaptor at its
+    production width (64 ch, 5x5), D 64/128 channels on a 32^2 patch of a 128^2 image: blocks b128..b16 in the reference's fp16 set, b8 / b4 fp32."""
+    return dict(cmax=128, cbase=4096, tri_res=64, feat_dim=32, num_ray_steps=12, patch_res=32, img_resolution=128, c_dim=5,
+                use_depth=True, learn_camera_dist=False, hid_dim=64, w_dim=64, z_dim=64, depth_hid=64, embedding_dim=16, d_fmaps=2.0)
+
+
+def net_kwargs(variant):
+    return dict(small=small_net_kwargs, wide=wide_net_kwargs)[variant]()
+
+
 _KEEP_BUFFERS = ('resample_filter', 'fourier_coefs', 'progress_coef')
 
 
@@ -226,7 +238,25 @@ def eval_variates(kw, B):
     return dict(u_coarse=rs.uniform(0, 1, (B, Re, N)).astype(np.float32), u_fine=rs.uniform(0, 1, (B, Re, N)).astype(np.float32))
 
 
-def probe_params(which):
+def grad_probe(g, limit=4096):
+    """Strided sample of a (possibly large) gradient tensor: keeps the fixtures small; tests apply the same stride to the CUDA result."""
+    g = np.asarray(g).reshape(-1)
+    return g[::max(1, g.size // limit)].copy()
+
+
+def probe_params(which, variant='small'):
+    if variant == 'wide':
+        if which == 'D':
+            return ['b128.fromrgb.weight', 'b128.conv0.weight', 'b128.conv1.weight', 'b128.conv1.affine.weight', 'b128.skip.weight', 'b64.conv0.bias',
+                    'b32.conv1.weight', 'b32.skip.weight', 'b16.conv0.weight', 'b8.conv1.weight', 'b8.skip.weight', 'b4.fc.weight', 'b4.out.bias',
+                    'head_mapping.fc1.weight', 'hyper_mod_mapping.embed.weight']
+        return ['synthesis.tri_plane_mlp.model.0.weight', 'synthesis.tri_plane_mlp.model.1.bias', 'synthesis.tri_plane_decoder.b4.const',
+                'synthesis.tri_plane_decoder.b8.conv0.weight', 'synthesis.tri_plane_decoder.b8.conv0.noise_strength',
+                'synthesis.tri_plane_decoder.b16.conv1.weight', 'synthesis.tri_plane_decoder.b32.conv1.affine.weight',
+                'synthesis.tri_plane_decoder.b32.torgb.weight', 'synthesis.tri_plane_decoder.b32.torgb.affine.bias',
+                'synthesis.tri_plane_decoder.b64.conv0.weight', 'synthesis.tri_plane_decoder.b64.conv1.weight', 'synthesis.tri_plane_decoder.b64.conv1.bias',
+                'synthesis.tri_plane_decoder.b64.torgb.weight', 'synthesis.depth_adaptor.layers.0.weight', 'synthesis.depth_adaptor.layers.1.weight',
+                'synthesis.depth_adaptor.head.weight', 'mapping.fc0.weight']
     if which == 'D':
         return ['b64.fromrgb.weight', 'b64.conv1.affine.weight', 'b16.conv0.weight', 'b8.skip.weight', 'b4.fc.weight', 'b4.out.bias',
                 'head_mapping.fc1.weight', 'hyper_mod_mapping.embed.weight']

@@ -134,11 +134,17 @@ def gen_render(ns, report):
     np.savez_compressed(os.path.join(GOLD, 'render.npz'), **out)
 
 
-def gen_networks(ns, report):
+def gen_networks(ns, report, variant='small'):
+    """variant 'small': 32-channel networks (every conv below the tensor-core path's channel granularity -> ATen in the product);
+    variant 'wide': cases.wide_net_kwargs() -- every hot conv eligible for the tcgen05 path; large tensors are stored as strided probes."""
     out = {}
     meta = {}
     ED = ns.dnnlib.EasyDict
-    kw = cases.small_net_kwargs()
+    kw = cases.net_kwargs(variant)
+    wide = variant != 'small'
+    tag = 'networks' if not wide else 'networks_' + variant
+    rp = (lambda k: k) if not wide else (lambda k: f'{variant}/{k}')
+    gp_ = (lambda g: g.numpy()) if not wide else (lambda g: cases.grad_probe(g.numpy()))
     Gc, Dc, m = rh.make_cfg(**kw)
     G = rh.build_reference_G(Gc, m['img_resolution'], seed=0)
     D = rh.build_reference_D(Dc, m['patch_res'], use_depth=True, embedding_dim=m['embedding_dim'], seed=1, fp32=True)
@@ -160,7 +166,7 @@ def gen_networks(ns, report):
     ws = G.mapping(t['z'], t['c'])
     out['G/ws'] = ws.detach().numpy()
     ws_or = R.mapping_network(sdG, 'mapping.', t['z'], t['c'], G.num_ws)
-    report['G/mapping'] = maxrel(ws_or, ws.detach())
+    report[rp('G/mapping')] = maxrel(ws_or, ws.detach())
 
     # --- training-mode synthesis (fused_modconv=False, random layer noise injected, patch render, depth head fixed by np seed)
     G.train()
@@ -169,12 +175,21 @@ def gen_networks(ns, report):
     np.random.seed(1234)
     orig_choice = np.random.choice
     np.random.choice = lambda *a, **k: head_idx.copy()
+    hooks = []
+    if wide:   # per-block activations (strided probes): localise a deviation to a block instead of to "the decoder"
+        dec = G.synthesis.tri_plane_decoder
+        for res in dec.block_resolutions:
+            def hk(mod, args, outs, res=res):
+                out[f'G/block/b{res}/x'] = cases.grad_probe(outs[0].detach().numpy()); out[f'G/block/b{res}/img'] = cases.grad_probe(outs[1].detach().numpy())
+            hooks.append(getattr(dec, f'b{res}').register_forward_hook(hk))
     try:
         with rh.injected_rng(randn=[n.clone() for n in layer_noise], rand_like=[t['u_coarse'].reshape(B, Rr, N, 1)], rand=[t['u_fine'].reshape(B * Rr, N)]):
             G.synthesis.nerf_noise_std = 0.0
             o = G.synthesis(ws, cam, patch_params=pp, render_opts=dict(concat_depth=True, return_depth=True))
     finally:
         np.random.choice = orig_choice
+        for h in hooks:
+            h.remove()
     out['G/train/img'] = o.img.detach().numpy(); out['G/train/depth'] = o.depth.detach().numpy()
     # decoder planes via the reference decoder alone (same noise)
     with rh.injected_rng(randn=[n.clone() for n in layer_noise]):
@@ -184,8 +199,8 @@ def gen_networks(ns, report):
     o_or = R.generator_synthesis(sdG, Gc, ws.detach(), t['angles'], t['fov'], t['radius'], t['look_at'], pr, t['patch_scales'], t['patch_offsets'],
                                  t['u_coarse'], t['u_fine'], noise_mode='random', noises=layer_noise, fused_modconv=False,
                                  depth_head_idx=torch.from_numpy(head_idx))
-    report['G/train/planes'] = maxrel(o_or['planes'], planes_ref.detach())
-    report['G/train/img'] = maxrel(o_or['img'], o.img.detach()); report['G/train/depth'] = maxrel(o_or['depth'], o.depth.detach())
+    report[rp('G/train/planes')] = maxrel(o_or['planes'], planes_ref.detach())
+    report[rp('G/train/img')] = maxrel(o_or['img'], o.img.detach()); report[rp('G/train/depth')] = maxrel(o_or['depth'], o.depth.detach())
 
     # --- eval-mode synthesis (fused modconv, const noise, full-frame render at img_resolution)
     G.eval()
@@ -193,29 +208,51 @@ def gen_networks(ns, report):
     ue = cases.eval_variates(kw, B)
     with rh.injected_rng(rand_like=[torch.from_numpy(ue['u_coarse']).reshape(B, Re, N, 1)], rand=[torch.from_numpy(ue['u_fine']).reshape(B * Re, N)]):
         oe = G.synthesis(ws, cam, noise_mode='const', render_opts=dict(concat_depth=True, return_depth=True))
-    out['G/eval/img'] = oe.img.detach().numpy(); out['G/eval/depth'] = oe.depth.detach().numpy()
+    out['G/eval/img'] = gp_(oe.img.detach()) if wide else oe.img.detach().numpy()
+    out['G/eval/depth'] = gp_(oe.depth.detach()) if wide else oe.depth.detach().numpy()
     oe_or = R.generator_synthesis(sdG, Gc, ws.detach(), t['angles'], t['fov'], t['radius'], t['look_at'], res, None, None,
                                   torch.from_numpy(ue['u_coarse']), torch.from_numpy(ue['u_fine']), noise_mode='const', fused_modconv=True)
-    report['G/eval/img'] = maxrel(oe_or['img'], oe.img.detach())
+    report[rp('G/eval/img')] = maxrel(oe_or['img'], oe.img.detach())
 
     # --- discriminator on the training-mode fake patch + R1-style double backward
     D.train()
     img = o.img.detach().clone().requires_grad_(True)
+    hooks = []
+    if wide:
+        for res in D.block_resolutions:
+            def hk(mod, args, outs, res=res):
+                out[f'D/block/b{res}'] = cases.grad_probe(outs.detach().numpy())
+            hooks.append(getattr(D, f'b{res}').register_forward_hook(hk))
     logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    for h in hooks:
+        h.remove()
     out['D/logits'] = logits.detach().numpy(); out['D/feats'] = feats.detach().numpy()
     lg_or, f_or = R.discriminator(sdD, o.img.detach(), t['c'], t['patch_scales'], t['patch_offsets'], D.block_resolutions,
                                   Dc['num_additional_start_blocks'], predict_feat=True)
-    report['D/logits'] = maxrel(lg_or, logits.detach()); report['D/feats'] = maxrel(f_or, feats.detach())
+    report[rp('D/logits')] = maxrel(lg_or, logits.detach()); report[rp('D/feats')] = maxrel(f_or, feats.detach())
     with ns.conv2d_gradfix.no_weight_gradients():
         r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
     out['D/r1_grads'] = r1.detach().numpy()
     pen = r1.square().sum([1, 2, 3])
     loss = torch.nn.functional.softplus(-logits).mean() + pen.mean() * 0.5
-    names = cases.probe_params('D')
+    names = cases.probe_params('D', variant)
     pars = dict(D.named_parameters())
     gs = torch.autograd.grad(loss, [pars[n] for n in names])
     for n, g in zip(names, gs):
-        out['D/grad/' + n] = g.numpy()
+        out['D/grad/' + n] = gp_(g)
+
+    if wide:
+        # --- first-order discriminator pass (Dmain on a given patch: adversarial + knowledge-distillation terms, loss.py:256-316): the phase the
+        # fused first-order nodes of the product serve (R1 above needs the twice-differentiable composition)
+        img1 = o.img.detach().clone().requires_grad_(True)
+        lg1, f1 = D(img1, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+        embs = torch.from_numpy(cases.cotangent((B, kw['embedding_dim']), 31))
+        loss1 = torch.nn.functional.softplus(-lg1).mean() + (f1 - embs).norm(dim=1).mean()
+        gs1 = torch.autograd.grad(loss1, [img1] + [pars[n] for n in names])
+        out['D/loss1'] = np.array([loss1.item()])
+        out['D/grad1/img'] = gs1[0].numpy()
+        for n, g in zip(names, gs1[1:]):
+            out['D/grad1/' + n] = gp_(g)
 
     # --- generator loss gradient through D (Gmain): d softplus(-D(G(z))) / d params
     G.train()
@@ -230,15 +267,15 @@ def gen_networks(ns, report):
         np.random.choice = orig_choice
     lg2, _ = D(o2.img, t['c'], patch_params=pp, camera_angles=t['angles'])
     lossG = torch.nn.functional.softplus(-lg2).mean()
-    namesG = cases.probe_params('G')
+    namesG = cases.probe_params('G', variant)
     parsG = dict(G.named_parameters())
     gsG = torch.autograd.grad(lossG, [parsG[n] for n in namesG])
     out['G/loss'] = np.array([lossG.item()])
     for n, g in zip(namesG, gsG):
-        out['G/grad/' + n] = g.numpy()
+        out['G/grad/' + n] = gp_(g)
 
-    np.savez_compressed(os.path.join(GOLD, 'networks.npz'), **out)
-    with open(os.path.join(GOLD, 'networks_meta.json'), 'w') as f:
+    np.savez_compressed(os.path.join(GOLD, tag + '.npz'), **out)
+    with open(os.path.join(GOLD, tag + '_meta.json'), 'w') as f:
         json.dump(meta, f, indent=1, sort_keys=True)
 
 
@@ -287,7 +324,7 @@ def main():
     report = {}
     only = sys.argv[1:]
     gens = dict(upfirdn2d=gen_upfirdn2d, bias_act=gen_bias_act, filtered_lrelu=gen_filtered_lrelu, render=gen_render, networks=gen_networks,
-                camera_adaptor=gen_camera_adaptor)
+                networks_wide=lambda ns_, rep_: gen_networks(ns_, rep_, 'wide'), camera_adaptor=gen_camera_adaptor)
     for name, fn in gens.items():
         if only and name not in only:
             continue

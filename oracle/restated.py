@@ -44,14 +44,23 @@ def _parse_scaling(s):
 FAST_FIR = False   # bench.py's CPU arm sets this: FIR through ATen's grouped conv2d exactly as the reference's own CPU path does
 
 
+DIFFERENTIABLE = False   # bench.py's EXECUTED CPU training step (oracle/train_step.py) sets this: every op stays a torch op, so autograd can
+                         # differentiate the restatement exactly as it differentiates the reference's own CPU path
+
+
 def _upfirdn2d_aten(x, f, up, down, padding, flip_filter, gain):
+    """numpy-in / numpy-out wrapper of `upfirdn2d_t` (CPU timing with FAST_FIR)."""
+    ft = None if f is None else torch.as_tensor(np.ascontiguousarray(f), dtype=torch.float32)
+    return upfirdn2d_t(torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32), ft, up, down, padding, flip_filter, gain).numpy()
+
+
+def upfirdn2d_t(xt, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
     """torch_utils/ops/upfirdn2d.py:167-211 evaluated the way the reference does on CPU: zero-stuff, pad, grouped F.conv2d, slice.
-    Multi-threaded; used only for CPU timing (tests/test_cpu_oracle.py checks it against the explicit restatement)."""
-    xt = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32)
+    Multi-threaded and differentiable; tests/test_cpu_oracle.py checks it against the explicit restatement."""
     N, C, H, W = xt.shape
     upx, upy = _parse_scaling(up); downx, downy = _parse_scaling(down)
     px0, px1, py0, py1 = _parse_padding(padding)
-    ft = torch.ones([1, 1]) if f is None else torch.as_tensor(np.ascontiguousarray(f), dtype=torch.float32)
+    ft = torch.ones([1, 1]) if f is None else (f if isinstance(f, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(f), dtype=torch.float32))
     xt = xt.reshape([N, C, H, 1, W, 1])
     xt = F.pad(xt, [0, upx - 1, 0, 0, 0, upy - 1]).reshape([N, C, H * upy, W * upx])
     xt = F.pad(xt, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
@@ -65,7 +74,7 @@ def _upfirdn2d_aten(x, f, up, down, padding, flip_filter, gain):
     else:
         xt = F.conv2d(xt, ft.unsqueeze(2), groups=C)
         xt = F.conv2d(xt, ft.unsqueeze(3), groups=C)
-    return xt[:, :, ::downy, ::downx].numpy()
+    return xt[:, :, ::downy, ::downx]
 
 
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
@@ -212,6 +221,8 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return F.conv2d(x, w, stride=stride, padding=padding, groups=groups)
 
     def fir(x, **kw_):
+        if DIFFERENTIABLE:
+            return upfirdn2d_t(x, f, **kw_)
         return _t(upfirdn2d(x.numpy(), f, **kw_))
 
     if kw == 1 and kh == 1 and down > 1 and up == 1:                         # :94-97
@@ -237,7 +248,10 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return x
     if up == 1 and down == 1 and px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:   # :132-134
         return conv(x, w, padding=[py0, px0], flip_weight=flip_weight)
-    x = _t(upfirdn2d(x.numpy(), f if up > 1 else None, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter))
+    if DIFFERENTIABLE:
+        x = upfirdn2d_t(x, f if up > 1 else None, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    else:
+        x = _t(upfirdn2d(x.numpy(), f if up > 1 else None, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter))
     x = conv(x, w, flip_weight=flip_weight)
     if down > 1:
         x = fir(x, down=down, flip_filter=flip_filter)
@@ -248,7 +262,22 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 # training/layers.py, networks_stylegan2.py
 
 
+_ACT_T = {'linear': lambda x, a: x, 'relu': lambda x, a: torch.relu(x), 'lrelu': lambda x, a: F.leaky_relu(x, a), 'tanh': lambda x, a: torch.tanh(x),
+          'sigmoid': lambda x, a: torch.sigmoid(x), 'softplus': lambda x, a: F.softplus(x)}
+
+
 def t_bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
+    if DIFFERENTIABLE:   # torch_utils/ops/bias_act.py:91-120 in torch ops (what the reference itself runs on CPU tensors)
+        _, da, dg = ACT[act]
+        alpha = float(da if alpha is None else alpha); gain = float(dg if gain is None else gain)
+        if b is not None:
+            x = x + b.reshape([-1 if i == dim else 1 for i in range(x.ndim)])
+        x = _ACT_T[act](x, alpha)
+        if gain != 1:
+            x = x * gain
+        if clamp is not None and clamp >= 0:
+            x = x.clamp(-clamp, clamp)
+        return x
     return _t(bias_act(x.detach().numpy(), None if b is None else b.detach().numpy(), dim, act, alpha, gain, clamp))
 
 
@@ -359,7 +388,12 @@ def tri_plane_decoder(sd, prefix, ws, block_resolutions, noise_mode='const', noi
             x = synthesis_layer(sd, bp + 'conv0.', x, cur[:, wi], up=2, noise_mode=noise_mode, noise_in=nxt() if noise_mode == 'random' else None, fused_modconv=fused_modconv); wi += 1
             x = synthesis_layer(sd, bp + 'conv1.', x, cur[:, wi], noise_mode=noise_mode, noise_in=nxt() if noise_mode == 'random' else None, fused_modconv=fused_modconv); wi += 1
         if img is not None:
-            img = _t(upsample2d(img.numpy(), sd[bp + 'resample_filter'].numpy()))
+            if DIFFERENTIABLE:     # upsample2d (upfirdn2d.py:313-348) for the 4-tap filter: up 2, pad [2, 1, 2, 1], gain 4
+                fl = sd[bp + 'resample_filter']
+                p0, p1 = (fl.shape[-1] + 1) // 2, (fl.shape[-1] - 2) // 2
+                img = upfirdn2d_t(img, fl, up=2, padding=[p0, p1, p0, p1], gain=4)
+            else:
+                img = _t(upsample2d(img.numpy(), sd[bp + 'resample_filter'].numpy()))
         y = torgb_layer(sd, bp + 'torgb.', x, cur[:, wi], fused_modconv=fused_modconv)
         img = img + y if img is not None else y
     return img
@@ -537,7 +571,7 @@ def render(planes, w1, b1, w2, b2, ray_o, ray_d, u_coarse, u_fine, ray_start, ra
     t_co = s2t(s_co)
     c_co, d_co = run(t_co, sn_coarse)
     _, _, w_co, _ = ray_march(c_co, d_co, s_co, use_inf_depth, last_back, white_back_end_idx, clamp_mode)   # s-space (:152)
-    wts = w_co.reshape(B * R, N) + 1e-5
+    wts = w_co.detach().reshape(B * R, N) + 1e-5          # importance sampling runs under no_grad + detach (:241, :254)
     z = s_co.reshape(B * R, N)
     zmid = 0.5 * (z[:, :-1] + z[:, 1:])
     s_fi = sample_pdf(zmid, wts[:, 1:-1], u_fine.reshape(B * R, N)).reshape(B, R, N)
@@ -546,7 +580,7 @@ def render(planes, w1, b1, w2, b2, ray_o, ray_d, u_coarse, u_fine, ray_start, ra
     all_t = torch.cat([t_co, t_fi], dim=-1)
     all_c = torch.cat([c_co, c_fi], dim=-2)
     all_d = torch.cat([d_co, d_fi], dim=-1)
-    order = np.argsort(all_t.numpy(), axis=-1, kind='stable')
+    order = np.argsort(all_t.detach().numpy(), axis=-1, kind='stable')
     order = torch.from_numpy(order)
     all_t = torch.gather(all_t, -1, order)
     all_d = torch.gather(all_d, -1, order)

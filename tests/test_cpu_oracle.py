@@ -61,22 +61,20 @@ def test_render_oracle_vs_golden(golden, name, kw):
     assert maxrel(T, g[name + '/tfinal']) < TOL
 
 
-def _net_state():
+@pytest.mark.parametrize('variant', ['small', 'wide'])
+def test_generator_discriminator_oracle_vs_golden(golden, variant):
     from conftest import ROOT
-    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
-    return meta
-
-
-def test_generator_discriminator_oracle_vs_golden(golden):
-    meta = _net_state()
+    tag = 'networks' if variant == 'small' else 'networks_wide'
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', tag + '_meta.json')))
     kw = meta['net_kwargs']
+    pr = (lambda a: np.asarray(a)) if variant == 'small' else (lambda a: cases.grad_probe(np.asarray(a)))
     Gc, Dc, m = ref_harness.make_cfg(**kw)
     sdG = cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, _structural_buffers(meta['G_keys']), seed=100)
     sdD = cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, _structural_buffers(meta['D_keys']), seed=200)
     inp = cases.net_inputs(kw)
     t = {k: torch.from_numpy(v) for k, v in inp.items()}
     B = t['z'].shape[0]
-    g = golden('networks')
+    g = golden(tag)
     num_ws = g['G/ws'].shape[1]
     ws = R.mapping_network(sdG, 'mapping.', t['z'], t['c'], num_ws)
     assert maxrel(ws, g['G/ws']) < TOL
@@ -133,3 +131,51 @@ def test_fast_fir_path_used_for_cpu_timing_matches_the_restatement():
     a = R.upfirdn2d(x, f, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain'])
     b = R._upfirdn2d_aten(x, f, kw['up'], kw['down'], kw['padding'], kw['flip_filter'], kw['gain'])
     assert a.shape == b.shape and maxrel(a, b) < TOL
+
+
+@pytest.mark.parametrize('variant', ['small', 'wide'])
+def test_differentiable_oracle_gradients_vs_golden(golden, variant):
+    """oracle/restated.py with DIFFERENTIABLE=True (the arithmetic bench.py's executed CPU training step runs, oracle/train_step.py) against the
+    reference's own autograd: Gmain loss and parameter gradients through G and D, D loss incl. the R1 double backward."""
+    from conftest import ROOT
+    tag = 'networks' if variant == 'small' else 'networks_wide'
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', tag + '_meta.json')))
+    kw = meta['net_kwargs']
+    Gc, Dc, m = ref_harness.make_cfg(**kw)
+    sdG = cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, _structural_buffers(meta['G_keys']), seed=100)
+    sdD = cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, _structural_buffers(meta['D_keys']), seed=200)
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(kw).items()}
+    B = t['z'].shape[0]
+    g = golden(tag)
+    pr = (lambda a: a) if variant == 'small' else cases.grad_probe
+    old = (R.DIFFERENTIABLE, R.FAST_FIR)
+    R.DIFFERENTIABLE, R.FAST_FIR = True, True
+    try:
+        namesG, namesD = cases.probe_params('G', variant), cases.probe_params('D', variant)
+        for n in namesG:
+            sdG[n].requires_grad_(True)
+        for n in namesD:
+            sdD[n].requires_grad_(True)
+        noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+        ws = R.mapping_network(sdG, 'mapping.', t['z'], t['c'], g['G/ws'].shape[1])
+        o = R.generator_synthesis(sdG, Gc, ws, t['angles'], t['fov'], t['radius'], t['look_at'], kw['patch_res'], t['patch_scales'], t['patch_offsets'],
+                                  t['u_coarse'], t['u_fine'], noise_mode='random', noises=noises, fused_modconv=False,
+                                  depth_head_idx=torch.from_numpy(cases.depth_heads(B)))
+        top = kw['img_resolution']
+        block_res = [2 ** i for i in range(int(np.log2(top)), 2, -1)]
+        lg, _ = R.discriminator(sdD, o['img'], t['c'], t['patch_scales'], t['patch_offsets'], block_res, Dc['num_additional_start_blocks'])
+        lossG = torch.nn.functional.softplus(-lg).mean()
+        assert abs(lossG.item() - float(g['G/loss'][0])) < 1e-5 * max(1.0, abs(float(g['G/loss'][0])))
+        gs = torch.autograd.grad(lossG, [sdG[n] for n in namesG])
+        for n, gr in zip(namesG, gs):
+            assert maxrel(pr(gr.numpy()), g['G/grad/' + n]) < 2e-4, n
+        img = torch.from_numpy(g['G/train/img']).requires_grad_(True)
+        lg, _ = R.discriminator(sdD, img, t['c'], t['patch_scales'], t['patch_offsets'], block_res, Dc['num_additional_start_blocks'], predict_feat=True)
+        r1 = torch.autograd.grad([lg.sum()], [img], create_graph=True)[0]
+        assert maxrel(r1.detach().numpy(), g['D/r1_grads']) < 1e-4
+        loss = torch.nn.functional.softplus(-lg).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+        gs = torch.autograd.grad(loss, [sdD[n] for n in namesD])
+        for n, gr in zip(namesD, gs):
+            assert maxrel(pr(gr.numpy()), g['D/grad/' + n]) < 2e-4, n
+    finally:
+        R.DIFFERENTIABLE, R.FAST_FIR = old

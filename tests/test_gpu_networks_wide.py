@@ -1,0 +1,259 @@
+"""GPU parity of the TENSOR-CORE path through whole networks: goldens produced by the unmodified reference (CPU, fp32) at widths where every hot
+convolution is eligible for the tcgen05 kernels (oracle/cases.py::wide_net_kwargs; tests/golden/networks_wide.npz).  Identical weights, latents,
+cameras, patch parameters and injected layer / renderer noise.  The product runs in its DEFAULT configuration -- fused modulated-conv nodes,
+polyphase / strided tcgen05 forms, tcgen05 weight gradients, fused ray-march -- i.e. the path bench.py times.
+
+Tolerances: north_star's 1e-3 max-rel for outputs of fp32 stacks; 3e-3 l2-rel for parameter gradients; for the discriminator blocks the reference runs
+in fp16 (res >= 16 here) the product's reduced-precision arithmetic is held to MIXED_TOL against the reference's fp32 evaluation (the reference's own
+fp16 result is itself ~1e-3 away from fp32; it cannot be produced on CPU: networks_discriminator.py:79 forces fp32 off-GPU)."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import cases
+from util import maxrel, l2rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+MIXED_TOL = 1e-2          # reduced-precision D blocks vs the reference's fp32 D (logits / features, max-rel)
+MIXED_GRAD_TOL = 3e-2     # ... and its parameter / input gradients (l2-rel)
+pr = cases.grad_probe
+
+
+def _build(fp32_D):
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_wide_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0)
+    G, D = cfgm.build_networks(cfg, 'cuda', fp32_D=fp32_D)
+    sdG = cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, G.state_dict(), seed=100)
+    sdD = cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, D.state_dict(), seed=200)
+    assert set(sdG) == set(G.state_dict()) and set(sdD) == set(D.state_dict())
+    G.load_state_dict(sdG); D.load_state_dict(sdD)
+    t = {k: torch.from_numpy(v).cuda() for k, v in cases.net_inputs(meta['net_kwargs']).items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    pp = dict(scales=t['patch_scales'], offsets=t['patch_offsets'])
+    return cfg, G, D, t, cam, pp, meta['net_kwargs']
+
+
+def _stats():
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    return dict(tc.stats)
+
+
+def _delta(a, b):
+    return {k: b[k] - a[k] for k in a}
+
+
+def _train_forward(G, t, cam, pp, kw, hooks=None):
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n).cuda() for n in cases.layer_noises(kw, B)]
+    G.train()
+    G.synthesis.nerf_noise_std = 0.0
+    ws = G.mapping(t['z'], t['c'])
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)))
+    out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
+    return ws, out, noises
+
+
+def test_wide_generator_runs_on_tensor_cores_and_matches_reference(golden):
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=True)
+    g = golden('networks_wide')
+    blocks = {}
+    dec = G.synthesis.tri_plane_decoder
+    hs = [getattr(dec, f'b{r}').register_forward_hook(lambda m, a, o, r=r: blocks.__setitem__(r, (o[0].detach(), o[1].detach()))) for r in dec.block_resolutions]
+    s0 = _stats()
+    ws, out, noises = _train_forward(G, t, cam, pp, kw)
+    d = _delta(s0, _stats())
+    for h in hs:
+        h.remove()
+    # every decoder layer (9 modulated 3x3 convs + 5 toRGB) is one fused tcgen05 node; the depth adaptor's two 64->64 5x5 convs are tcgen05 primitives;
+    # ATen sees only the adaptor's 1-channel ends (1->64 5x5 once, the shared 64->1 head three times)
+    assert d['fused'] == 14 and d['tc'] == 2 and d['aten'] == 4, d
+    assert maxrel(ws.detach().cpu().numpy(), g['G/ws']) < 1e-5
+    for r, (x, img) in blocks.items():
+        ex = maxrel(pr(x.contiguous().cpu().numpy()), g[f'G/block/b{r}/x']); ei = maxrel(pr(img.contiguous().cpu().numpy()), g[f'G/block/b{r}/img'])
+        assert ex < TOL and ei < TOL, (r, ex, ei)
+    planes = dec(ws, noise_mode='random', layer_noises=noises, fused_modconv=False)
+    assert maxrel(planes.detach().contiguous().flatten()[::31].cpu().numpy(), g['G/train/planes_probe']) < TOL
+    assert maxrel(out.img.detach().cpu().numpy(), g['G/train/img']) < TOL
+    assert maxrel(out.depth.detach().cpu().numpy(), g['G/train/depth']) < TOL
+    # eval: const noise, full-frame render at img_resolution (the G-inference path)
+    G.eval()
+    B = t['z'].shape[0]
+    ue = cases.eval_variates(kw, B)
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=torch.from_numpy(ue['u_coarse']).cuda(), u_fine=torch.from_numpy(ue['u_fine']).cuda())
+    s0 = _stats()
+    with torch.no_grad():
+        oe = G.synthesis(ws, cam, render_opts=ro, noise_mode='const')
+    d = _delta(s0, _stats())
+    assert d['fused'] == 14 and d['aten'] == 4, d
+    assert maxrel(pr(oe.img.contiguous().cpu().numpy()), g['G/eval/img']) < TOL
+    assert maxrel(pr(oe.depth.contiguous().cpu().numpy()), g['G/eval/depth']) < TOL
+
+
+def test_wide_generator_loss_gradients_vs_reference(golden):
+    """Gmain: softplus(-D(G(z))) differentiated through the fused D nodes (input gradients), the fused ray-march backward and the fused decoder nodes."""
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=True)
+    g = golden('networks_wide')
+    D.train()
+    D.requires_grad_(False)
+    s0 = _stats()
+    ws, out, _ = _train_forward(G, t, cam, pp, kw)
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    d = _delta(s0, _stats())
+    # D: 15 stride-1 Conv2dLayers as fused first-order nodes, 6 down-sampling convs (3 strided 3x3 + 3 1x1 skips) as tcgen05 primitives, ATen only for
+    # fromrgb (4 input channels) and the epilogue conv (129 input channels: minibatch-std adds one)
+    assert d['fused'] == 14 + 15 and d['tc'] == 2 + 6 and d['aten'] == 4 + 2, d
+    loss = torch.nn.functional.softplus(-logits).mean()
+    assert abs(loss.item() - float(g['G/loss'][0])) < 1e-3 * max(1.0, abs(float(g['G/loss'][0])))
+    names = cases.probe_params('G', 'wide')
+    pars = dict(G.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['G/grad/' + n]) for n, gr in zip(names, gs)}
+    assert max(errs.values()) < 3e-3, errs
+
+
+def test_wide_discriminator_fp32_first_order_and_r1_vs_reference(golden):
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=True)
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    g = golden('networks_wide')
+    D.train()
+    B = t['z'].shape[0]
+    names = cases.probe_params('D', 'wide')
+    pars = dict(D.named_parameters())
+    # first-order phase (Dmain): fused nodes
+    blocks = {}
+    hs = [getattr(D, f'b{r}').register_forward_hook(lambda m, a, o, r=r: blocks.__setitem__(r, o.detach())) for r in D.block_resolutions]
+    img = torch.from_numpy(g['G/train/img']).cuda().requires_grad_(True)
+    s0 = _stats()
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    d = _delta(s0, _stats())
+    for h in hs:
+        h.remove()
+    assert d['fused'] == 15 and d['tc'] == 6 and d['aten'] == 2, d
+    for r, x in blocks.items():
+        e = maxrel(pr(x.contiguous().cpu().numpy()), g[f'D/block/b{r}'])
+        assert e < TOL, (r, e)
+    assert maxrel(logits.detach().cpu().numpy(), g['D/logits']) < TOL
+    assert maxrel(feats.detach().cpu().numpy(), g['D/feats']) < TOL
+    embs = torch.from_numpy(cases.cotangent((B, kw['embedding_dim']), 31)).cuda()
+    loss1 = torch.nn.functional.softplus(-logits).mean() + (feats - embs).norm(dim=1).mean()
+    assert abs(loss1.item() - float(g['D/loss1'][0])) < 1e-3 * abs(float(g['D/loss1'][0]))
+    gs = torch.autograd.grad(loss1, [img] + [pars[n] for n in names])
+    assert l2rel(gs[0].cpu().numpy(), g['D/grad1/img']) < 2e-3
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['D/grad1/' + n]) for n, gr in zip(names, gs[1:])}
+    assert max(errs.values()) < 2e-3, errs
+    # R1 phase (Dreg): twice-differentiable composition on the tcgen05 primitives (forward, input gradient, weight gradient of the input gradient)
+    img = torch.from_numpy(g['G/train/img']).cuda().requires_grad_(True)
+    s0 = _stats()
+    with layers.first_order_only(False):
+        logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    d = _delta(s0, _stats())
+    assert d['fused'] == 0 and d['tc'] == 21 and d['aten'] == 2, d
+    with cg.no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    assert l2rel(r1.detach().cpu().numpy(), g['D/r1_grads']) < TOL
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['D/grad/' + n]) for n, gr in zip(names, gs)}
+    assert max(errs.values()) < 3e-3, errs
+
+
+def test_wide_discriminator_benchmarked_precision_vs_reference(golden, capsys):
+    """The mode bench.py times: blocks the reference runs in fp16 (b128..b16 here) use reduced-precision tensor-core operands with fp32 accumulation
+    and fp32 storage; b8 / b4 are fp32-grade.  Held against the reference's fp32 evaluation with the stated MIXED_TOL."""
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=False)
+    g = golden('networks_wide')
+    D.train()
+    B = t['z'].shape[0]
+    assert [getattr(D, f'b{r}').use_fp16 for r in D.block_resolutions] == [True, True, True, True, False]
+    img = torch.from_numpy(g['G/train/img']).cuda().requires_grad_(True)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    e_l, e_f = maxrel(logits.detach().cpu().numpy(), g['D/logits']), maxrel(feats.detach().cpu().numpy(), g['D/feats'])
+    names = cases.probe_params('D', 'wide')
+    pars = dict(D.named_parameters())
+    embs = torch.from_numpy(cases.cotangent((B, kw['embedding_dim']), 31)).cuda()
+    loss1 = torch.nn.functional.softplus(-logits).mean() + (feats - embs).norm(dim=1).mean()
+    gs = torch.autograd.grad(loss1, [img] + [pars[n] for n in names])
+    e_img = l2rel(gs[0].cpu().numpy(), g['D/grad1/img'])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['D/grad1/' + n]) for n, gr in zip(names, gs[1:])}
+    with capsys.disabled():
+        print(f'\n[mixed-precision D vs fp32 reference] logits {e_l:.2e} feats {e_f:.2e} d/d(img) {e_img:.2e} worst param grad {max(errs.values()):.2e}')
+    assert e_l < MIXED_TOL and e_f < MIXED_TOL, (e_l, e_f)
+    assert e_img < MIXED_GRAD_TOL and max(errs.values()) < MIXED_GRAD_TOL, (e_img, errs)
+    # R1 in the benchmarked precision
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    img = torch.from_numpy(g['G/train/img']).cuda().requires_grad_(True)
+    with layers.first_order_only(False):
+        logits, _ = D(img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    with cg.no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    e_r1 = l2rel(r1.detach().cpu().numpy(), g['D/r1_grads'])
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['D/grad/' + n]) for n, gr in zip(names, gs)}
+    with capsys.disabled():
+        print(f'[mixed-precision D vs fp32 reference] R1 gradient {e_r1:.2e} worst param grad incl. R1 {max(errs.values()):.2e}')
+    assert e_r1 < MIXED_GRAD_TOL and max(errs.values()) < MIXED_GRAD_TOL, (e_r1, errs)
+
+
+def test_wide_generator_gradients_through_benchmarked_discriminator(golden, capsys):
+    """Gmain exactly as benchmarked: fp32-grade G, mixed-precision D."""
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=False)
+    g = golden('networks_wide')
+    D.train(); D.requires_grad_(False)
+    ws, out, _ = _train_forward(G, t, cam, pp, kw)
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    names = cases.probe_params('G', 'wide')
+    pars = dict(G.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['G/grad/' + n]) for n, gr in zip(names, gs)}
+    with capsys.disabled():
+        print(f'\n[G gradients through the mixed-precision D vs fp32 reference] loss {abs(loss.item() - float(g["G/loss"][0])):.2e} worst {max(errs.values()):.2e}')
+    assert abs(loss.item() - float(g['G/loss'][0])) < MIXED_TOL * max(1.0, abs(float(g['G/loss'][0])))
+    assert max(errs.values()) < MIXED_GRAD_TOL, errs
+
+
+def test_g_ema_sees_updated_weights_after_a_step():
+    """The fused optimiser kernel writes G_ema's flat storage behind autograd's version counters: its cached bf16 conv operands must be dropped, or every
+    G_ema forward after the first would mix frozen conv weights with current affine / bias parameters."""
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=True)
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    sg = importlib.import_module('3dgp_b200.training.networks_stylegan2')
+    B = t['z'].shape[0]
+    loss = lossm.StyleGAN2Loss(cfg, 'cuda', G, D, r1_gamma=1.0)
+    tr = stepm.Trainer(G, D, loss, cfg, D_reg_interval=16, ema_kimg=0.001, ema_rampup=None)     # fast EMA: G_ema moves visibly in one step
+    torch.manual_seed(0); np.random.seed(0)
+    res = kw['img_resolution']
+    real = dn.EasyDict(img=torch.rand(B, 3, res, res, device='cuda') * 2 - 1, depth=torch.rand(B, 1, res, res, device='cuda') * 2 - 1, c=t['c'],
+                       embs=torch.randn(B, kw['embedding_dim'], device='cuda'), camera_angles=t['angles'])
+    gen = dn.EasyDict(z=t['z'], c=t['c'], camera_params=cam)
+    Ge = tr.G_ema
+    ws = Ge.mapping(t['z'], t['c']).detach()
+
+    def planes(fused):
+        sg.fused_layer_enabled = fused
+        try:
+            with torch.no_grad():
+                return Ge.synthesis.tri_plane_decoder(ws, noise_mode='const').clone()
+        finally:
+            sg.fused_layer_enabled = True
+    p0 = planes(True)                      # populates the operand cache of G_ema's conv weights
+    tr.step(real, gen)
+    p1, p1_ref = planes(True), planes(False)
+    assert not torch.equal(p0, p1)
+    assert maxrel(p1.cpu().numpy(), p1_ref.cpu().numpy()) < 1e-4, 'G_ema forward used stale conv operands'
+    w0 = Ge.synthesis.tri_plane_decoder.b8.conv0.weight
+    assert maxrel(w0.detach().cpu().numpy(), G.synthesis.tri_plane_decoder.b8.conv0.weight.detach().cpu().numpy()) < 1e-2   # G_ema tracks G

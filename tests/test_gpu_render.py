@@ -184,3 +184,38 @@ def test_render_backward_generations_agree_at_full_size():
     nzi = b.abs() > 1e-3 * b.abs().max()
     rel = ((a[nzi] - b[nzi]).abs() / b[nzi].abs())
     assert rel.median().item() < 1e-4 and (rel > 1e-2).float().mean().item() < 1e-3
+
+
+def test_render_baseline_geometry_vs_oracle():
+    """BASELINE geometry (one image: 512^2 x 32-ch tri-planes, 64x64 patch rays from the reference's ray generator, 48+48 samples/ray) against the CPU
+    oracle run on this box: forward outputs within 1e-3 max-rel, all parameter / plane / ray gradients within 1e-3 l2-rel (training default: 3xTF32 MLP)."""
+    rm = _rm()
+    rs = np.random.RandomState(11)
+    B, P, res, N = 1, 512, 64, 48
+    Rr = res * res
+    planes = rs.standard_normal((B, 3, 32, P, P)).astype(np.float32)
+    w1 = rs.standard_normal((64, 32)).astype(np.float32); b1 = (0.2 * rs.standard_normal(64)).astype(np.float32)
+    w2 = rs.standard_normal((4, 64)).astype(np.float32); b2 = (0.2 * rs.standard_normal(4)).astype(np.float32)
+    angles = torch.tensor([[0.4, 1.3, 0.0]]); look = torch.tensor([[0.5, 1.4, 0.1]])
+    c2w = R.compute_cam2world_matrix(angles, torch.ones(B), look)
+    ro, rd = R.sample_rays(c2w, torch.tensor([28.0]), (res, res), torch.full((B, 2), 0.5), torch.tensor([[0.2, 0.3]]))
+    u1 = torch.from_numpy(rs.uniform(0, 1, (B, Rr, N)).astype(np.float32)); u2 = torch.from_numpy(rs.uniform(0, 1, (B, Rr, N)).astype(np.float32))
+    tp = [torch.from_numpy(a).requires_grad_(True) for a in (planes, w1, b1, w2, b2)]
+    ro_c, rd_c = ro.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+    old = R.DIFFERENTIABLE
+    R.DIFFERENTIABLE = True
+    try:
+        o_rgb, o_depth, o_wsum, o_T = R.render(*tp, ro_c, rd_c, u1, u2, 0.75, 1.25, 0.5, N)
+        g_rgb = torch.from_numpy(cases.cotangent(tuple(o_rgb.shape), 21)); g_dep = torch.from_numpy(cases.cotangent(tuple(o_depth.shape), 22))
+        og = torch.autograd.grad([o_rgb, o_depth], tp + [ro_c, rd_c], [g_rgb, g_dep])
+    finally:
+        R.DIFFERENTIABLE = old
+    args = [cu(a).requires_grad_(True) for a in (planes, w1, b1, w2, b2)] + [ro.cuda().requires_grad_(True), rd.cuda().requires_grad_(True)]
+    rgb, depth, wsum, tfin = rm.render_rays(*args, num_steps=N, ray_start=0.75, ray_end=1.25, box_size=1.0, u_coarse=u1.cuda(), u_fine=u2.cuda(), mlp_mode=2)
+    assert maxrel(rgb.detach().cpu().numpy(), o_rgb.detach().numpy()) < TOL
+    assert maxrel(depth.detach().squeeze(-1).cpu().numpy(), o_depth.detach().numpy()) < TOL
+    assert maxrel(wsum.detach().squeeze(-1).cpu().numpy(), o_wsum.detach().numpy()) < TOL
+    assert maxrel(tfin.detach().cpu().numpy(), o_T.detach().numpy()) < TOL
+    gs = torch.autograd.grad([rgb, depth], args, [g_rgb.cuda(), g_dep.cuda().unsqueeze(-1)])
+    for nm, a, b in zip(['planes', 'w1', 'b1', 'w2', 'b2', 'ray_o', 'ray_d'], gs, og):
+        assert l2rel(a.contiguous().cpu().numpy().reshape(-1), b.numpy().reshape(-1)) < TOL, nm

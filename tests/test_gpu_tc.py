@@ -406,12 +406,10 @@ def test_fused_conv2d_layer_matches_unfused(terms, k, act, hyper, bias, clamp, g
     params = [x] + [p for p in layer.parameters()]
     outs = []
     for fused in (True, False):
-        layers.fused_hyper_mod = fused
-        with cg.tc_terms(terms):
+        with layers.first_order_only(fused), cg.tc_terms(terms):
             y = layer(x, c=c, gain=gain)
             gs = torch.autograd.grad(y, params, dy)
         outs.append((y, gs))
-    layers.fused_hyper_mod = True
     rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
     tol = 3e-4 if terms == 3 else 2e-3
     assert outs[0][0].shape == outs[1][0].shape and rel(outs[0][0], outs[1][0]) < tol
