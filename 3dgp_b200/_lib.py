@@ -30,6 +30,19 @@ class RaymarchOpts(ctypes.Structure):
     ]
 
 
+class ConvDesc(ctypes.Structure):
+    """gp3d_conv_desc (include/gp3d_b200.h)."""
+    _fields_ = [('xh', c_void_p), ('xl', c_void_p), ('wh', c_void_p), ('wl', c_void_p), ('w_format', c_int), ('x_format', c_int), ('y', c_void_p),
+                ('N', c_int), ('H', c_int), ('W', c_int), ('Cin', c_int), ('Cout', c_int), ('num_slabs', c_int), ('ntaps', c_int), ('taps', c_void_p),
+                ('in_stride', c_int), ('HoP', c_int), ('WoP', c_int), ('Hout', c_int), ('Wout', c_int), ('osy', c_int), ('osx', c_int), ('oy0', c_int),
+                ('ox0', c_int), ('accumulate', c_int), ('epi', ctypes.POINTER(ConvEpilogue))]
+
+
+class RaymarchCam(ctypes.Structure):
+    """gp3d_raymarch_cam (include/gp3d_b200.h)."""
+    _fields_ = [('c2w', c_void_p), ('fov', c_void_p), ('patch_scales', c_void_p), ('patch_offsets', c_void_p), ('img_h', c_int), ('img_w', c_int)]
+
+
 # name -> (restype, argtypes); must list EVERY symbol of include/gp3d_b200.h (tests/test_abi.py checks this).
 PROTOTYPES = {
     'gp3d_last_error': (ctypes.c_char_p, []),
@@ -41,6 +54,8 @@ PROTOTYPES = {
                        + [c_int] * 2 + [c_int64] * 4 + [c_void_p]),
     'gp3d_filtered_lrelu_act': (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 4 + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p]),
     'gp3d_raymarch_forward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 14 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
+    'gp3d_raymarch_forward_cam': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [ctypes.POINTER(RaymarchCam)] + [c_void_p] * 12 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
+    'gp3d_generate_rays': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 3),
     'gp3d_raymarch_backward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 19 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
     'gp3d_modulate': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     'gp3d_demod_act': (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 6 + [c_float] * 3 + [c_void_p]),
@@ -55,8 +70,11 @@ PROTOTYPES = {
     'gp3d_gemm_bf16_tn': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16x3': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    'gp3d_conv_nhwc': (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
     'gp3d_conv_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p] + [c_int] * 10 + [c_void_p]),
     'gp3d_wgrad_taps_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 9 + [c_void_p] + [c_int] * 4 + [c_void_p]),
+    'gp3d_wgrad_taps_nhwc_fmt': (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_void_p] + [c_int] * 9 + [c_void_p] + [c_int] * 4 + [c_void_p]),
+    'gp3d_split_pad': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'gp3d_split_bf16': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'gp3d_adam_ema_step': (c_int, [c_void_p] * 5 + [c_int64] + [c_float] * 11 + [c_void_p, c_void_p, c_void_p]),
     'gp3d_split_bf16_pad': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

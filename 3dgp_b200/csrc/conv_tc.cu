@@ -26,6 +26,7 @@ struct ConvGeom {
     int osy, osx, oy0, ox0;
     int TW, TH, TN;              // pixel tile: TN images x TH rows x TW cols = 128
     int tiles_x, tiles_y, tiles_n, tiles_co;
+    int x_fp16, w_fp16;          // operand element formats (0 bf16, 1 fp16)
 };
 
 // Optional fused epilogue of the modulated-conv layer (networks_stylegan2.py:71 fma + :144 bias_act, no clamp):
@@ -38,6 +39,8 @@ struct ConvEpi {
 
 // TERMS == 1: y += xh * wh.   TERMS == 3 (error-compensated "bf16x3", ~2^-16 relative): y += xh*wh + xh*wl + xl*wh with
 // x = xh + xl, w = wh + wl split into bf16 pairs; all three products accumulate into the same TMEM tile.
+// TERMS == 2 ("x2w16"): y += xh*w16 + xl*w16 -- the activation keeps its bf16 pair (16 mantissa bits, fp32 range), the weight is ONE fp16
+// operand (11 bits, relative rounding 2^-12; weights are bounded, fp16 range is ample): mixed bf16 x fp16 MMAs (a_format BF16, b_format F16).
 template <int BN, int TERMS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -47,7 +50,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     // tile i overlap the TMA / MMA main loop of tile i+1; the smem ring and its phases run continuously across tiles.
     constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
     constexpr uint32_t kOperand = (CBM + BN) * CBK * 2;
-    constexpr uint32_t kStage = kOperand * (TERMS == 3 ? 2 : 1);
+    constexpr uint32_t kStage = kOperand + (TERMS == 3 ? kOperand : TERMS == 2 ? CBM * CBK * 2 : 0);     // [A_hi | B_hi] [A_lo] [B_lo]
     constexpr uint32_t kAccStride = (BN <= 128) ? 128 : 256;      // TMEM columns per accumulator buffer (two buffers: 256 or all 512 columns)
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,16 +101,14 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     mbar_expect_tx(&full_bar[st], kStage);
                     tma_load_4d(sa, &tmX, &full_bar[st], cb * CBK, cx, cy, n0);
                     tma_load_2d(sb, &tmW, &full_bar[st], slab * g.Cin + cb * CBK, co0);
-                    if (TERMS == 3) {
-                        tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, cx, cy, n0);
-                        tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], slab * g.Cin + cb * CBK, co0);
-                    }
+                    if (TERMS >= 2) tma_load_4d(sa + kOperand, &tmXl, &full_bar[st], cb * CBK, cx, cy, n0);
+                    if (TERMS == 3) tma_load_2d(sb + kOperand, &tmWl, &full_bar[st], slab * g.Cin + cb * CBK, co0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16_f32(CBM, BN);
+            const uint32_t idesc = make_idesc_f16kind(CBM, BN, g.x_fp16, g.w_fp16);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
@@ -124,10 +125,8 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     for (int k = 0; k < CBK / 16; k++) {
                         const uint64_t dah = make_desc_k_sw128(sa + k * 32), dbh = make_desc_k_sw128(sb + k * 32);
                         umma_bf16(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        if (TERMS == 3) {
-                            umma_bf16(tmem_d, dah, make_desc_k_sw128(sb + kOperand + k * 32), idesc, 1u);
-                            umma_bf16(tmem_d, make_desc_k_sw128(sa + kOperand + k * 32), dbh, idesc, 1u);
-                        }
+                        if (TERMS == 3) umma_bf16(tmem_d, dah, make_desc_k_sw128(sb + kOperand + k * 32), idesc, 1u);
+                        if (TERMS >= 2) umma_bf16(tmem_d, make_desc_k_sw128(sa + kOperand + k * 32), dbh, idesc, 1u);
                     }
                     umma_commit(&empty_bar[st]);
                 }
@@ -196,7 +195,7 @@ template <int BN, int TERMS>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXl, const CUtensorMap& tmWl, float* y, const ConvGeom& g,
                 int accumulate, cudaStream_t s, const ConvEpi& ep) {
     constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
-    constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1);
+    constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1) + (TERMS == 2 ? CBM * CBK * 2 : 0);
     const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256;
     auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -216,8 +215,13 @@ static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // General tap convolution.  taps: ntaps x (dy, dx, slab).  num_slabs = weight slabs per output channel.
 static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
                      int num_slabs, int ntaps, const int* taps, int in_stride, int HoP, int WoP, int Hout, int Wout,
-                     int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who, const gp3d_conv_epilogue* epi = nullptr) {
+                     int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who, const gp3d_conv_epilogue* epi = nullptr,
+                     int w_format = 0, int x_format = 0) {
     GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
+    GP3D_CHECK_ARG((w_format == 0 || w_format == 1) && (x_format == 0 || x_format == 1), "%s: operand formats are 0 (bf16) or 1 (fp16)", who);
+    GP3D_CHECK_ARG(w_format == 0 || wl == nullptr, "%s: fp16 weights have no low-order half", who);
+    GP3D_CHECK_ARG(x_format == 0 || xl == nullptr, "%s: fp16 activations have no low-order half", who);
+    GP3D_CHECK_ARG(!(xl != nullptr && wl == nullptr) || w_format == 1, "%s: a bf16 activation pair with a single weight operand needs fp16 weights (two-term form)", who);
     tc::ConvEpi ep{};
     if (epi) {
         GP3D_CHECK_ARG(!accumulate, "%s: the fused epilogue cannot accumulate into y", who);
@@ -226,7 +230,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         ep.dcoef = epi->dcoef; ep.noise = epi->noise; ep.bias = epi->bias; ep.enabled = 1; ep.noise_per_sample = epi->noise_per_sample;
         ep.act = epi->act; ep.alpha = epi->alpha; ep.gain = epi->gain; ep.clamp = epi->clamp;
     }
-    GP3D_CHECK_ARG((xl == nullptr) == (wl == nullptr), "%s: both low-order operands are required", who);
+    GP3D_CHECK_ARG(!(wl != nullptr && xl == nullptr), "%s: a low-order weight half needs the low-order activation half", who);
     GP3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && HoP > 0 && WoP > 0, "%s: empty tensor", who);
     GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (in_stride == 1 || in_stride == 2), "%s: bad tap list / stride", who);
     if (Cin % 64 != 0 || !(Cout % 128 == 0 || Cout == 96 || Cout == 64)) {
@@ -236,6 +240,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     GP3D_CHECK_ARG((HoP - 1) * osy + oy0 < Hout && (WoP - 1) * osx + ox0 < Wout, "%s: output lattice exceeds the output tensor", who);
     tc::ConvGeom g{};
     g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.ntaps = ntaps; g.in_stride = in_stride;
+    g.x_fp16 = x_format; g.w_fp16 = w_format;
     for (int t = 0; t < ntaps; t++) { g.tdy[t] = taps[3 * t]; g.tdx[t] = taps[3 * t + 1]; g.tslab[t] = taps[3 * t + 2];
         GP3D_CHECK_ARG(g.tslab[t] >= 0 && g.tslab[t] < num_slabs, "%s: weight slab out of range", who); }
     g.HoP = HoP; g.WoP = WoP; g.Hout = Hout; g.Wout = Wout; g.osy = osy; g.osx = osx; g.oy0 = oy0; g.ox0 = ox0;
@@ -257,7 +262,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)(g.TW * in_stride), (cuuint32_t)(g.TH * in_stride), (cuuint32_t)g.TN};
         cuuint32_t estr[4] = {1, (cuuint32_t)in_stride, (cuuint32_t)in_stride, 1};
-        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(tm, x_format == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { gp3d_set_error("%s: activation tensor map encode failed (CUresult %d)", who, (int)r); return GP3D_E_BADARG; }
     }
@@ -269,7 +274,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         cuuint64_t strides[1] = {Kt * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(tm, w_format == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { gp3d_set_error("%s: weight tensor map encode failed (CUresult %d)", who, (int)r); return GP3D_E_BADARG; }
     }
@@ -281,6 +286,11 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
            : (BN == 128) ? tc::launch_conv<128, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
            : (BN == 96)  ? tc::launch_conv<96, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
                          : tc::launch_conv<64, 1>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
+    } else if (!wl) {
+        tmWl = tmW;
+        rc = (BN == 128) ? tc::launch_conv<128, 2>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+           : (BN == 96)  ? tc::launch_conv<96, 2>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+                         : tc::launch_conv<64, 2>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
     } else {
         rc = (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
            : (BN == 96)  ? tc::launch_conv<96, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
@@ -328,4 +338,12 @@ extern "C" int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* w
     GP3D_CHECK_ARG(h_taps != nullptr, "conv_taps_nhwc: null tap list");
     return conv_impl(xh, xl, wh, wl, y, N, H, W, Cin, Cout, num_slabs, ntaps, h_taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0,
                      accumulate, stream, "conv_taps_nhwc");
+}
+
+// One descriptor-based entry point covering every form above (and the two-term bf16-pair x fp16-weight form).
+extern "C" int gp3d_conv_nhwc(const gp3d_conv_desc* d, void* stream) {
+    GP3D_CHECK_ARG(d != nullptr, "conv_nhwc: null descriptor");
+    GP3D_CHECK_ARG(d->taps != nullptr, "conv_nhwc: null tap list");
+    return conv_impl(d->xh, d->xl, d->wh, d->wl, d->y, d->N, d->H, d->W, d->Cin, d->Cout, d->num_slabs, d->ntaps, d->taps, d->in_stride,
+                     d->HoP, d->WoP, d->Hout, d->Wout, d->osy, d->osx, d->oy0, d->ox0, d->accumulate, stream, "conv_nhwc", d->epi, d->w_format, d->x_format);
 }

@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(256) grad_epilogue_kernel(float* g, int64_t nu
 }
 
 // hi = bf16(x * s), lo = bf16(x * s - hi); channel-minor tensors, 8 channels per thread
-template <class T>
-__global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
-                                                         __nv_bfloat16* __restrict__ lo, int N, int HW, int C, int Cp) {
+template <class T, class OT = __nv_bfloat16>
+__global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x, const float* __restrict__ s, OT* __restrict__ hi,
+                                                         OT* __restrict__ lo, int N, int HW, int C, int Cp) {
     // Cp >= C: channel count of the outputs (zero-padded tail so that 96-channel tensors fill whole 64-channel TMA blocks)
     const int64_t nvec = (int64_t)N * HW * Cp / 8;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
@@ -197,21 +197,21 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const T* __restrict__ x
             f[0] *= sa.x; f[1] *= sa.y; f[2] *= sa.z; f[3] *= sa.w; f[4] *= sb.x; f[5] *= sb.y; f[6] *= sb.z; f[7] *= sb.w;
         }
         float r[8];
-        vec16<__nv_bfloat16> h; h.pack(f); h.store(hi + o0);
+        vec16<OT> h; h.pack(f); h.store(hi + o0);
         if (lo) {
             float hf[8]; h.unpack(hf);
 #pragma unroll
             for (int k = 0; k < 8; k++) r[k] = f[k] - hf[k];
-            vec16<__nv_bfloat16> l; l.pack(r); l.store(lo + o0);
+            vec16<OT> l; l.pack(r); l.store(lo + o0);
         }
     }
 }
 
 // Division-free form for the common channel counts (C_out / 8 divides 256): grid (pixel blocks, N); a thread keeps ONE 8-channel group
 // (its styles stay in registers) and walks the pixels of image blockIdx.y, four independent pixels in flight.
-template <class T>
-__global__ void __launch_bounds__(256) split_bf16_cm_kernel(const T* __restrict__ x, const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
-                                                            __nv_bfloat16* __restrict__ lo, int HW, int C, int Cp) {
+template <class T, class OT = __nv_bfloat16>
+__global__ void __launch_bounds__(256) split_bf16_cm_kernel(const T* __restrict__ x, const float* __restrict__ s, OT* __restrict__ hi,
+                                                            OT* __restrict__ lo, int HW, int C, int Cp) {
     constexpr int U = 4;
     const int CV = Cp >> 3, PL = 256 / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(256) split_bf16_cm_kernel(const T* __restrict_
         sv[0] = sa.x; sv[1] = sa.y; sv[2] = sa.z; sv[3] = sa.w; sv[4] = sb.x; sv[5] = sb.y; sv[6] = sb.z; sv[7] = sb.w;
     }
     const T* xb = x + (int64_t)n * HW * C + c0;
-    __nv_bfloat16* hb = hi + (int64_t)n * HW * Cp + c0;
-    __nv_bfloat16* lb = lo ? lo + (int64_t)n * HW * Cp + c0 : nullptr;
+    OT* hb = hi + (int64_t)n * HW * Cp + c0;
+    OT* lb = lo ? lo + (int64_t)n * HW * Cp + c0 : nullptr;
     for (int px0 = blockIdx.x * PL * U + pl; px0 < HW; px0 += gridDim.x * PL * U) {
         float f[U][8];
 #pragma unroll
@@ -250,12 +250,12 @@ __global__ void __launch_bounds__(256) split_bf16_cm_kernel(const T* __restrict_
             if (px < HW) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) f[u][k] *= sv[k];
-                vec16<__nv_bfloat16> h; h.pack(f[u]); h.store(hb + (int64_t)px * Cp);
+                vec16<OT> h; h.pack(f[u]); h.store(hb + (int64_t)px * Cp);
                 if (lb) {
                     float hf[8], r[8]; h.unpack(hf);
 #pragma unroll
                     for (int k = 0; k < 8; k++) r[k] = f[u][k] - hf[k];
-                    vec16<__nv_bfloat16> l; l.pack(r); l.store(lb + (int64_t)px * Cp);
+                    vec16<OT> l; l.pack(r); l.store(lb + (int64_t)px * Cp);
                 }
             }
         }
@@ -388,10 +388,11 @@ extern "C" int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, floa
     GP3D_RETURN_LAUNCH();
 }
 
-extern "C" int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream) {
+extern "C" int gp3d_split_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, int hi_format, void* stream) {
     GP3D_CHECK_ARG(x && hi && N >= 1 && HW >= 1 && C >= 1, "split_bf16: bad arguments");
     GP3D_CHECK_ARG(C % 8 == 0 && C_out % 8 == 0 && C_out >= C, "split_bf16: channel counts must be multiples of 8 with C_out >= C (got %d -> %d)", C, C_out);
     GP3D_CHECK_ARG(gp3d_aligned16(x) && gp3d_aligned16(hi) && (!lo || gp3d_aligned16(lo)) && (!s || gp3d_aligned16(s)), "split_bf16: pointers must be 16-byte aligned");
+    GP3D_CHECK_ARG(hi_format == 0 || (hi_format == 1 && lo == nullptr), "split: hi_format is 0 (bf16, optional low-order half) or 1 (fp16, no low-order half)");
     const int64_t nvec = (int64_t)N * HW * C_out / 8;
     const int grid = gp3d_grid_for(nvec, 256, 8);
     cudaStream_t st = (cudaStream_t)stream;
@@ -404,14 +405,23 @@ extern "C" int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s,
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         const dim3 g2((unsigned)gx, (unsigned)N);
-        if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float><<<g2, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
+        if (hi_format == 1) {
+            if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float, __half><<<g2, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)nullptr, HW, C, C_out);
+            else split_bf16_cm_kernel<__half, __half><<<g2, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)nullptr, HW, C, C_out);
+        } else if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float><<<g2, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
         else split_bf16_cm_kernel<__half><<<g2, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
         GP3D_RETURN_LAUNCH();
     }
-    if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
-    else if (src_dtype == GP3D_F16) split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
-    else { gp3d_set_error("split_bf16: source must be float32 or float16"); return GP3D_E_BADARG; }
+    if (hi_format == 1) {
+        if (src_dtype == GP3D_F32) split_bf16_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)nullptr, N, HW, C, C_out);
+        else split_bf16_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)nullptr, N, HW, C, C_out);
+    } else if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
+    else split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     GP3D_RETURN_LAUNCH();
+}
+
+extern "C" int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream) {
+    return gp3d_split_pad(x, src_dtype, s, hi, lo, N, HW, C, C_out, 0, stream);
 }
 
 extern "C" int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream) {

@@ -21,7 +21,37 @@ struct Params {
     const float* g_rgb; const float* g_depth;
     float* g_planes; float* g_w1; float* g_b1; float* g_w2; float* g_b2; float* g_ray_o; float* g_ray_d;
     gp3d_raymarch_opts o;
+    // in-kernel ray generation (third-generation forward, gp3d_generate_rays): pinhole camera per image instead of ray_o / ray_d
+    const float* cam_c2w;      // [B][4][4] row-major cam2world (rendering_utils.py:194-218)
+    const float* cam_fov;      // [B] degrees
+    const float* patch_scale;  // [B][2] or NULL (full frame)
+    const float* patch_offset; // [B][2] or NULL
+    int img_w, img_h;          // rays form an img_h x img_w grid, row-major (ray = y * img_w + x); 0 = unknown (1-D tiles)
 };
+
+// One pinhole-camera ray (tri_plane_renderer.py:487-527): NDC grid x in linspace(-1, 1, w), y in linspace(1, -1, h) (ATen's symmetric linspace),
+// optional patch transform (:511-512), z = -1 / tan(fov / 2), normalise, rotate by cam2world; origin = cam2world translation.
+__device__ __forceinline__ float linspace_sym(float start, float end, int steps, int i) {
+    const float step = (end - start) / (float)(steps - 1);
+    return (i < steps / 2) ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+__device__ __forceinline__ void generate_ray(const Params& p, int b, int x, int y, float (&o)[3], float (&d)[3]) {
+    const float* M = p.cam_c2w + (size_t)b * 16;
+    float xs = linspace_sym(-1.f, 1.f, p.img_w, x), ys = linspace_sym(1.f, -1.f, p.img_h, y);
+    if (p.patch_scale != nullptr) {
+        xs = (xs + 1.0f) * p.patch_scale[b * 2 + 0] - 1.0f + p.patch_offset[b * 2 + 0] * 2.0f;
+        ys = (ys + 1.0f) * p.patch_scale[b * 2 + 1] - 1.0f + p.patch_offset[b * 2 + 1] * 2.0f;
+    }
+    const float fov_rad = p.cam_fov[b] / 360.0f * 2.0f * 3.14159265358979323846f;
+    const float z = -1.0f / tanf(fov_rad * 0.5f);
+    const float nrm = sqrtf(xs * xs + ys * ys + z * z);
+    const float dx = xs / nrm, dy = ys / nrm, dz = z / nrm;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        d[i] = M[i * 4 + 0] * dx + M[i * 4 + 1] * dy + M[i * 4 + 2] * dz;
+        o[i] = M[i * 4 + 3];
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Counter-based RNG (Philox4x32-10) for the production mode (u_* == NULL).  Stream layout:

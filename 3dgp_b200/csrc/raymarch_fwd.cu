@@ -3,6 +3,7 @@
 // Algorithmic HBM traffic: every touched plane texel once + 24 B/ray in + 2*N*4 B/ray of injected variates
 // (parity mode only) + 24 B/ray out.  No per-sample tensor ever reaches HBM.
 #include "raymarch_block.cuh"
+#include <stdlib.h>
 
 namespace rm {
 
@@ -105,6 +106,56 @@ int gp3d_raymarch_check(const void* planes, int planes_dtype, int64_t psB, int64
     return GP3D_OK;
 }
 
+int gp3d_raymarch_forward_v3(const rm::Params& p, int planes_dtype, int mode, cudaStream_t st);   // raymarch_fwd3.cu
+bool gp3d_raymarch_v3_ok(const rm::Params& p, int planes_dtype);
+
+static bool use_legacy_v2() {
+    static const int flag = [] { const char* e = getenv("GP3D_RAYMARCH_V2"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+    return flag != 0;
+}
+
+static int raymarch_forward_impl(const void* planes, int planes_dtype,
+                                 int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
+                                 const float* ray_o, const float* ray_d, const gp3d_raymarch_cam* cam,
+                                 const float* w1, const float* b1, const float* w2, const float* b2,
+                                 const float* u_coarse, const float* u_fine, const float* sn_coarse, const float* sn_fine,
+                                 float* rgb, float* depth, float* wsum, float* tfinal,
+                                 const gp3d_raymarch_opts* opts, void* stream, const char* who) {
+    int rc = gp3d_raymarch_check(planes, planes_dtype, psB, psP, psC, psY, psX, opts, who);
+    if (rc != GP3D_OK) return rc;
+    GP3D_CHECK_ARG(w1 && b1 && w2 && b2 && rgb && depth && wsum && tfinal, "%s: null pointer", who);
+    rm::Params p{};
+    p.planes = planes; p.psB = psB; p.psP = psP; p.psY = psY; p.psX = psX;
+    p.ray_o = ray_o; p.ray_d = ray_d; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+    p.u_coarse = u_coarse; p.u_fine = u_fine; p.sn_coarse = sn_coarse; p.sn_fine = sn_fine;
+    p.rgb = rgb; p.depth = depth; p.wsum = wsum; p.tfinal = tfinal;
+    p.o = *opts;
+    if (cam != nullptr) {
+        GP3D_CHECK_ARG(cam->c2w && cam->fov, "%s: camera needs cam2world matrices and fields of view", who);
+        GP3D_CHECK_ARG((cam->patch_scales == nullptr) == (cam->patch_offsets == nullptr), "%s: patch scales and offsets go together", who);
+        GP3D_CHECK_ARG(cam->img_h >= 2 && cam->img_w >= 2 && (int64_t)cam->img_h * cam->img_w == opts->R, "%s: img_h * img_w must equal R (got %d x %d, R = %d)", who,
+                       cam->img_h, cam->img_w, opts->R);
+        p.cam_c2w = cam->c2w; p.cam_fov = cam->fov; p.patch_scale = cam->patch_scales; p.patch_offset = cam->patch_offsets;
+        p.img_w = cam->img_w; p.img_h = cam->img_h;
+    } else {
+        GP3D_CHECK_ARG(ray_o && ray_d, "%s: null ray pointers", who);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    GP3D_CHECK_ARG(opts->mlp_mode >= 0 && opts->mlp_mode <= 2, "%s: mlp_mode must be 0 (fp32 SIMT), 1 (TF32) or 2 (3xTF32)", who);
+    int r;
+    if (opts->mlp_mode != 0 && gp3d_raymarch_v3_ok(p, planes_dtype) && !(use_legacy_v2() && cam == nullptr)) r = gp3d_raymarch_forward_v3(p, planes_dtype, opts->mlp_mode, s);
+    else {
+        if (cam != nullptr) {
+            gp3d_set_error("%s: in-kernel ray generation needs the third-generation kernel (mlp_mode 1 / 2, strides that are multiples of 8 elements)", who);
+            return GP3D_E_UNSUPPORTED;
+        }
+        if (opts->mlp_mode == 0) r = (planes_dtype == GP3D_F32) ? rm::launch_fwd<float>(p, s) : rm::launch_fwd<__half>(p, s);
+        else r = gp3d_raymarch_forward_v2(p, planes_dtype, opts->mlp_mode, s);
+    }
+    if (r != 0) return r;
+    GP3D_RETURN_LAUNCH();
+}
+
 extern "C" int gp3d_raymarch_forward(const void* planes, int planes_dtype,
                                      int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
                                      const float* ray_o, const float* ray_d,
@@ -113,20 +164,19 @@ extern "C" int gp3d_raymarch_forward(const void* planes, int planes_dtype,
                                      const float* sn_coarse, const float* sn_fine,
                                      float* rgb, float* depth, float* wsum, float* tfinal,
                                      const gp3d_raymarch_opts* opts, void* stream) {
-    int rc = gp3d_raymarch_check(planes, planes_dtype, psB, psP, psC, psY, psX, opts, "raymarch_forward");
-    if (rc != GP3D_OK) return rc;
-    GP3D_CHECK_ARG(ray_o && ray_d && w1 && b1 && w2 && b2 && rgb && depth && wsum && tfinal, "raymarch_forward: null pointer");
-    rm::Params p{};
-    p.planes = planes; p.psB = psB; p.psP = psP; p.psY = psY; p.psX = psX;
-    p.ray_o = ray_o; p.ray_d = ray_d; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
-    p.u_coarse = u_coarse; p.u_fine = u_fine; p.sn_coarse = sn_coarse; p.sn_fine = sn_fine;
-    p.rgb = rgb; p.depth = depth; p.wsum = wsum; p.tfinal = tfinal;
-    p.o = *opts;
-    cudaStream_t s = (cudaStream_t)stream;
-    GP3D_CHECK_ARG(opts->mlp_mode >= 0 && opts->mlp_mode <= 2, "raymarch_forward: mlp_mode must be 0 (fp32 SIMT), 1 (TF32) or 2 (3xTF32)");
-    int r;
-    if (opts->mlp_mode == 0) r = (planes_dtype == GP3D_F32) ? rm::launch_fwd<float>(p, s) : rm::launch_fwd<__half>(p, s);
-    else r = gp3d_raymarch_forward_v2(p, planes_dtype, opts->mlp_mode, s);
-    if (r != 0) return r;
-    GP3D_RETURN_LAUNCH();
+    return raymarch_forward_impl(planes, planes_dtype, psB, psP, psC, psY, psX, ray_o, ray_d, nullptr, w1, b1, w2, b2, u_coarse, u_fine, sn_coarse, sn_fine,
+                                 rgb, depth, wsum, tfinal, opts, stream, "raymarch_forward");
+}
+
+extern "C" int gp3d_raymarch_forward_cam(const void* planes, int planes_dtype,
+                                         int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
+                                         const gp3d_raymarch_cam* cam,
+                                         const float* w1, const float* b1, const float* w2, const float* b2,
+                                         const float* u_coarse, const float* u_fine,
+                                         const float* sn_coarse, const float* sn_fine,
+                                         float* rgb, float* depth, float* wsum, float* tfinal,
+                                         const gp3d_raymarch_opts* opts, void* stream) {
+    GP3D_CHECK_ARG(cam != nullptr, "raymarch_forward_cam: camera is null");
+    return raymarch_forward_impl(planes, planes_dtype, psB, psP, psC, psY, psX, nullptr, nullptr, cam, w1, b1, w2, b2, u_coarse, u_fine, sn_coarse, sn_fine,
+                                 rgb, depth, wsum, tfinal, opts, stream, "raymarch_forward_cam");
 }

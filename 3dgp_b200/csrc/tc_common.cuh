@@ -27,15 +27,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Bounded wait: a mis-encoded tensor map or a lost arrival must surface as an ERROR (trap -> cudaErrorLaunchFailure at the next sync), not as a hang
+// of the GPU.  try_wait itself blocks for a hardware-defined interval, so 2^26 polls are tens of seconds -- far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    asm volatile(
-        "{\n\t.reg .pred P;\n"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
-        "@P bra DONE;\n\t"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n\t}\n" ::"r"(addr), "r"(parity) : "memory");
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); spin++) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > 64) __nanosleep(spin > 4096 ? 256 : 32);
+    }
+    printf("lib3dgp_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+    __trap();
 }
 
 // ---- TMA ------------------------------------------------------------------------------------------------------------
@@ -98,6 +104,12 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
 //   c_format F32 = 1 at [4,6); a_format BF16 = 1 at [7,10); b_format BF16 = 1 at [10,13); N>>3 at [17,23); M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::f16 with per-operand element formats (library convention: 0 = bf16, 1 = fp16; the descriptor encodes F16 = 0, BF16 = 1) and majors
+// (a_mn / b_mn = 1: MN-major operand, bits 15 / 16).  Operand formats may differ (bf16 x fp16): both are widened exactly inside the tensor core.
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, int a_is_fp16, int b_is_fp16, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | ((a_is_fp16 ? 0u : 1u) << 7) | ((b_is_fp16 ? 0u : 1u) << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T   (single CTA, issued by ONE thread)
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {

@@ -24,6 +24,7 @@ struct WgradGeom {
     int HoP, WoP;               // pixel domain
     int TW, TH, TN, tiles_x, tiles_y, tiles_n;
     int tiles_co, tiles_ci, splitk;
+    int dy_fp16, x_fp16;         // operand element formats (0 bf16, 1 fp16)
 };
 
 // Shared-memory descriptor of an MN-major operand tile made of 64-channel (128-byte) column blocks of `rows_k` pixel rows:
@@ -111,7 +112,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16_f32_mn(WBM, WBN);
+            const uint32_t idesc = make_idesc_f16kind(WBM, WBN, g.dy_fp16, g.x_fp16, 1, 1);
             for (int kb = 0; kb < my_tiles; kb++) {
                 const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full_bar[st], ph);
@@ -160,14 +161,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
 
 static int wg_pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-static int encode_act_map(CUtensorMap* tm, const void* p, int N, int H, int W, int C, int TW, int TH, int TN, int stride, const char* who) {
+static int encode_act_map(CUtensorMap* tm, const void* p, int N, int H, int W, int C, int TW, int TH, int TN, int stride, const char* who, int fp16 = 0) {
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
     if (!enc) { gp3d_set_error("cuTensorMapEncodeTiled is not available from this driver"); return GP3D_E_UNSUPPORTED; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), (cuuint32_t)TN};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { gp3d_set_error("%s: tensor map encode failed (CUresult %d)", who, (int)r); return GP3D_E_BADARG; }
     return 0;
@@ -176,8 +177,16 @@ static int encode_act_map(CUtensorMap* tm, const void* p, int N, int H, int W, i
 extern "C" int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const void* xl, float* dW,
                                     int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
                                     int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream) {
+    return gp3d_wgrad_taps_nhwc_fmt(dyh, dyl, xh, xl, 0, 0, dW, N, Hd, Wd, Cout, Hx, Wx, Cin, num_slabs, ntaps, h_taps, sa, sb, HoP, WoP, stream);
+}
+
+extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const void* xh, const void* xl, int dy_format, int x_format, float* dW,
+                                        int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
+                                        int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream) {
     const char* who = "wgrad_taps_nhwc";
     GP3D_CHECK_ARG(dyh && xh && dW && h_taps, "%s: null pointer", who);
+    GP3D_CHECK_ARG((dy_format == 0 || dy_format == 1) && (x_format == 0 || x_format == 1), "%s: operand formats are 0 (bf16) or 1 (fp16)", who);
+    GP3D_CHECK_ARG(dyl == nullptr || (dy_format == 0 && x_format == 0), "%s: the three-term form takes bf16 pairs", who);
     GP3D_CHECK_ARG((dyl == nullptr) == (xl == nullptr), "%s: both low-order operands are required", who);
     GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (sa == 1 || sa == 2) && (sb == 1 || sb == 2), "%s: bad tap list / strides", who);
     GP3D_CHECK_ARG(N > 0 && HoP > 0 && WoP > 0, "%s: empty domain", who);
@@ -187,6 +196,7 @@ extern "C" int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void
     }
     tc::WgradGeom g{};
     g.N = N; g.Cin = Cin; g.Cout = Cout; g.num_slabs = num_slabs; g.ntaps = ntaps; g.sa = sa; g.sb = sb; g.HoP = HoP; g.WoP = WoP;
+    g.dy_fp16 = dy_format; g.x_fp16 = x_format;
     for (int t = 0; t < ntaps; t++) {
         g.ay[t] = h_taps[5 * t]; g.ax[t] = h_taps[5 * t + 1]; g.by[t] = h_taps[5 * t + 2]; g.bx[t] = h_taps[5 * t + 3]; g.slab[t] = h_taps[5 * t + 4];
         GP3D_CHECK_ARG(g.slab[t] >= 0 && g.slab[t] < num_slabs, "%s: weight slab out of range", who);
@@ -205,8 +215,8 @@ extern "C" int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void
     if (splitk < 1) splitk = 1;
     g.splitk = (int)splitk;
     CUtensorMap tmDh, tmXh, tmDl, tmXl;
-    int rc = encode_act_map(&tmDh, dyh, N, Hd, Wd, Cout, g.TW, g.TH, g.TN, sa, who); if (rc) return rc;
-    rc = encode_act_map(&tmXh, xh, N, Hx, Wx, Cin, g.TW, g.TH, g.TN, sb, who); if (rc) return rc;
+    int rc = encode_act_map(&tmDh, dyh, N, Hd, Wd, Cout, g.TW, g.TH, g.TN, sa, who, dy_format); if (rc) return rc;
+    rc = encode_act_map(&tmXh, xh, N, Hx, Wx, Cin, g.TW, g.TH, g.TN, sb, who, x_format); if (rc) return rc;
     if (dyl) {
         rc = encode_act_map(&tmDl, dyl, N, Hd, Wd, Cout, g.TW, g.TH, g.TN, sa, who); if (rc) return rc;
         rc = encode_act_map(&tmXl, xl, N, Hx, Wx, Cin, g.TW, g.TH, g.TN, sb, who); if (rc) return rc;

@@ -22,8 +22,9 @@ _forced_terms = None
 
 @contextlib.contextmanager
 def tc_terms(n):
-    """Precision of the tensor-core convs issued inside the block: 3 = error-compensated bf16x3 (fp32-grade, default for float32
-    tensors), 1 = single bf16 product with fp32 accumulation (the class of arithmetic the reference's fp16 discriminator blocks use).
+    """Precision of the tensor-core convs issued inside the block (ops.tc.operand_formats): 3 = error-compensated bf16x3 (fp32-grade, default for
+    float32 tensors), 16 = single product with fp16 activations / weights and bf16 gradients, fp32 accumulation and storage (the class of arithmetic
+    the reference's fp16 discriminator blocks use), 1 = single bf16 product.
     The choice is captured at forward time and reused by the corresponding backward convs."""
     global _forced_terms
     old = _forced_terms
@@ -40,34 +41,34 @@ def _terms_for(dtype):
     return 3 if dtype == torch.float32 else 1
 
 
-def _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms):
+def _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms, xg=False, wg=False):
     k = weight.shape[2]
     if (tc_enabled and bias is None and weight.shape[2] == weight.shape[3] and input.dtype in (torch.float32, torch.float16)
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[0], k, stride, padding, dilation, groups)):
         tc_stats['tc'] += 1
-        return tc.conv2d_forward(input, weight, terms)
+        return tc.conv2d_forward(input, weight, terms, x_is_grad=xg, w_is_grad=wg)
     if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and padding[0] == padding[1]
             and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
             and tc.channels_eligible(input.shape[1], weight.shape[0])):
         tc_stats['tc'] += 1
-        return tc.conv2d_strided_forward(input, weight, 2, padding[0], terms)
+        return tc.conv2d_strided_forward(input, weight, 2, padding[0], terms, x_is_grad=xg, w_is_grad=wg)
     tc_stats['aten'] += 1
     return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding, dilation=dilation, groups=groups)
 
 
-def _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms):
+def _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms, xg=False, wg=False):
     # stride-1 transposed conv == correlation with the flipped, transposed kernel and padding k-1-p
     k = weight.shape[2]
     if (tc_enabled and bias is None and tuple(stride) == (1, 1) and tuple(output_padding) == (0, 0) and weight.shape[2] == weight.shape[3]
             and tuple(padding) == (k - 1 - k // 2, k - 1 - k // 2) and input.dtype in (torch.float32, torch.float16)
             and tc.conv_eligible(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[1], k, (1, 1), (k // 2, k // 2), dilation, groups)):
         tc_stats['tc'] += 1
-        return tc.conv2d_forward(input, weight, terms, adjoint=True)
+        return tc.conv2d_forward(input, weight, terms, adjoint=True, x_is_grad=xg, w_is_grad=wg)
     if (tc_enabled and bias is None and k == 3 and weight.shape[3] == 3 and tuple(stride) == (2, 2) and tuple(padding) == (0, 0)
             and tuple(dilation) == (1, 1) and groups == 1 and input.dtype in (torch.float32, torch.float16)
             and tc.channels_eligible(input.shape[1], weight.shape[1])):
         tc_stats['tc'] += 1
-        return tc.conv_transpose2d_s2_forward(input, weight, tuple(output_padding), terms)
+        return tc.conv_transpose2d_s2_forward(input, weight, tuple(output_padding), terms, x_is_grad=xg, w_is_grad=wg)
     tc_stats['aten'] += 1
     return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
@@ -102,9 +103,10 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 _cache = dict()
 
 
-def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms=3):
+def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms=3, xg=False, wg=False):
+    """xg / wg: the op's input / weight operand is gradient-like (created inside a backward pass): precision 16 keeps those in bf16 (range)."""
     weight_shape = tuple(weight_shape)
-    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms, xg, wg)
     if key in _cache:
         return _cache[key]
     ndim = 2
@@ -122,9 +124,9 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
         def forward(ctx, input, weight, bias):
             assert tuple(weight.shape) == weight_shape
             if not transpose:
-                out = _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms)
+                out = _primitive_conv(input, weight, bias, stride, padding, dilation, groups, terms, xg, wg)
             else:
-                out = _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms)
+                out = _primitive_conv_transpose(input, weight, bias, stride, padding, output_padding, dilation, groups, terms, xg, wg)
             ctx.save_for_backward(input, weight, bias)
             return out
 
@@ -134,7 +136,7 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
                 p = out_pad_for(input.shape, grad_output.shape)
-                gi = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms).apply(grad_output, weight, None)
+                gi = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms, True, wg).apply(grad_output, weight, None)
                 assert gi.shape == input.shape
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 gw = Conv2dGradWeight.apply(grad_output, input, bias)
@@ -160,9 +162,9 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
                     # stride-1 transposed conv == conv with the flipped, transposed kernel and padding k-1-p (= k//2 here): take that conv's
                     # weight gradient and undo the flip / transpose.  This is the weight-gradient of an input-gradient op, i.e. the second-order
                     # term of the R1 penalty (loss.py:238-253).
-                    gw = tc.conv_wgrad(grad_output, input, k, 'conv', 1, k // 2, terms).flip([2, 3]).transpose(0, 1)
+                    gw = tc.conv_wgrad(grad_output, input, k, 'conv', 1, k // 2, terms, x_is_grad=xg).flip([2, 3]).transpose(0, 1)
                 else:
-                    gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], terms)
+                    gw = tc.conv_wgrad(grad_output, input, k, 'transpose' if transpose else 'conv', stride[0], padding[0], terms, x_is_grad=xg)
                 ctx.save_for_backward(grad_output, input)
                 return gw
             tc_stats['aten'] += 1
@@ -178,11 +180,11 @@ def _conv(transpose, weight_shape, stride, padding, output_padding, dilation, gr
         def backward(ctx, g2_gw):
             grad_output, input = ctx.saved_tensors
             g2_go = g2_in = None
-            if ctx.needs_input_grad[0]:
-                g2_go = Conv2d.apply(input, g2_gw, None)
+            if ctx.needs_input_grad[0]:      # the "weight" operand of these second-order ops is a gradient (g2_gw): keep it in bf16
+                g2_go = _conv(transpose, weight_shape, stride, padding, output_padding, dilation, groups, terms, xg, True).apply(input, g2_gw, None)
             if ctx.needs_input_grad[1]:
                 p = out_pad_for(input.shape, grad_output.shape)
-                g2_in = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms).apply(grad_output, g2_gw, None)
+                g2_in = _conv(not transpose, weight_shape, stride, padding, p, dilation, groups, terms, True, True).apply(grad_output, g2_gw, None)
             return g2_go, g2_in, None
 
     _cache[key] = Conv2d

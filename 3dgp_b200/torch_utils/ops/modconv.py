@@ -34,15 +34,13 @@ def _nhwc(t):
     return t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
 
+G_TERMS = 3     # precision of the tri-plane decoder's forward / input-gradient convolutions: 3 = bf16x3, 2 = x2w16 (ops.tc.operand_formats)
+
+
 def _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up):
-    L = _lib.lib()
+    """Raw convolution of the up-sampling layers: stride-2 transposed conv as four polyphase tap convolutions -> [N, 2H+1, 2W+1, Cout]."""
     dev = xh.device
-    if up == 1:
-        y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            rc = L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, 0, _lib.stream_ptr())
-        _lib.check(rc, 'conv2d_nhwc_bf16x3')
-        return y
+    assert up == 2
     Ho, Wo = 2 * H + 1, 2 * W + 1
     y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=dev)
     for a in (0, 1):
@@ -56,7 +54,7 @@ def _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up):
 
 class _ModConvLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain):
+    def forward(ctx, x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain, terms):
         L = _lib.lib()
         upfirdn2d._init()
         tc.stats['fused'] += 1
@@ -66,7 +64,7 @@ class _ModConvLayer(torch.autograd.Function):
         xn = _nhwc(x)
         st = styles.to(torch.float32).contiguous()
         xh, xl = tc.split_bf16(xn, styles=st)
-        wh, wl = tc.weight_operands(weight, 'fwd', lambda w_: w_.permute(0, 2, 3, 1))
+        wh, wl = tc.weight_operands(weight, 'fwd', lambda w_: w_.permute(0, 2, 3, 1), terms)
         d = dcoefs.to(torch.float32).contiguous() if dcoefs is not None else None
         nz = None
         nps = 0
@@ -77,11 +75,8 @@ class _ModConvLayer(torch.autograd.Function):
         if up == 1:   # demodulation, noise, bias and activation ride in the conv kernel's TMEM -> HBM epilogue: the raw conv output is never stored
             Ho, Wo = H, W
             y = torch.empty([N, H, W, Cout], dtype=torch.float32, device=dev)
-            epi = _lib.ConvEpilogue(_lib.ptr(d), _lib.ptr(nz), _lib.ptr(b), nps, 3 if act == 'lrelu' else 1, float(alpha), float(gain))
-            with torch.cuda.device(dev):
-                rc = tc.timed(2.0 * N * H * W * Cin * Cout * k * k, lambda: L.gp3d_conv2d_nhwc_bf16x3_act(
-                    xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, k, ctypes.byref(epi), _lib.stream_ptr()))
-            _lib.check(rc, 'conv2d_nhwc_bf16x3_act')
+            epi = _lib.ConvEpilogue(_lib.ptr(d), _lib.ptr(nz), _lib.ptr(b), nps, 3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0)
+            tc.conv_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, k * k, tc.same_taps(k), 1, H, W, H, W, 1, 1, 0, 0, epi=epi, what='conv2d_nhwc_act')
         else:
             c = _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up)
             # FIR after the stride-2 transposed conv: pad 1, gain up^2 (conv2d_resample.py:119-126 for k=3, fw=4)
@@ -103,7 +98,7 @@ class _ModConvLayer(torch.autograd.Function):
                               noise if noise is not None else torch.empty(0, device=dev),
                               noise_strength if noise is not None else torch.empty(0, device=dev),
                               b if b is not None else torch.empty(0, device=dev), fir if fir is not None else torch.empty(0, device=dev))
-        ctx.cfg = (N, Cin, H, W, Cout, k, up, act, float(alpha), float(gain), nps, Ho, Wo)
+        ctx.cfg = (N, Cin, H, W, Cout, k, up, act, float(alpha), float(gain), nps, Ho, Wo, terms)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -114,7 +109,7 @@ class _ModConvLayer(torch.autograd.Function):
         xn, xh, xl, weight, st, d, y, noise, noise_strength, b, fir = ctx.saved_tensors
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         need_gw = ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled
-        N, Cin, H, W, Cout, k, up, act, alpha, gain, nps, Ho, Wo = ctx.cfg
+        N, Cin, H, W, Cout, k, up, act, alpha, gain, nps, Ho, Wo, terms = ctx.cfg
         dev = dy.device
         has_d, has_n, has_b = d.numel() > 0, noise.numel() > 0, b.numel() > 0
         dyn = _nhwc(dy.to(torch.float32))
@@ -156,13 +151,10 @@ class _ModConvLayer(torch.autograd.Function):
         if not need_dx:
             pass
         elif up == 1:
-            wdh, wdl = tc.weight_operands(weight, 'dgrad1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), pad_to=Cp)    # [Cin,k,k,Cout(+pad)]
-            with torch.cuda.device(dev):
-                rc = tc.timed(2.0 * N * H * W * Cp * Cin * k * k, lambda: L.gp3d_conv2d_nhwc_bf16x3(
-                    dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cp, Cin, k, 0, _lib.stream_ptr()))
-            _lib.check(rc, 'conv2d_nhwc_bf16x3')
+            wdh, wdl = tc.weight_operands(weight, 'dgrad1', lambda w_: w_.flip([2, 3]).permute(1, 2, 3, 0), terms, pad_to=Cp)    # [Cin,k,k,Cout(+pad)]
+            tc.conv_launch(dch, dcl, wdh, wdl, dxs, N, H, W, Cp, Cin, k * k, tc.same_taps(k), 1, H, W, H, W, 1, 1, 0, 0, what='conv2d_nhwc (input gradient)')
         else:   # dx[i,j] = sum dc1[2i+ky, 2j+kx] w[co][ci][ky][kx]: strided gather over the (2H+1)^2 gradient
-            wdh, wdl = tc.weight_operands(weight, 'dgrad2', lambda w_: w_.permute(1, 2, 3, 0), pad_to=Cp)                 # [Cin,ky,kx,Cout]
+            wdh, wdl = tc.weight_operands(weight, 'dgrad2', lambda w_: w_.permute(1, 2, 3, 0), terms, pad_to=Cp)          # [Cin,ky,kx,Cout]
             taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
             tc._taps_launch(dch, dcl, wdh, wdl, dxs, N, 2 * H + 1, 2 * W + 1, Cp, Cin, 9, taps, 2, H, W, H, W, 1, 1, 0, 0)
         # weight gradient
@@ -177,11 +169,7 @@ class _ModConvLayer(torch.autograd.Function):
                 taps = [(ky, kx, 0, 0, ky * 3 + kx) for ky in range(3) for kx in range(3)]
                 sa, sb, HoP, WoP, Hd, Wd = 2, 1, H, W, 2 * H + 1, 2 * W + 1
             gw = torch.zeros([Cp, k * k, Cin], dtype=torch.float32, device=dev)
-            arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
-            with torch.cuda.device(dev):
-                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), dcl.data_ptr(), xh.data_ptr(), xl.data_ptr(), gw.data_ptr(), N, Hd, Wd, Cp, H, W, Cin, k * k,
-                                            len(taps), ctypes.cast(arr, ctypes.c_void_p), sa, sb, HoP, WoP, _lib.stream_ptr())
-            _lib.check(rc, 'wgrad_taps_nhwc')
+            tc.wgrad_launch(dch, dcl, xh, xl, gw, N, Hd, Wd, Cp, H, W, Cin, k * k, taps, sa, sb, HoP, WoP)
             gw = gw[:Cout].view(Cout, k, k, Cin).permute(0, 3, 1, 2).to(weight.dtype)
         else:
             raise RuntimeError('modconv: weight-gradient shape not covered by the tensor-core kernel (Cin %% 64 != 0)')
@@ -194,13 +182,13 @@ class _ModConvLayer(torch.autograd.Function):
                 rc = L.gp3d_modulate_bwd(dxs.data_ptr(), xn.data_ptr(), st.data_ptr(), dx.data_ptr(), g_s.data_ptr(), N, H * W, Cin, _lib.stream_ptr())
             _lib.check(rc, 'modulate_bwd')
             dx = dx.permute(0, 3, 1, 2)
-        return (dx, gw, g_s, g_d, None, g_ns, g_b, None, None, None, None, None)
+        return (dx, gw, g_s, g_d, None, g_ns, g_b, None, None, None, None, None, None)
 
 
-def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=None, bias=None, up=1, fir=None, act='lrelu', alpha=0.2, gain=1.0):
+def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=None, bias=None, up=1, fir=None, act='lrelu', alpha=0.2, gain=1.0, terms=None):
     if noise is not None and not torch.is_tensor(noise_strength):
         noise_strength = torch.as_tensor(float(noise_strength if noise_strength is not None else 1.0), device=x.device)
-    return _ModConvLayer.apply(x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain)
+    return _ModConvLayer.apply(x, weight, styles, dcoefs, noise, noise_strength, bias, up, fir, act, alpha, gain, G_TERMS if terms is None else terms)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------
@@ -225,15 +213,14 @@ class _ConvBiasAct(torch.autograd.Function):
         dev = x.device
         xn = _nhwc(x)
         st = s.to(torch.float32).contiguous() if s is not None else None
-        xh, xl = tc.split_bf16(xn, styles=st, want_lo=(terms == 3))
+        x_lo, _, x_fp16, _ = tc.operand_formats(terms)
+        xh, xl = tc.split_bf16(xn, styles=st, want_lo=x_lo, fp16=x_fp16)
         wh, wl = tc.weight_operands(weight, ('cfwd', float(wgain)), lambda w_: (w_ * wgain).permute(0, 2, 3, 1), terms)
         b = bias.to(torch.float32).contiguous() if bias is not None else None
         # channel-minor storage behind an ordinary NCHW-shaped tensor (not a view: DiscriminatorBlock adds into the skip output in place)
         y = torch.empty([N, Cout, H, W], dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         epi = _lib.ConvEpilogue(None, None, _lib.ptr(b), 0, 3 if act == 'lrelu' else 1, float(alpha), float(gain), float(clamp) if clamp is not None else -1.0)
-        with torch.cuda.device(dev):
-            rc = L.gp3d_conv2d_nhwc_act(xh.data_ptr(), _lib.ptr(xl), wh.data_ptr(), _lib.ptr(wl), y.data_ptr(), N, H, W, Cin, Cout, k, ctypes.byref(epi), _lib.stream_ptr())
-        _lib.check(rc, 'conv2d_nhwc_act')
+        tc.conv_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, k * k, tc.same_taps(k), 1, H, W, H, W, 1, 1, 0, 0, epi=epi, what='conv2d_nhwc_act')
         # linear, unclamped layers (the residual skip) do not need their output in the backward: callers may update it in place (y.add_(x))
         keep_y = (act == 'lrelu') or (clamp is not None)
         empty = torch.empty(0, device=dev)
@@ -264,12 +251,7 @@ class _ConvBiasAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] or (st.numel() and ctx.needs_input_grad[3]):
             wdh, wdl = tc.weight_operands(weight, ('cadj', wgain), lambda w_: (w_ * wgain).flip([2, 3]).permute(1, 2, 3, 0), terms)      # [Cin,k,k,Cout]
             dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
-                if terms == 3:
-                    rc = L.gp3d_conv2d_nhwc_bf16x3(dch.data_ptr(), dcl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
-                else:
-                    rc = L.gp3d_conv2d_nhwc_bf16(dch.data_ptr(), wdh.data_ptr(), dxs.data_ptr(), N, H, W, Cout, Cin, k, 0, _lib.stream_ptr())
-            _lib.check(rc, 'conv2d_nhwc (input gradient)')
+            tc.conv_launch(dch, dcl, wdh, wdl, dxs, N, H, W, Cout, Cin, k * k, tc.same_taps(k), 1, H, W, H, W, 1, 1, 0, 0, what='conv2d_nhwc (input gradient)')
             if st.numel():
                 dxo = torch.empty_like(dxs)
                 g_s = torch.zeros_like(st)
@@ -282,11 +264,7 @@ class _ConvBiasAct(torch.autograd.Function):
         if ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled:
             taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
             gwf = torch.zeros([Cout, k * k, Cin], dtype=torch.float32, device=dev)
-            arr = (ctypes.c_int * (5 * len(taps)))(*[v for t_ in taps for v in t_])
-            with torch.cuda.device(dev):
-                rc = L.gp3d_wgrad_taps_nhwc(dch.data_ptr(), _lib.ptr(dcl), xh.data_ptr(), _lib.ptr(xl), gwf.data_ptr(), N, H, W, Cout, H, W, Cin, k * k,
-                                            len(taps), ctypes.cast(arr, ctypes.c_void_p), 1, 1, H, W, _lib.stream_ptr())
-            _lib.check(rc, 'wgrad_taps_nhwc')
+            tc.wgrad_launch(dch, dcl, xh, xl, gwf, N, H, W, Cout, H, W, Cin, k * k, taps, 1, 1, H, W)
             gw = (gwf.view(Cout, k, k, Cin).permute(0, 3, 1, 2) * wgain).to(weight.dtype)
         return dx, gw, g_b, g_s, None, None, None, None, None, None
 

@@ -7,6 +7,9 @@ from ..torch_utils.ops import conv2d_gradfix, upfirdn2d
 from .layers import Conv2dLayer, FullyConnectedLayer, MappingNetwork, ScalarEncoder1d
 
 
+LOW_PRECISION_TERMS = 16     # ops.tc.operand_formats: 16 = fp16 activations / weights + bf16 gradients; 1 = bf16 everywhere
+
+
 class DiscriminatorBlock(torch.nn.Module):
     def __init__(self, cfg, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, activation='lrelu',
                  resample_filter=[1, 3, 3, 1], conv_clamp=None, use_fp16=False, fp16_channels_last=False, freeze_layers=0, down=2,
@@ -34,13 +37,14 @@ class DiscriminatorBlock(torch.nn.Module):
                                 trainable=trainable(), resample_filter=resample_filter, channels_last=cl)
 
     def forward(self, x, img, c=None, force_fp32=False):
-        """Blocks the reference runs in fp16 (res >= 32, networks_discriminator.py:240) keep float32 STORAGE here and issue their
-        convolutions as single-product bf16 tensor-core convs with fp32 accumulation (conv2d_gradfix.tc_terms(1)); the fp32 blocks
-        use the error-compensated bf16x3 form.  This removes every fp16<->fp32 cast pass of the reference path."""
+        """Blocks the reference runs in fp16 (res >= 32, networks_discriminator.py:240) keep float32 STORAGE here and issue their convolutions as
+        single-product tensor-core convs with fp16 activation / weight operands (bf16 for gradients) and fp32 accumulation
+        (conv2d_gradfix.tc_terms(LOW_PRECISION_TERMS)): the reference's arithmetic class (fp16 operands, fp32 accumulate) without its fp16 storage
+        rounding; the fp32 blocks use the error-compensated bf16x3 form.  This removes every fp16<->fp32 cast pass of the reference path."""
         low_precision = self.use_fp16 and not force_fp32
         if x is not None:
             x = x.to(dtype=torch.float32)
-        with conv2d_gradfix.tc_terms(1 if low_precision else 3):
+        with conv2d_gradfix.tc_terms(LOW_PRECISION_TERMS if low_precision else 3):
             if self.in_channels == 0:
                 y = self.fromrgb(img.to(dtype=torch.float32), c=c)
                 x = x + y if x is not None else y

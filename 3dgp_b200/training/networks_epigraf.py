@@ -117,7 +117,6 @@ class SynthesisNetwork(torch.nn.Module):
         h = w = (self.train_resolution if self.training else self.test_resolution)
         noise_std = self.nerf_noise_std if self.training else 0.0
         c2w = compute_cam2world_matrix(camera_params)
-        ray_o, ray_d = sample_rays(c2w, fov=camera_params.fov, resolution=(h, w), patch_params=patch_params, device=ws.device)
         if cfg.use_full_box:
             raise NotImplementedError('use_full_box=true (ray/box intersection bounds) is not on the 3dgp path')
         opts = EasyDict(box_size=cfg.camera.cube_scale * 2, num_proposal_steps=N, clamp_mode=cfg.get('clamp_mode', 'softplus'),
@@ -128,7 +127,11 @@ class SynthesisNetwork(torch.nn.Module):
             if k in ro:
                 opts[k] = ro[k]
         # no run_batchwise chunking (networks_epigraf.py:232-240): the fused kernel never materialises per-sample tensors
-        feats, depths, _w, _t = self.renderer(planes, self.tri_plane_mlp, ray_o, ray_d, opts)
+        if opts.get('mlp_mode', 2) == 0:      # first-generation fp32 SIMT kernels take explicit rays
+            ray_o, ray_d = sample_rays(c2w, fov=camera_params.fov, resolution=(h, w), patch_params=patch_params, device=ws.device)
+            feats, depths, _w, _t = self.renderer(planes, self.tri_plane_mlp, ray_o, ray_d, opts)
+        else:                                 # ray generation (tri_plane_renderer.py:487-527) fused into the render launch
+            feats, depths, _w, _t = self.renderer.forward_camera(planes, self.tri_plane_mlp, c2w, camera_params.fov, (h, w), patch_params, opts)
         img = feats.reshape(B, h, w, self.img_channels).permute(0, 3, 1, 2).contiguous()
         depth = depths.reshape(B, 1, h, w)
         depth_adapted = None

@@ -64,3 +64,27 @@ class ImportanceRenderer(torch.nn.Module):
             white_back_end_idx=ro.get('white_back_end_idx', 0), clamp_mode=ro.get('clamp_mode', 'softplus'),
             mlp_mode=ro.get('mlp_mode', 2), seed=ro.get('seed', 0), offset=self.launch_counter)
         return rgb, depth, wsum, tfin
+
+    def forward_camera(self, planes, decoder, c2w, fov, resolution, patch_params, rendering_options):
+        """sample_rays (:487-527) + forward (:126-170) as ONE launch: the rays of the pinhole cameras `c2w` [B,4,4] / `fov` [B] (degrees) over a
+        `resolution` = (h, w) grid (optionally the patch `patch_params` = {scales, offsets} of it) are generated inside the kernel; CTAs own 4 x 4
+        pixel tiles.  Same 4-tuple result; differentiable w.r.t. planes, decoder parameters, c2w and fov."""
+        ro = rendering_options
+        if ro.get('cut_quantile', 0.0) > 0.0:
+            raise NotImplementedError('cut_quantile > 0 is a visualisation-only option and is not built')
+        if ro['num_fine_steps'] != ro['num_proposal_steps']:
+            raise NotImplementedError('the fused kernel assumes num_fine_steps == num_proposal_steps (networks_epigraf.py:228-229)')
+        fc0, fc1 = decoder.model[0], decoder.model[1]
+        self.launch_counter += 1
+        B = planes.shape[0]
+        fov_t = fov if isinstance(fov, torch.Tensor) else torch.full([B], float(fov), device=planes.device)
+        ps = po = None
+        if patch_params is not None and len(patch_params) > 0:
+            ps, po = patch_params['scales'], patch_params['offsets']
+        return raymarch.render_camera(
+            planes, fc0.weight, fc0.bias, fc1.weight, fc1.bias, c2w, fov_t, resolution, ps, po,
+            num_steps=ro['num_proposal_steps'], ray_start=ro['ray_start'], ray_end=ro['ray_end'], box_size=ro['box_size'],
+            u_coarse=ro.get('u_coarse'), u_fine=ro.get('u_fine'), sn_coarse=ro.get('sn_coarse'), sn_fine=ro.get('sn_fine'),
+            density_noise=ro.get('density_noise', 0.0), use_inf_depth=ro.get('use_inf_depth', True), last_back=ro.get('last_back', False),
+            white_back_end_idx=ro.get('white_back_end_idx', 0), clamp_mode=ro.get('clamp_mode', 'softplus'),
+            mlp_mode=ro.get('mlp_mode', 2) or 2, seed=ro.get('seed', 0), offset=self.launch_counter)

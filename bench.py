@@ -121,9 +121,9 @@ RM = dict(B=16, P=512, C=32, H=64, res=64, N=48, ray_start=0.75, ray_end=1.25, b
 
 
 def raymarch_inputs(B, device, seed=0):
-    """Synthetic tri-planes N(0,1) stored channel-minor (the layout the tri-plane decoder emits), full-frame 64x64 rays
-    from cameras ~ configs/camera/{base,uniform}.yaml through the product's own ray generator, random-init MLP (layers.py:36: randn weights, zero bias).
-    On a CUDA device nothing here touches oracle/; the CPU arm (device='cpu') generates the same rays with the oracle's restated ray generator."""
+    """Synthetic tri-planes N(0,1) stored channel-minor (the layout the tri-plane decoder emits), cameras ~ configs/camera/{base,uniform}.yaml
+    (full-frame 64x64 rays), random-init MLP (layers.py:36: randn weights, zero bias).  Returns camera PARAMETERS; rays are generated by the consumer:
+    inside the kernel on the GPU arm, by the oracle's restated ray generator on the CPU arm."""
     g = torch.Generator(device='cpu').manual_seed(seed)
     P, C = RM['P'], RM['C']
     if torch.device(device).type == 'cuda':
@@ -136,18 +136,8 @@ def raymarch_inputs(B, device, seed=0):
     angles = torch.stack([yaw, pitch, torch.zeros(B)], 1)
     fov = torch.rand(B, generator=g) * 35 + 10
     look = torch.stack([torch.rand(B, generator=g) * 6.28 - 3.14, torch.acos(1 - 2 * torch.rand(B, generator=g).clamp(1e-5, 1 - 1e-5)), torch.rand(B, generator=g) * 0.2], 1)
-    if torch.device(device).type == 'cuda':
-        dn = importlib.import_module('3dgp_b200.dnnlib')
-        ru = importlib.import_module('3dgp_b200.training.rendering_utils')
-        tpr = importlib.import_module('3dgp_b200.training.tri_plane_renderer')
-        c2w = ru.compute_cam2world_matrix(dn.TensorGroup(angles=angles, radius=torch.ones(B), look_at=look))
-        ro, rd = tpr.sample_rays(c2w, fov, (RM['res'], RM['res']))
-    else:
-        from oracle import restated as R
-        c2w = R.compute_cam2world_matrix(angles, torch.ones(B), look)
-        ro, rd = R.sample_rays(c2w, fov, (RM['res'], RM['res']))
     w1 = torch.randn(RM['H'], C, generator=g); w2 = torch.randn(4, RM['H'], generator=g)
-    return dict(planes=planes, ray_o=ro, ray_d=rd, w1=w1, b1=torch.zeros(RM['H']), w2=w2, b2=torch.zeros(4))
+    return dict(planes=planes, angles=angles, fov=fov, look_at=look, w1=w1, b1=torch.zeros(RM['H']), w2=w2, b2=torch.zeros(4))
 
 
 def raymarch_algorithmic_bytes(B, R, N, P, C, plane_bytes=4, injected_noise=False):
@@ -157,31 +147,42 @@ def raymarch_algorithmic_bytes(B, R, N, P, C, plane_bytes=4, injected_noise=Fals
 
 def run_raymarch(args, rank, world, local):
     rmod = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    ru = importlib.import_module('3dgp_b200.training.rendering_utils')
     dev = torch.device('cuda', local)
     B = args.batch_gpu or RM['B']
     inp = raymarch_inputs(B, dev, seed=rank)
     R_ = RM['res'] ** 2
+    res = (RM['res'], RM['res'])
     d = {k: (v.to(dev) if k != 'planes' else v) for k, v in inp.items()}
     kw = dict(num_steps=RM['N'], ray_start=RM['ray_start'], ray_end=RM['ray_end'], box_size=2 * RM['box_half'], mlp_mode=args.mlp_mode)
     launches = {'n': 0}
     pl = rmod.planes_channel_minor(d['planes'])
     if args.planes_fp16:
         pl = pl.half()
+    c2w = ru.compute_cam2world_matrix(dn.TensorGroup(angles=d['angles'], radius=torch.ones(B, device=dev), look_at=d['look_at']))
 
     def step():
-        out = rmod.render_rays(pl, d['w1'], d['b1'], d['w2'], d['b2'], d['ray_o'], d['ray_d'], seed=launches['n'], **kw)
+        out = rmod.render_camera(pl, d['w1'], d['b1'], d['w2'], d['b2'], c2w, d['fov'], res, seed=launches['n'], **kw)
         launches['n'] += 1
         return out
 
+    rmod.TIMING = None
     ms, clocks = timed_region(step, args.steps, args.warmup, world)
-    n0 = launches['n']
-    # end-to-end: rays from pinned host memory every step, results read back to the host
-    ro_h = inp['ray_o'].pin_memory(); rd_h = inp['ray_d'].pin_memory()
+    # the kernel alone, live: CUDA events around every launch on the launching stream
+    rmod.TIMING = []
+    timed_region(step, args.steps, 0, world)
+    ev = rmod.TIMING; rmod.TIMING = None
+    torch.cuda.synchronize()
+    kms = float(np.mean([a.elapsed_time(b) for (a, b, *_r) in ev]))
+    # end-to-end: camera parameters from pinned host memory every step (cam2world is built on the device), results read back to the host
+    cam_h = {k: inp[k].pin_memory() for k in ('angles', 'fov', 'look_at')}
     out_h = torch.empty([B, R_, 5], pin_memory=True)
 
     def step_e2e():
-        ro = ro_h.to(dev, non_blocking=True); rd = rd_h.to(dev, non_blocking=True)
-        rgb, depth, wsum, _ = rmod.render_rays(pl, d['w1'], d['b1'], d['w2'], d['b2'], ro, rd, seed=launches['n'], **kw)
+        cd = {k: v.to(dev, non_blocking=True) for k, v in cam_h.items()}
+        c2 = ru.compute_cam2world_matrix(dn.TensorGroup(angles=cd['angles'], radius=torch.ones(B, device=dev), look_at=cd['look_at']))
+        rgb, depth, wsum, _ = rmod.render_camera(pl, d['w1'], d['b1'], d['w2'], d['b2'], c2, cd['fov'], res, seed=launches['n'], **kw)
         launches['n'] += 1
         out_h.copy_(torch.cat([rgb, depth, wsum], dim=-1), non_blocking=True)
 
@@ -193,7 +194,7 @@ def run_raymarch(args, rank, world, local):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for i in range(args.warmup + args.steps):
         evs[0].record()
-        rgb, depth, _, _ = rmod.render_rays(plg, *wsg, d['ray_o'], d['ray_d'], seed=i, density_noise=0.5, **kw)
+        rgb, depth, _, _ = rmod.render_camera(plg, *wsg, c2w, d['fov'], res, seed=i, density_noise=0.5, **kw)
         evs[1].record()
         torch.autograd.grad([rgb, depth], [plg] + wsg, [torch.ones_like(rgb), torch.ones_like(depth)])
         evs[2].record()
@@ -204,22 +205,30 @@ def run_raymarch(args, rank, world, local):
     pb = 2 if args.planes_fp16 else 4
     alg = raymarch_algorithmic_bytes(B, R_, RM['N'], RM['P'], RM['C'], plane_bytes=pb)
     peaks = measured_peaks()
-    ach = alg / (ms * 1e-3) / 1e9
-    res = dict(
+    ach = alg / (kms * 1e-3) / 1e9
+    traffic = RAYMARCH_TRAFFIC.get(f'B{B}_mode{args.mlp_mode}_{"f16" if args.planes_fp16 else "f32"}')
+    res_ = dict(
         metric='ray-march images/s (64x64 rays, 48+48 samples/ray, 32-ch 512^2 tri-planes)', value=world * B / (ms * 1e-3), unit='images/s',
-        ms_per_step=ms, dtype='f32' if not args.planes_fp16 else 'f32 math / f16 planes',
+        ms_per_step=ms, dtype='f32 (3xTF32 mma.sync MLP)' if not args.planes_fp16 else 'f32 math / f16 planes',
         config=dict(workload='raymarch (BASELINE configs[2])', batch_per_gpu=B, rays=R_, samples_per_ray=2 * RM['N'], plane_res=RM['P'],
                     l2='inputs (%.2f GB of planes per GPU) larger than the 126 MB L2' % (B * 3 * RM['C'] * RM['P'] ** 2 * pb / 1e9),
-                    rng='in-kernel Philox', mlp_mode=args.mlp_mode, parallelism=f'replicas x{world} (render does not shard)'),
-        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'],
-                      # dram__bytes_read + dram__bytes_write of one launch at this configuration (ncu --set full, profiles/r1_raymarch_fwd_v2_raw.csv)
-                      traffic=468696320 if (B == 16 and args.mlp_mode == 2 and not args.planes_fp16) else None,
-                      kernel='raymarch_fwd2_kernel' if args.mlp_mode else 'raymarch_fwd_kernel', peak_source=peaks['source'], algorithmic_bytes_per_launch=alg),
-        e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(2 * B * R_ * 12), d2h_bytes_per_step=int(B * R_ * 20)),
+                    rng='in-kernel Philox', rays_from='camera, generated in the kernel', mlp_mode=args.mlp_mode, parallelism=f'replicas x{world} (render does not shard)'),
+        roofline=dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'], traffic=traffic,
+                      kernel='raymarch_fwd3_kernel' if args.mlp_mode else 'raymarch_fwd_kernel', peak_source=peaks['source'] + ' (burst copy: kernel timed alone)',
+                      algorithmic_bytes_per_launch=alg, mean_kernel_ms=kms, launches_timed=len(ev),
+                      traffic_source='profiles/raymarch_traffic.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one launch)' if traffic else None),
+        e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=int(sum(v.numel() * 4 for v in cam_h.values())), d2h_bytes_per_step=int(B * R_ * 20)),
         gpu_launches=args.steps, clocks=clocks,
         forward_backward=dict(forward_ms=tf / args.steps, backward_ms=tb / args.steps, kernel_bwd='raymarch_bwd2_kernel' if args.mlp_mode else 'raymarch_bwd_kernel',
-                              note='backward includes the zero-fill of the plane-gradient buffer (B*3*C*P^2*4 bytes)'))
-    return res
+                              note='backward includes the ray generator launch and the zero-fill of the plane-gradient buffer (B*3*C*P^2*4 bytes)'))
+    return res_
+
+
+RAYMARCH_TRAFFIC = {}
+try:
+    RAYMARCH_TRAFFIC = json.load(open(os.path.join(ROOT, 'profiles', 'raymarch_traffic.json')))
+except Exception:
+    pass
 
 
 def cpu_raymarch(sample_rays=4096, repeats=2):
@@ -228,7 +237,9 @@ def cpu_raymarch(sample_rays=4096, repeats=2):
     torch.set_num_threads(os.cpu_count())
     inp = raymarch_inputs(1, 'cpu', seed=0)
     planes = inp['planes'].contiguous()
-    ro = inp['ray_o'][:, :sample_rays]; rd = inp['ray_d'][:, :sample_rays]
+    c2w = R.compute_cam2world_matrix(inp['angles'], torch.ones(1), inp['look_at'])
+    ro, rd = R.sample_rays(c2w, inp['fov'], (RM['res'], RM['res']))
+    ro = ro[:, :sample_rays]; rd = rd[:, :sample_rays]
     N = RM['N']
     u1 = torch.rand(1, sample_rays, N); u2 = torch.rand(1, sample_rays, N)
     best = None

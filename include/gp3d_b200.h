@@ -123,6 +123,33 @@ int gp3d_raymarch_forward(const void* planes, int planes_dtype,
                           float* rgb, float* depth, float* wsum, float* tfinal,
                           const gp3d_raymarch_opts* opts, void* stream);
 
+/* The same render with the rays GENERATED IN THE KERNEL from a pinhole camera per image -- replaces compute_cam2world_matrix's consumers
+ * sample_rays (tri_plane_renderer.py:487-527) + ImportanceRenderer.forward in one launch; no ray tensors in HBM.  Rays form an img_h x img_w grid
+ * (R == img_h * img_w, ray = y * img_w + x): x in linspace(-1, 1, img_w), y in linspace(1, -1, img_h), optional patch transform
+ * x' = (x + 1) * scale_x - 1 + 2 * offset_x (:511-512), z = -1 / tan(fov / 2), direction = cam2world[:3,:3] . normalize(x, y, z), origin = cam2world[:3, 3].
+ * CTAs own 4 x 4 pixel tiles.  Needs mlp_mode 1 / 2 and plane strides that are multiples of 8 elements. */
+typedef struct gp3d_raymarch_cam {
+    const float* c2w;            /* [B][4][4] row-major cam2world (rendering_utils.py:194-218) */
+    const float* fov;            /* [B] field of view, degrees */
+    const float* patch_scales;   /* [B][2] or NULL */
+    const float* patch_offsets;  /* [B][2] or NULL */
+    int img_h, img_w;
+} gp3d_raymarch_cam;
+
+int gp3d_raymarch_forward_cam(const void* planes, int planes_dtype,
+                              int64_t psB, int64_t psP, int64_t psC, int64_t psY, int64_t psX,
+                              const gp3d_raymarch_cam* cam,
+                              const float* w1, const float* b1, const float* w2, const float* b2,
+                              const float* u_coarse, const float* u_fine,
+                              const float* sn_coarse, const float* sn_fine,
+                              float* rgb, float* depth, float* wsum, float* tfinal,
+                              const gp3d_raymarch_opts* opts, void* stream);
+
+/* The ray generator on its own (sample_rays, tri_plane_renderer.py:487-527): ray_o, ray_d [B][img_h * img_w][3].  Used by the backward pass, which
+ * takes explicit rays. */
+int gp3d_generate_rays(const float* c2w, const float* fov, const float* patch_scales, const float* patch_offsets,
+                       int B, int img_h, int img_w, float* ray_o, float* ray_d, void* stream);
+
 /* Backward of the above.  Recomputes the forward per ray block (nothing was saved), then back-propagates
  * g_rgb [B][R][3] and g_depth [B][R] into
  *   g_planes (same strides as planes, float32, ACCUMULATED with red.global.add -- caller zero-fills),
@@ -232,6 +259,24 @@ typedef struct gp3d_conv_epilogue {
     float alpha, gain;
     float clamp;        /* > 0: clamp the result to [-clamp, clamp] (bias_act's clamp, layers.py:239); <= 0: none */
 } gp3d_conv_epilogue;
+
+/* Descriptor form of the tap convolution (every form of conv2d_resample.py:93-141 on one kernel family), including the two-term precision:
+ *   xl == NULL, wl == NULL, w_format 0 : single bf16 product                                (1 MMA  / product)
+ *   xl, wl given,           w_format 0 : bf16x3  xh*wh + xh*wl + xl*wh                      (3 MMAs / product, ~2^-16)
+ *   xl given, wl == NULL,   w_format 1 : x2w16   (xh + xl) * w16, weights in fp16           (2 MMAs / product, weight rounding 2^-12)
+ * Single-term operands may be fp16 or bf16 independently (x_format / w_format): the tensor core widens both exactly (kind::f16, mixed a/b formats). */
+typedef struct gp3d_conv_desc {
+    const void* xh; const void* xl;      /* activations, bf16 [N][H][W][Cin] (+ low-order half) */
+    const void* wh; const void* wl;      /* weights [Cout][num_slabs][Cin]: bf16 (+ low-order half), or fp16 when w_format == 1 */
+    int w_format;                        /* 0 bf16, 1 fp16 */
+    int x_format;                        /* 0 bf16, 1 fp16 (single-term only): fp16 x fp16 is the arithmetic class of the reference's fp16 discriminator blocks */
+    float* y;                            /* [N][Hout][Wout][Cout] */
+    int N, H, W, Cin, Cout, num_slabs;
+    int ntaps; const int* taps;          /* ntaps x (dy, dx, slab), host memory */
+    int in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0, accumulate;
+    const gp3d_conv_epilogue* epi;       /* optional fused epilogue */
+} gp3d_conv_desc;
+int gp3d_conv_nhwc(const gp3d_conv_desc* desc, void* stream);
 int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                                 int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
 /* same epilogue for either precision: xl / wl both NULL = single-term bf16 (the discriminator's low-precision blocks: Conv2dLayer's
@@ -269,6 +314,11 @@ int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const vo
 int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const void* xl, float* dW,
                          int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
                          int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream);
+/* Same with per-operand element formats for the single-term form (0 bf16, 1 fp16): the discriminator's fp16-class blocks multiply a bf16 gradient
+ * (range) with the fp16 activation saved by the forward pass. */
+int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const void* xh, const void* xl, int dy_format, int x_format, float* dW,
+                             int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
+                             int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream);
 
 /* fp32 / fp16 -> bf16 hi (+ lo) split with optional per-(n, c) modulation (x * styles, networks_stylegan2.py:68), channel-minor
  * (NHWC) tensors: hi = bf16(x * s[n][c]); lo = bf16(x * s[n][c] - hi) (lo may be NULL).  s may be NULL.  src_dtype: GP3D_F32 / F16.
@@ -276,6 +326,8 @@ int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const
 int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream);
 /* same, with the outputs zero-padded to C_out >= C channels (96-channel toRGB tensors -> 128 so that they fill whole 64-channel TMA blocks) */
 int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream);
+/* Same with the element format of `hi` selectable: hi_format 0 = bf16 (lo optional), 1 = fp16 (lo must be NULL). */
+int gp3d_split_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, int hi_format, void* stream);
 
 #ifdef __cplusplus
 }
