@@ -39,8 +39,9 @@ struct ConvEpi {
 
 // TERMS == 1: y += xh * wh.   TERMS == 3 (error-compensated "bf16x3", ~2^-16 relative): y += xh*wh + xh*wl + xl*wh with
 // x = xh + xl, w = wh + wl split into bf16 pairs; all three products accumulate into the same TMEM tile.
-// TERMS == 2 ("x2w16"): y += xh*w16 + xl*w16 -- the activation keeps its bf16 pair (16 mantissa bits, fp32 range), the weight is ONE fp16
-// operand (11 bits, relative rounding 2^-12; weights are bounded, fp16 range is ample): mixed bf16 x fp16 MMAs (a_format BF16, b_format F16).
+// TERMS == 2 ("x2w16"): y += xh*w16 + xl*w16 -- the activation is an fp16 PAIR (22 mantissa bits; forward activations are O(1), far inside fp16's
+// range), the weight ONE fp16 operand (11 bits, relative rounding 2^-12).  Both operands of one tcgen05.mma.kind::f16 must have the SAME element
+// format: mixed bf16 x fp16 instruction descriptors raise an illegal-instruction fault on sm_100a (measured, tools/probe_formats.py).
 template <int BN, int TERMS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -219,9 +220,9 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
                      int w_format = 0, int x_format = 0) {
     GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
     GP3D_CHECK_ARG((w_format == 0 || w_format == 1) && (x_format == 0 || x_format == 1), "%s: operand formats are 0 (bf16) or 1 (fp16)", who);
+    GP3D_CHECK_ARG(w_format == x_format, "%s: both operands of a tcgen05 kind::f16 product must have the same element format (got x %d, w %d)", who, x_format, w_format);
     GP3D_CHECK_ARG(w_format == 0 || wl == nullptr, "%s: fp16 weights have no low-order half", who);
-    GP3D_CHECK_ARG(x_format == 0 || xl == nullptr, "%s: fp16 activations have no low-order half", who);
-    GP3D_CHECK_ARG(!(xl != nullptr && wl == nullptr) || w_format == 1, "%s: a bf16 activation pair with a single weight operand needs fp16 weights (two-term form)", who);
+    GP3D_CHECK_ARG(!(xl != nullptr && wl == nullptr) || w_format == 1, "%s: an activation pair with a single weight operand is the fp16 two-term form", who);
     tc::ConvEpi ep{};
     if (epi) {
         GP3D_CHECK_ARG(!accumulate, "%s: the fused epilogue cannot accumulate into y", who);

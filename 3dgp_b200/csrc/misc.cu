@@ -392,7 +392,7 @@ extern "C" int gp3d_split_pad(const void* x, int src_dtype, const float* s, void
     GP3D_CHECK_ARG(x && hi && N >= 1 && HW >= 1 && C >= 1, "split_bf16: bad arguments");
     GP3D_CHECK_ARG(C % 8 == 0 && C_out % 8 == 0 && C_out >= C, "split_bf16: channel counts must be multiples of 8 with C_out >= C (got %d -> %d)", C, C_out);
     GP3D_CHECK_ARG(gp3d_aligned16(x) && gp3d_aligned16(hi) && (!lo || gp3d_aligned16(lo)) && (!s || gp3d_aligned16(s)), "split_bf16: pointers must be 16-byte aligned");
-    GP3D_CHECK_ARG(hi_format == 0 || (hi_format == 1 && lo == nullptr), "split: hi_format is 0 (bf16, optional low-order half) or 1 (fp16, no low-order half)");
+    GP3D_CHECK_ARG(hi_format == 0 || hi_format == 1, "split: hi_format is 0 (bf16) or 1 (fp16); either takes an optional low-order half of the same format");
     const int64_t nvec = (int64_t)N * HW * C_out / 8;
     const int grid = gp3d_grid_for(nvec, 256, 8);
     cudaStream_t st = (cudaStream_t)stream;
@@ -406,15 +406,15 @@ extern "C" int gp3d_split_pad(const void* x, int src_dtype, const float* s, void
         if (gx < 1) gx = 1;
         const dim3 g2((unsigned)gx, (unsigned)N);
         if (hi_format == 1) {
-            if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float, __half><<<g2, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)nullptr, HW, C, C_out);
-            else split_bf16_cm_kernel<__half, __half><<<g2, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)nullptr, HW, C, C_out);
+            if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float, __half><<<g2, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)lo, HW, C, C_out);
+            else split_bf16_cm_kernel<__half, __half><<<g2, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)lo, HW, C, C_out);
         } else if (src_dtype == GP3D_F32) split_bf16_cm_kernel<float><<<g2, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
         else split_bf16_cm_kernel<__half><<<g2, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, HW, C, C_out);
         GP3D_RETURN_LAUNCH();
     }
     if (hi_format == 1) {
-        if (src_dtype == GP3D_F32) split_bf16_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)nullptr, N, HW, C, C_out);
-        else split_bf16_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)nullptr, N, HW, C, C_out);
+        if (src_dtype == GP3D_F32) split_bf16_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)x, s, (__half*)hi, (__half*)lo, N, HW, C, C_out);
+        else split_bf16_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)x, s, (__half*)hi, (__half*)lo, N, HW, C, C_out);
     } else if (src_dtype == GP3D_F32) split_bf16_kernel<float><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     else split_bf16_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, HW, C, C_out);
     GP3D_RETURN_LAUNCH();

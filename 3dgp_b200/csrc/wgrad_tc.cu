@@ -186,6 +186,7 @@ extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const 
     const char* who = "wgrad_taps_nhwc";
     GP3D_CHECK_ARG(dyh && xh && dW && h_taps, "%s: null pointer", who);
     GP3D_CHECK_ARG((dy_format == 0 || dy_format == 1) && (x_format == 0 || x_format == 1), "%s: operand formats are 0 (bf16) or 1 (fp16)", who);
+    GP3D_CHECK_ARG(dy_format == x_format, "%s: both operands of a tcgen05 kind::f16 product must have the same element format (got dy %d, x %d)", who, dy_format, x_format);
     GP3D_CHECK_ARG(dyl == nullptr || (dy_format == 0 && x_format == 0), "%s: the three-term form takes bf16 pairs", who);
     GP3D_CHECK_ARG((dyl == nullptr) == (xl == nullptr), "%s: both low-order operands are required", who);
     GP3D_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && (sa == 1 || sa == 2) && (sb == 1 || sb == 2), "%s: bad tap list / strides", who);

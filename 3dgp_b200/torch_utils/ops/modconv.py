@@ -34,7 +34,8 @@ def _nhwc(t):
     return t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
 
-G_TERMS = 3     # precision of the tri-plane decoder's forward / input-gradient convolutions: 3 = bf16x3, 2 = x2w16 (ops.tc.operand_formats)
+import os
+G_TERMS = int(os.environ.get('GP3D_G_TERMS', '3'))     # precision of the tri-plane decoder's forward / input-gradient convolutions: 3 = bf16x3, 2 = x2w16 (ops.tc.operand_formats)
 
 
 def _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up):
@@ -63,7 +64,7 @@ class _ModConvLayer(torch.autograd.Function):
         dev = x.device
         xn = _nhwc(x)
         st = styles.to(torch.float32).contiguous()
-        xh, xl = tc.split_bf16(xn, styles=st)
+        xh, xl = tc.split_bf16(xn, styles=st, fp16=(terms == 2))          # terms 2: fp16 pair x fp16 weight (operands of one MMA share their format)
         wh, wl = tc.weight_operands(weight, 'fwd', lambda w_: w_.permute(0, 2, 3, 1), terms)
         d = dcoefs.to(torch.float32).contiguous() if dcoefs is not None else None
         nz = None
@@ -94,6 +95,8 @@ class _ModConvLayer(torch.autograd.Function):
                     rc = L.gp3d_demod_act(c.data_ptr(), _lib.ptr(d), _lib.ptr(nz), nps, _lib.ptr(b), y.data_ptr(), 0, N, Cout, Ho * Wo, 1,
                                           3 if act == 'lrelu' else 1, float(alpha), float(gain), -1.0, _lib.stream_ptr())
                 _lib.check(rc, 'demod_act')
+        if terms == 2:      # the gradient products run as bf16x3 (range): the backward re-splits the modulated input into a bf16 pair
+            xh = xl = torch.empty(0, device=dev)
         ctx.save_for_backward(xn, xh, xl, weight, st, d if d is not None else torch.empty(0, device=dev), y,
                               noise if noise is not None else torch.empty(0, device=dev),
                               noise_strength if noise is not None else torch.empty(0, device=dev),
@@ -111,6 +114,10 @@ class _ModConvLayer(torch.autograd.Function):
         need_gw = ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled
         N, Cin, H, W, Cout, k, up, act, alpha, gain, nps, Ho, Wo, terms = ctx.cfg
         dev = dy.device
+        if terms == 2:
+            terms = 3
+            if need_gw:
+                xh, xl = tc.split_bf16(xn, styles=st)
         has_d, has_n, has_b = d.numel() > 0, noise.numel() > 0, b.numel() > 0
         dyn = _nhwc(dy.to(torch.float32))
         # channels of the gradient operand are zero-padded to whole 64-channel TMA blocks (toRGB: 96 -> 128)
@@ -196,7 +203,8 @@ def modconv_layer(x, weight, styles, dcoefs=None, noise=None, noise_strength=Non
 #   y = clamp( act( conv( x * s[n, ci]?, w * wgain ) + b ) * gain )
 # forward : split (hyper-modulation fused) -> tcgen05 conv whose epilogue applies bias / activation / gain / clamp
 # backward: act backward (clamp mask, bias gradient) emitting the bf16 operand -> tcgen05 input-gradient conv (+ modulate_bwd) + weight gradient.
-# terms = 1 (single bf16 product: the blocks the reference runs in fp16) or 3 (bf16x3).  Stride-1 'same' shapes only.
+# terms = 3 (bf16x3), 16 (fp16 x fp16 forward, bf16 x bf16 gradient products: the blocks the reference runs in fp16) or 1 (bf16 throughout).
+# Stride-1 'same' shapes only.
 
 def conv_act_eligible(x, weight, k, up, down, padding, act, cin, cout):
     return (x.is_cuda and x.dtype == torch.float32 and up == 1 and down == 1 and k in (1, 3) and padding == k // 2 and act in ('linear', 'lrelu')
@@ -238,6 +246,7 @@ class _ConvBiasAct(torch.autograd.Function):
         N, Cin, H, W, Cout, k, wgain, act, alpha, gain, clamp, terms, has_b = ctx.cfg
         dev = dy.device
         xl = xl if xl.numel() else None
+        gterms = 3 if terms == 3 else 1             # gradient products: bf16x3, or one bf16 x bf16 product (gradients need bf16's range)
         dyn = _nhwc(dy.to(torch.float32))
         dch = torch.empty([N, H, W, Cout], dtype=torch.bfloat16, device=dev)
         dcl = torch.empty_like(dch) if terms == 3 else None
@@ -249,7 +258,7 @@ class _ConvBiasAct(torch.autograd.Function):
         _lib.check(rc, 'act_bwd_split')
         dx = g_s = gw = None
         if ctx.needs_input_grad[0] or (st.numel() and ctx.needs_input_grad[3]):
-            wdh, wdl = tc.weight_operands(weight, ('cadj', wgain), lambda w_: (w_ * wgain).flip([2, 3]).permute(1, 2, 3, 0), terms)      # [Cin,k,k,Cout]
+            wdh, wdl = tc.weight_operands(weight, ('cadj', wgain), lambda w_: (w_ * wgain).flip([2, 3]).permute(1, 2, 3, 0), gterms)      # [Cin,k,k,Cout]
             dxs = torch.empty([N, H, W, Cin], dtype=torch.float32, device=dev)
             tc.conv_launch(dch, dcl, wdh, wdl, dxs, N, H, W, Cout, Cin, k * k, tc.same_taps(k), 1, H, W, H, W, 1, 1, 0, 0, what='conv2d_nhwc (input gradient)')
             if st.numel():
@@ -264,6 +273,8 @@ class _ConvBiasAct(torch.autograd.Function):
         if ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled:
             taps = [(0, 0, ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
             gwf = torch.zeros([Cout, k * k, Cin], dtype=torch.float32, device=dev)
+            if xh.dtype == torch.float16:           # the forward's fp16 operand -> bf16 for the product with the bf16 gradient (same-format rule)
+                xh = xh.to(torch.bfloat16)
             tc.wgrad_launch(dch, dcl, xh, xl, gwf, N, H, W, Cout, H, W, Cin, k * k, taps, 1, 1, H, W)
             gw = (gwf.view(Cout, k, k, Cin).permute(0, 3, 1, 2) * wgain).to(weight.dtype)
         return dx, gw, g_b, g_s, None, None, None, None, None, None

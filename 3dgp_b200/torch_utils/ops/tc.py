@@ -50,7 +50,7 @@ def conv2d_nhwc_bf16(x, w, out=None, accumulate=False):
 def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None, fp16=False):
     """x [N, ..., C] channel-minor contiguous (float32 / float16) -> (hi, lo) bfloat16 with x * styles == hi + lo up to 2^-16.
     styles: optional float32 [N, C] per-sample channel scale fused into the split.  pad_to: output channel count (zero tail).
-    fp16=True: ONE float16 operand (hi; lo is None) -- the discriminator's fp16-class blocks."""
+    fp16=True: float16 operand(s) -- one for the discriminator's fp16-class blocks, a pair (22 bits) for the two-term x2w16 form."""
     L = _lib.lib()
     _lib.require_cuda(x_nhwc, 'x')
     assert x_nhwc.is_contiguous()
@@ -58,7 +58,7 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None, fp16=False):
     Cp = C if pad_to is None else int(pad_to)
     HW = x_nhwc.numel() // (N * C)
     hi = torch.empty(list(x_nhwc.shape[:-1]) + [Cp], dtype=torch.float16 if fp16 else torch.bfloat16, device=x_nhwc.device)
-    lo = torch.empty_like(hi) if (want_lo and not fp16) else None
+    lo = torch.empty_like(hi) if want_lo else None
     with torch.cuda.device(x_nhwc.device):
         rc = L.gp3d_split_pad(x_nhwc.data_ptr(), _lib.dtype_code(x_nhwc), _lib.ptr(styles), hi.data_ptr(), _lib.ptr(lo), N, HW, C, Cp, 1 if fp16 else 0, _lib.stream_ptr())
     _lib.check(rc, 'split')
@@ -67,19 +67,26 @@ def split_bf16(x_nhwc, styles=None, want_lo=True, pad_to=None, fp16=False):
 
 # Precision codes of the tensor-core convolutions ("terms"):
 #   3  bf16x3 : x = xh + xl, w = wh + wl (bf16 pairs), xh*wh + xh*wl + xl*wh            3 MMAs / product, ~2^-16, fp32-grade
-#   2  x2w16  : (xh + xl) * w16, bf16 activation pair x ONE fp16 weight operand          2 MMAs / product, weight rounding 2^-12
+#   2  x2w16  : (xh + xl) * w16, fp16 activation PAIR x ONE fp16 weight operand          2 MMAs / product, weight rounding 2^-12
+#               (forward activations only; a product with a gradient operand -- unbounded range -- runs as bf16x3)
 #   1  bf16   : single bf16 product                                                      1 MMA
-#   16 f16    : single product with fp16 activations and weights, bf16 for anything gradient-like (range): the arithmetic class of the
-#               reference's fp16 discriminator blocks (fp16 operands, fp32 accumulation), with fp32 storage
+#   16 f16    : single fp16 x fp16 product for activation x weight -- the arithmetic class of the reference's fp16 discriminator blocks (fp16
+#               operands, fp32 accumulation), with fp32 storage; a product with a gradient operand (range) is bf16 x bf16
+# Both operands of one MMA share their element format: tcgen05.mma.kind::f16 with a_format != b_format is an illegal instruction on sm_100a
+# (measured: tools/probe_formats.py, profiles/r2_operand_format_probe.txt).
+def effective_terms(terms, grad=False):
+    """Precision code actually executed: products with a gradient operand (`grad`) leave the fp16 forms (range)."""
+    if terms == 2:
+        return 3 if grad else 2
+    if terms == 16:
+        return 1 if grad else 16
+    return terms
+
+
 def operand_formats(terms, x_is_grad=False, w_is_grad=False):
     """(activation has low half, weight has low half, activation is fp16, weight is fp16) for a precision code."""
-    if terms == 3:
-        return True, True, False, False
-    if terms == 2:
-        return True, False, False, True
-    if terms == 16:
-        return False, False, not x_is_grad, not w_is_grad
-    return False, False, False, False
+    return {3: (True, True, False, False), 2: (True, False, True, True), 16: (False, False, True, True),
+            1: (False, False, False, False)}[effective_terms(terms, x_is_grad or w_is_grad)]
 
 
 _weight_cache = {}
@@ -117,23 +124,23 @@ def tag_weight_source(w, param, gain):
 
 
 def _operands_of(w, tag, make_nhwc, terms, w_is_grad=False):
-    """Operands of conv weight `w` in layout make_nhwc(w) for precision `terms`: cached per source Parameter when `w` carries a tag."""
+    """Operands of conv weight `w` in layout make_nhwc(w) for the (effective) precision `terms`: cached per source Parameter when `w` carries a tag."""
     src = getattr(w, '_gp3d_src', None)
     if src is not None and src[0].shape == w.shape and isinstance(src[0], torch.nn.Parameter) and not w_is_grad:
         param, gain = src
         dt = w.dtype
         return weight_operands(param, (tag, gain, dt), lambda p_: make_nhwc((p_ * gain).to(dt).to(torch.float32)), terms)
-    return _make_weight_operands(make_nhwc(w.detach().to(torch.float32)).contiguous(), terms, None, w_is_grad)
+    return _make_weight_operands(make_nhwc(w.detach().to(torch.float32)).contiguous(), terms, None)
 
 
-def _make_weight_operands(wn, terms, pad_to, w_is_grad=False):
-    _, w_lo, _, w_fp16 = operand_formats(terms, w_is_grad=w_is_grad)
+def _make_weight_operands(wn, terms, pad_to):
+    _, w_lo, _, w_fp16 = operand_formats(terms)
     return split_bf16(wn, want_lo=w_lo, pad_to=pad_to, fp16=w_fp16)
 
 
 def weight_operands(weight, tag, make_nhwc, terms=3, pad_to=None):
     """Operand(s) of a weight tensor in the layout `make_nhwc(weight)` produces ([rows][taps][cols], cols contiguous) for precision `terms`:
-    bf16 (hi, lo) pair (3), bf16 (hi, None) (1) or fp16 (w16, None) (2, 16).
+    bf16 (hi, lo) pair (3), bf16 (hi, None) (1) or fp16 (w16, None) (2, 16); `terms` is an EFFECTIVE code (effective_terms).
     Parameters are re-laid-out and split ONCE per optimiser step: the cache is keyed by (id, tag) and invalidated by the tensor's
     autograd version counter (bumped by every in-place update).  Every entry holds a weak reference to its parameter whose callback removes
     the entry: an id() reused by a new tensor after the old one died can never produce a hit, and no operand copy outlives its weight."""
@@ -162,7 +169,8 @@ def conv_eligible(N, Cin, H, W, Cout, k, stride, padding, dilation, groups):
 
 
 def _prep(x, w, tag, make_nhwc, terms, x_is_grad=False, w_is_grad=False):
-    x_lo, _, x_fp16, w_fp16 = operand_formats(terms, x_is_grad, w_is_grad)
+    terms = effective_terms(terms, x_is_grad or w_is_grad)
+    x_lo, _, x_fp16, w_fp16 = operand_formats(terms)
     xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)          # NHWC view, contiguous
     xh, xl = split_bf16(xn, want_lo=x_lo, fp16=x_fp16)
     wh, wl = _operands_of(w, tag, make_nhwc, terms, w_is_grad)
@@ -264,15 +272,15 @@ def conv_wgrad(dy, x, k, mode, stride, padding, terms, x_is_grad=False):
     """Weight gradient on the tcgen05 pixel-GEMM (csrc/wgrad_tc.cu).
     mode 'conv'      : y = conv2d(x, w[Cout,Cin,k,k], stride, padding)            -> returns dW [Cout,Cin,k,k]
     mode 'transpose' : y = conv_transpose2d(x, w[Cin,Cout,k,k], stride 2, pad 0)  -> returns dW [Cin,Cout,k,k]
-    dy: gradient of y, x: the op's input (any strides; float32 / float16).  Two-term precision (2) has no weight-gradient form: it runs as bf16x3."""
-    if terms == 2:
-        terms = 3
+    dy: gradient of y, x: the op's input (any strides; float32 / float16).  A weight gradient always has a gradient operand: bf16x3, or one
+    bf16 x bf16 product for the single-term codes (effective_terms)."""
+    terms = effective_terms(terms, True)
     N, Cx, Hx, Wx = x.shape
     _, Cy, Hy, Wy = dy.shape
     dn = dy.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
     xn = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
     dh, dl = split_bf16(dn, want_lo=(terms == 3))                                   # gradients stay bf16 (range)
-    xh, xl = split_bf16(xn, want_lo=(terms == 3), fp16=(terms == 16 and not x_is_grad))
+    xh, xl = split_bf16(xn, want_lo=(terms == 3))
     if mode == 'conv':
         # M operand = dy (Cout = Cy), N operand = x (Cin = Cx); pixel domain = output grid
         taps = [(0, 0, ky - padding, kx - padding, ky * k + kx) for ky in range(k) for kx in range(k)]

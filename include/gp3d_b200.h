@@ -263,13 +263,14 @@ typedef struct gp3d_conv_epilogue {
 /* Descriptor form of the tap convolution (every form of conv2d_resample.py:93-141 on one kernel family), including the two-term precision:
  *   xl == NULL, wl == NULL, w_format 0 : single bf16 product                                (1 MMA  / product)
  *   xl, wl given,           w_format 0 : bf16x3  xh*wh + xh*wl + xl*wh                      (3 MMAs / product, ~2^-16)
- *   xl given, wl == NULL,   w_format 1 : x2w16   (xh + xl) * w16, weights in fp16           (2 MMAs / product, weight rounding 2^-12)
- * Single-term operands may be fp16 or bf16 independently (x_format / w_format): the tensor core widens both exactly (kind::f16, mixed a/b formats). */
+ *   xl given, wl == NULL,   x_format = w_format = 1 : x2w16   (xh + xl) * w16, fp16 activation pair x fp16 weight
+ *                                                                                            (2 MMAs / product, weight rounding 2^-12)
+ * x_format must equal w_format: tcgen05.mma.kind::f16 faults (illegal instruction) on sm_100a when the A and B element formats differ. */
 typedef struct gp3d_conv_desc {
     const void* xh; const void* xl;      /* activations, bf16 [N][H][W][Cin] (+ low-order half) */
     const void* wh; const void* wl;      /* weights [Cout][num_slabs][Cin]: bf16 (+ low-order half), or fp16 when w_format == 1 */
     int w_format;                        /* 0 bf16, 1 fp16 */
-    int x_format;                        /* 0 bf16, 1 fp16 (single-term only): fp16 x fp16 is the arithmetic class of the reference's fp16 discriminator blocks */
+    int x_format;                        /* 0 bf16, 1 fp16 (== w_format): fp16 x fp16 is the arithmetic class of the reference's fp16 discriminator blocks */
     float* y;                            /* [N][Hout][Wout][Cout] */
     int N, H, W, Cin, Cout, num_slabs;
     int ntaps; const int* taps;          /* ntaps x (dy, dx, slab), host memory */
@@ -314,8 +315,7 @@ int gp3d_conv_taps_nhwc(const void* xh, const void* xl, const void* wh, const vo
 int gp3d_wgrad_taps_nhwc(const void* dyh, const void* dyl, const void* xh, const void* xl, float* dW,
                          int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
                          int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream);
-/* Same with per-operand element formats for the single-term form (0 bf16, 1 fp16): the discriminator's fp16-class blocks multiply a bf16 gradient
- * (range) with the fp16 activation saved by the forward pass. */
+/* Same with the element format of the single-term form selectable (0 bf16, 1 fp16; dy_format must equal x_format). */
 int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const void* xh, const void* xl, int dy_format, int x_format, float* dW,
                              int N, int Hd, int Wd, int Cout, int Hx, int Wx, int Cin, int num_slabs,
                              int ntaps, const int* h_taps, int sa, int sb, int HoP, int WoP, void* stream);
@@ -326,7 +326,7 @@ int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const void* xh, c
 int gp3d_split_bf16(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, void* stream);
 /* same, with the outputs zero-padded to C_out >= C channels (96-channel toRGB tensors -> 128 so that they fill whole 64-channel TMA blocks) */
 int gp3d_split_bf16_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, void* stream);
-/* Same with the element format of `hi` selectable: hi_format 0 = bf16 (lo optional), 1 = fp16 (lo must be NULL). */
+/* Same with the element format of `hi` selectable: hi_format 0 = bf16, 1 = fp16; lo (optional) has the same format. */
 int gp3d_split_pad(const void* x, int src_dtype, const float* s, void* hi, void* lo, int N, int HW, int C, int C_out, int hi_format, void* stream);
 
 #ifdef __cplusplus

@@ -284,8 +284,10 @@ def test_camera_render_gradients_reach_the_camera():
             ro, rd = tpr.sample_rays(c, fov=f, resolution=(h, w), patch_params=dict(scales=ps, offsets=po), device='cuda')
             rgb, depth, _, _ = rm.render_rays(pl, w1, b1, w2, b2, ro, rd, **kw)
         outs.append((rgb, depth) + torch.autograd.grad([rgb, depth], [c, f, pl], [g1, g2]))
-    for x, y in zip(*outs):
-        assert l2rel(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-4
+    # outputs 1e-4; gradients at the suite's gradient bar (1e-3 l2-rel): the two ray generators differ in the last bit, and the inverse-CDF fine
+    # samples over white-noise planes amplify that
+    for i, (x, y) in enumerate(zip(*outs)):
+        assert l2rel(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < (1e-4 if i < 2 else 1e-3), i
     assert outs[0][2].abs().max() > 0 and outs[0][3].abs().max() > 0
 
 
