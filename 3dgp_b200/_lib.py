@@ -53,6 +53,7 @@ PROTOTYPES = {
     'gp3d_upfirdn2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 4 + [c_int64] * 4 + [c_int] * 11 + [c_float]
                        + [c_int] * 2 + [c_int64] * 4 + [c_void_p]),
     'gp3d_filtered_lrelu_act': (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 4 + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p]),
+    'gp3d_filtered_lrelu': (c_int, [c_void_p] * 6 + [c_int] * 18 + [c_float] * 3 + [c_int] * 3 + [c_void_p]),
     'gp3d_raymarch_forward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 14 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
     'gp3d_raymarch_forward_cam': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [ctypes.POINTER(RaymarchCam)] + [c_void_p] * 12 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
     'gp3d_generate_rays': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 3),
@@ -106,6 +107,7 @@ class Gp3dError(RuntimeError):
     pass
 
 
+E_UNSUPPORTED = -2   # GP3D_E_UNSUPPORTED (include/gp3d_b200.h)
 launch_count = 0   # number of successful kernel-launching C-ABI calls in this process (bench.py: gpu_launches)
 
 

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 ]
 # Memory-bound streaming ops follow the reference's --use_fast_math build (bias_act.py:46, upfirdn2d.py:31);
 # the ray-march keeps IEEE expf/log1pf/div for fp32 parity with the CPU oracle.
-FAST_MATH = {'bias_act.cu', 'upfirdn2d.cu', 'misc.cu'}
+FAST_MATH = {'bias_act.cu', 'upfirdn2d.cu', 'misc.cu', 'filtered_lrelu.cu'}
 
 
 def _nvcc():

@@ -124,15 +124,73 @@ class _Upfirdn2dPlugin:
 class _FilteredLreluPlugin:
     """filtered_lrelu_plugin (reference filtered_lrelu.cpp:16-298).
 
-    `filtered_lrelu` always answers return_code -1 ("no specialised kernel", filtered_lrelu.cpp:118-125), which makes
-    the caller take the generic path upfirdn2d -> filtered_lrelu_act_ -> upfirdn2d exactly as the reference does for
-    configurations its CASE table does not cover (filtered_lrelu.py:223-229).  The op has no call site on the 3DGP
-    path; the generic path runs entirely on this library's kernels.
+    `filtered_lrelu` runs the fused sm_100a kernel (csrc/filtered_lrelu.cu) for separable filters and contiguous NCHW float32 / float16 tensors;
+    any other configuration answers return_code -1 ("no specialised kernel", filtered_lrelu.cpp:50-55), which makes the caller take the generic
+    path upfirdn2d -> filtered_lrelu_act_ -> upfirdn2d exactly as the reference does outside its own kernel table (filtered_lrelu.py:223-229).
     """
 
     @staticmethod
     def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns):
-        return torch.empty([0], device=x.device, dtype=x.dtype), torch.empty([0], device=x.device, dtype=torch.uint8), -1
+        L = _lib.lib()
+        none = lambda: (torch.empty([0], device=x.device, dtype=x.dtype), torch.empty([0], device=x.device, dtype=torch.uint8), -1)
+        if not x.is_cuda:
+            raise RuntimeError('x must reside on CUDA device')
+        if fu.dtype != torch.float32 or fd.dtype != torch.float32:
+            raise RuntimeError('fu and fd must be float32')
+        if x.dim() != 4:
+            raise RuntimeError('x must be rank 4')
+        if x.numel() == 0:
+            raise RuntimeError('x is empty')
+        if fu.dim() not in (1, 2) or fd.dim() not in (1, 2):
+            raise RuntimeError('fu and fd must be rank 1 or 2')
+        if up < 1 or down < 1:
+            raise RuntimeError('up and down must be at least 1')
+        if b is not None and (b.dim() != 1 or b.shape[0] != x.shape[1]):
+            raise RuntimeError('b must be a vector with the same number of channels as x')
+        if b is not None and b.dtype != x.dtype:
+            raise RuntimeError('x and b must have the same dtype')
+        sep = lambda f: f.reshape(1) if tuple(f.shape) == (1, 1) else f           # a 1 x 1 filter is its own separable form
+        fu, fd = sep(fu), sep(fd)
+        if fu.dim() != 1 or fd.dim() != 1 or x.dtype not in (torch.float32, torch.float16) or not x.is_contiguous():
+            return none()
+        N, C, xh, xw = x.shape
+        fut, fdt = fu.shape[0] - 1, fd.shape[0] - 1
+        cw, ch = xw * up + (px0 + px1) - fut, xh * up + (py0 + py1) - fut           # logical size of the up-sampled buffer (filtered_lrelu.cpp:66-70)
+        if not (cw > fdt and ch > fdt):
+            raise RuntimeError('upsampled buffer must be at least the size of downsampling filter')
+        yw, yh = (cw - fdt + (down - 1)) // down, (ch - fdt + (down - 1)) // down
+        if yw < 1 or yh < 1:
+            raise RuntimeError('output must be at least 1x1')
+        read = si is not None and si.numel() > 0
+        so = torch.empty([0], device=x.device, dtype=torch.uint8)
+        s = si
+        sw_active = 0
+        if writeSigns:
+            sw_active = yw * down - (down - 1) + fdt                                 # filtered_lrelu.cpp:86-93
+            sh = yh * down - (down - 1) + fdt
+            sw = (sw_active + 15) & ~15
+            s = so = torch.zeros([N, C, sh, sw >> 2], dtype=torch.uint8, device=x.device)
+        elif read:
+            if si.dtype != torch.uint8 or si.dim() != 4 or not si.is_contiguous():
+                raise RuntimeError('signs must be a contiguous rank-4 uint8 tensor')
+            if si.shape[0] != N or si.shape[1] != C:
+                raise RuntimeError('signs must have same batch & channels as x')
+            sw_active = si.shape[3] << 2
+        has_s = writeSigns or read
+        y = torch.empty([N, C, yh, yw], dtype=x.dtype, device=x.device)
+        fuc, fdc = fu.contiguous(), fd.contiguous()
+        bc = b.contiguous() if b is not None else None
+        with _dev(x):
+            rc = L.gp3d_filtered_lrelu(
+                x.data_ptr(), fuc.data_ptr(), fdc.data_ptr(), _lib.ptr(bc), s.data_ptr() if has_s else None, y.data_ptr(), _lib.dtype_code(x),
+                N, C, xh, xw, yh, yw, fuc.shape[0], fdc.shape[0], int(up), int(down), int(px0), int(py0),
+                s.shape[2] if has_s else 0, s.shape[3] if has_s else 0, int(sx), int(sy), (sw_active + 3) >> 2,
+                float(gain), float(slope), float(clamp) if clamp is not None and clamp != float('inf') else -1.0, 1 if flip_filters else 0,
+                1 if writeSigns else 0, 1 if (read and not writeSigns) else 0, _lib.stream_ptr())
+        if rc == _lib.E_UNSUPPORTED:
+            return none()
+        _lib.check(rc, 'filtered_lrelu')
+        return y, so, 0
 
     @staticmethod
     def filtered_lrelu_act_(x, si, sx, sy, gain, slope, clamp, writeSigns):

@@ -1,11 +1,12 @@
 """Filtered leaky ReLU: bias -> upsample FIR -> gain * lrelu -> clamp -> downsample FIR (StyleGAN3's anti-aliased
 non-linearity).  Python surface of the reference op (src/torch_utils/ops/filtered_lrelu.py:56-272).
 
-The reference ships this op but nothing on the 3DGP path calls it; it is kept API-complete.  The
-implementation is the reference's own *generic* route -- upfirdn2d, the in-place sign-coded activation kernel
-`filtered_lrelu_act_`, upfirdn2d -- with every stage on lib3dgp_b200's sm_100a kernels.  Only the 2-bit/element sign
-tensor is retained for backward (bit 0: negative, bit 1: clamped; filtered_lrelu.cu:1136-1145), and the backward is
-the same op with up/down swapped and the signs read back (filtered_lrelu.py:252-263).
+The reference ships this op but nothing on the 3DGP path calls it; BASELINE configs[3] names it.  Separable filters on
+contiguous float32 / float16 tensors run as ONE fused kernel (csrc/filtered_lrelu.cu: the up-sampled intermediate never leaves shared
+memory); everything else takes the reference's own *generic* route -- upfirdn2d, the in-place sign-coded activation kernel
+`filtered_lrelu_act_`, upfirdn2d -- with every stage on lib3dgp_b200's sm_100a kernels.  Only the 2-bit/element sign tensor is retained
+for backward (0 positive, 1 negative, 2 clamped; filtered_lrelu.cu:1136-1145), and the backward is the same op with up/down swapped
+and the signs read back (filtered_lrelu.py:252-263).
 """
 import numpy as np
 import torch
@@ -63,13 +64,18 @@ def _filtered_lrelu_cuda(up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, cl
             if si is None:
                 si = torch.empty([0], dtype=torch.uint8, device=x.device)
             write_signs = (si.numel() == 0) and (x.requires_grad or (b is not None and b.requires_grad))
-            y = x if b is None else x + b.reshape(1, -1, 1, 1)
-            y = upfirdn2d.upfirdn2d(x=y, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-            y = y.contiguous()
-            if y.data_ptr() == x.data_ptr():
-                y = y.clone()
-            so = _plugin.filtered_lrelu_act_(y, si, sx, sy, gain, slope, clamp, write_signs)   # in place on y
-            y = upfirdn2d.upfirdn2d(x=y, f=fd, down=down, flip_filter=flip_filter)
+            y = so = None
+            return_code = -1
+            if x.dtype in (torch.float16, torch.float32):
+                y, so, return_code = _plugin.filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filter, write_signs)
+            if return_code < 0:     # generic route (filtered_lrelu.py:223-229)
+                y = x if b is None else x + b.reshape(1, -1, 1, 1)
+                y = upfirdn2d.upfirdn2d(x=y, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+                y = y.contiguous()
+                if y.data_ptr() == x.data_ptr():
+                    y = y.clone()
+                so = _plugin.filtered_lrelu_act_(y, si, sx, sy, gain, slope, clamp, write_signs)   # in place on y
+                y = upfirdn2d.upfirdn2d(x=y, f=fd, down=down, flip_filter=flip_filter)
             ctx.save_for_backward(fu, fd, (si if si.numel() else so))
             ctx.x_shape, ctx.y_shape, ctx.s_ofs = x.shape, y.shape, (sx, sy)
             return y

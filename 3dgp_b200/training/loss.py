@@ -112,8 +112,10 @@ class StyleGAN2Loss:
         s = patch_params['scales'].mean(dim=1) ** scale_pow
         return s / (s.mean(dim=0) + 1e-8)
 
-    def accumulate_gradients(self, phase, real_data, gen_data, gain, cur_nimg, render_opts=None):
-        """real_data: {img [B,3,H,W], depth [B,1,H,W], c, embs, camera_angles}; gen_data: {z, c, camera_params}."""
+    def accumulate_gradients(self, phase, real_data, gen_data, gain, cur_nimg, render_opts=None, final_backward=None):
+        """real_data: {img [B,3,H,W], depth [B,1,H,W], c, embs, camera_angles}; gen_data: {z, c, camera_params}.
+        final_backward: optional callable invoked right before the LAST backward() of the phase (training/step.py arms the bucketed all-reduce there)."""
+        arm = final_backward if final_backward is not None else (lambda: None)
         assert phase in ['Gmain', 'Dmain', 'Dreg', 'Dall']
         if self.r1_gamma == 0:
             phase = {'Dreg': 'none', 'Dall': 'Dmain'}.get(phase, phase)
@@ -127,6 +129,7 @@ class StyleGAN2Loss:
             logits, _ = self.run_D(gen_out.img, gen_data.c, blur_sigma=blur_sigma, patch_params=pp, camera_angles=gen_out.camera_params.angles)
             loss = torch.nn.functional.softplus(-logits)
             reg = self.camera_regularisers(stats) if self.learn_camera else 0.0
+            arm()
             (loss.mean() + reg).mul(gain).backward()
             stats['Loss/G/loss'] = loss.detach().mean()
 
@@ -163,5 +166,6 @@ class StyleGAN2Loss:
                 r1_penalty = r1_grads.square().sum([1, 2, 3])
                 loss_Dr1 = r1_penalty * (self.r1_gamma / 2)
                 stats['Loss/D/r1_penalty'] = r1_penalty.detach().mean()
+            arm()
             (loss_Dreal + loss_Dr1 + loss_Dkd).mean().mul(gain).backward()
         return stats

@@ -34,6 +34,66 @@ def allreduce_gradients(params, world_size, group=None):
     return flat.numel()
 
 
+class GradBuckets:
+    """Bucketed all-reduce of a flat gradient buffer, overlapped with the backward pass that fills it (training_loop.py:335-344 issues ONE blocking
+    all-reduce after backward; here the transfer hides behind the remaining backward kernels).
+
+    The buffer is cut into contiguous buckets of whole parameters, built from its END: autograd reaches the last layers first, so bucket 0 (the
+    tail of the buffer -- for G the 512^2 / 256^2 blocks) completes first.  `arm()` is called right before the phase's FINAL backward; every
+    parameter's post-accumulate hook then reports `ready(i)`, and a bucket whose parameters are all ready is all-reduced asynchronously on the
+    process group's own stream (NCCL: ordered after the work already enqueued on the compute stream).  Buckets are launched strictly in index
+    order, so every rank issues the same sequence of collectives whatever its hook order.  `finish()` reduces what never completed (parameters
+    without a gradient in this phase) and waits for all transfers."""
+
+    def __init__(self, flat, offsets, numels, bucket_elems=16 << 20):
+        self.flat = flat
+        self.bounds, self.members = [], []          # bucket -> (start, end), [parameter indices]
+        end, cur = flat.numel(), []
+        for i in range(len(offsets) - 1, -1, -1):
+            cur.append(i)
+            if end - offsets[i] >= bucket_elems or i == 0:
+                self.bounds.append((offsets[i], end)); self.members.append(cur)
+                end, cur = offsets[i], []
+        self.bucket_of = {i: b for b, m in enumerate(self.members) for i in m}
+        self.armed = False
+        self.launched_async = 0                     # buckets whose transfer started during the backward (diagnostics / tests)
+
+    def arm(self, world_size, group=None, expected=None):
+        """expected: indices of the parameters this backward will produce gradients for (None: all).  A phase's graph is static, so the caller
+        passes the set that `fired` in the previous final backward of the same phase; a bucket then does not wait for parameters that never fire."""
+        self.armed, self.world, self.group = True, world_size, group
+        self.pending = [set(m) if expected is None else set(m) & set(expected) for m in self.members]
+        self.next, self.handles, self.launched_async, self.fired = 0, [], 0, set()
+        self._launch_ready()
+
+    def _launch_ready(self):
+        while self.next < len(self.bounds) and not self.pending[self.next]:
+            a, b = self.bounds[self.next]
+            self.handles.append(dist.all_reduce(self.flat[a:b], group=self.group, async_op=True))
+            self.next += 1
+            self.launched_async += 1
+
+    def ready(self, i):
+        if self.armed:
+            self.fired.add(i)
+            b = self.bucket_of[i]
+            if b < self.next:       # its bucket is already on the wire: the sum would miss this rank's contribution
+                raise RuntimeError('GradBuckets: a parameter outside the expected set produced a gradient after its bucket was all-reduced '
+                                   '(the phase graph changed between iterations); set Trainer.overlap_allreduce = False')
+            self.pending[b].discard(i)
+            self._launch_ready()
+
+    def finish(self):
+        """After the backward: reduce the remaining buckets, wait for every transfer (the compute stream then sees the reduced buffer)."""
+        while self.next < len(self.bounds):
+            a, b = self.bounds[self.next]
+            self.handles.append(dist.all_reduce(self.flat[a:b], group=self.group, async_op=True))
+            self.next += 1
+        for h in self.handles:
+            h.wait()
+        self.handles, self.armed = [], False
+
+
 class FlatAdam:
     """torch.optim.Adam over ONE flat float32 storage per module (training_loop.py:190-205, 335-346, 357-364).
 
@@ -84,7 +144,14 @@ class FlatAdam:
         self.steps = [0] * len(self.params)
         self._param_ids = {id(p) for p in self.params}
         self.active = set()
-        self._hooks = [p.register_post_accumulate_grad_hook(lambda p_, i=i: self.active.add(i)) for i, p in enumerate(self.params) if p.requires_grad]
+        self.buckets = GradBuckets(self.flat_g, self.offsets, [p.numel() for p in self.params])
+
+        def hook(i):
+            def fn(_p):
+                self.active.add(i)
+                self.buckets.ready(i)
+            return fn
+        self._hooks = [p.register_post_accumulate_grad_hook(hook(i)) for i, p in enumerate(self.params) if p.requires_grad]
 
     def zero_grad(self):
         """Start of a phase: clear the flat gradient and (re-)attach every parameter's .grad view."""
@@ -94,8 +161,10 @@ class FlatAdam:
             p.grad = g
 
     def step(self, world_size=1, group=None, ema_beta=None):
-        """All-reduce the flat gradient, then the fused epilogue + Adam (+ EMA) kernel."""
-        if world_size > 1:
+        """All-reduce the flat gradient (bucket transfers already in flight when the phase armed `buckets`), then the fused epilogue + Adam (+ EMA) kernel."""
+        if self.buckets.armed:
+            self.buckets.finish()
+        elif world_size > 1:
             dist.all_reduce(self.flat_g, group=group)
         b1, b2 = self.betas
         for i in self.active:
@@ -168,6 +237,8 @@ class Trainer:
         self.D_reg_interval = D_reg_interval
         self.ema_kimg, self.ema_rampup, self.batch_size = ema_kimg, ema_rampup, batch_size
         self.micro_batch = micro_batch
+        self.overlap_allreduce = True
+        self._fired = {}         # phase -> parameters that produced gradients in its last final backward (GradBuckets.arm `expected`)
         self.cur_nimg = 0
         self.it = 0
 
@@ -178,11 +249,18 @@ class Trainer:
             opt.zero_grad(set_to_none=True)
         module.requires_grad_(True)
         stats = {}
-        for r_mb, g_mb in self._micro_batches(real, gen):     # gradient accumulation, training_loop.py:329-330
-            stats = self.loss.accumulate_gradients(phase=name, real_data=r_mb, gen_data=g_mb, gain=gain, cur_nimg=self.cur_nimg, render_opts=render_opts)
+        mbs = list(self._micro_batches(real, gen))
+        for j, (r_mb, g_mb) in enumerate(mbs):                 # gradient accumulation, training_loop.py:329-330
+            # the last backward of the phase streams its gradient buckets into the all-reduce while it is still running
+            arm = (lambda: opt.buckets.arm(self.world_size, expected=self._fired.get(name))) if (self.flat and self.world_size > 1 and self.overlap_allreduce and j == len(mbs) - 1) else None
+            stats = self.loss.accumulate_gradients(phase=name, real_data=r_mb, gen_data=g_mb, gain=gain, cur_nimg=self.cur_nimg, render_opts=render_opts,
+                                                   final_backward=arm)
         module.requires_grad_(False)
         if self.flat:
+            armed = opt.buckets.armed
             opt.step(self.world_size, ema_beta=ema_beta)
+            if armed:
+                self._fired[name] = set(opt.buckets.fired)
         else:
             allreduce_gradients([p for p in module.parameters() if p.numel() > 0], self.world_size)
             opt.step()

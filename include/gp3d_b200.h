@@ -82,6 +82,22 @@ int gp3d_filtered_lrelu_act(void* x, uint8_t* si, int dtype, int N, int C, int H
                             int write_signs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * filtered_lrelu -- replaces filtered_lrelu_plugin.filtered_lrelu (filtered_lrelu.cpp:16-209, kernels filtered_lrelu.cu:139-1099):
+ * bias -> zero-insert up-sample + pad + FIR(fu) * up^2 -> gain * lrelu -> clamp -> FIR(fd) + decimate in ONE kernel; the up-sampled
+ * intermediate exists only in shared memory.  SEPARABLE filters (fu, fd given as 1-D taps, applied along both axes); any other
+ * configuration returns GP3D_E_UNSUPPORTED and the caller takes the generic route (the reference's return code -1, filtered_lrelu.cpp:50-55).
+ *   x [N,C,xH,xW], y [N,C,yH,yW]: NCHW contiguous, dtype f32 / f16; b: [C] in x's dtype or NULL; px0 / py0: leading padding w.r.t. the up-sampled
+ *   signal (negative = crop); yW = (xW*up + px0 + px1 - (fu_taps-1) - (fd_taps-1) + down-1) / down (the caller computes it, filtered_lrelu.cpp:72-79).
+ *   s [N,C,sH,sW4] uint8: four 2-bit codes per byte (0 positive, 1 negative, 2 clamped) of intermediate element (u, v) at sign coordinate
+ *   (u + sx, v + sy); write_signs: produced (bytes up to sw_limit per row); read_signs: consumed instead of evaluating the activation
+ *   (x gain, x gain*slope, x 0) -- the backward pass (filtered_lrelu.py:252-263).  flip_filter: 0 convolution, 1 correlation.
+ */
+int gp3d_filtered_lrelu(const void* x, const float* fu, const float* fd, const void* b, uint8_t* s, void* y, int dtype,
+                        int N, int C, int xH, int xW, int yH, int yW, int fu_taps, int fd_taps, int up, int down, int px0, int py0,
+                        int sH, int sW4, int sx, int sy, int sw_limit, float gain, float slope, float clamp, int flip_filter,
+                        int write_signs, int read_signs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused tri-plane ray-march (forward).  Replaces the ~25 torch ops of ImportanceRenderer.forward
  * (reference src/training/tri_plane_renderer.py:126-170) together with simple_tri_plane_renderer
  * (:560-588, ATen grid_sampler_2d), TriPlaneMLP.forward (networks_epigraf.py:46-68),

@@ -99,6 +99,12 @@ def filtered_lrelu_cases():
         ('up2_down2', dict(shape=(2, 3, 8, 8), up=2, down=2, fu='k12', fd='k12', padding=[11, 10, 11, 10], gain=np.sqrt(2), slope=0.2, clamp=None)),
         ('up2_down1_clamp', dict(shape=(1, 4, 6, 10), up=2, down=1, fu='2d4', fd=None, padding=[2, 1, 2, 1], gain=1.3, slope=0.1, clamp=0.4)),
         ('up1_down2', dict(shape=(1, 2, 12, 12), up=1, down=2, fu=None, fd='2d4', padding=[1, 1, 1, 1], gain=np.sqrt(2), slope=0.2, clamp=None)),
+        # separable filters at sizes that span several 32 x 32 output tiles of the fused kernel (ragged edges, clamp codes, up != down)
+        ('sep_40x37_clamp', dict(shape=(2, 5, 40, 37), up=2, down=2, fu='k12', fd='k12', padding=[11, 10, 11, 10], gain=np.sqrt(2), slope=0.2, clamp=0.5)),
+        ('sep_up4_down2', dict(shape=(1, 3, 20, 24), up=4, down=2, fu='k12', fd='k6', padding=[9, 8, 9, 8], gain=1.1, slope=0.3, clamp=None)),
+        ('sep_up4_down2_k24', dict(shape=(1, 2, 24, 19), up=4, down=2, fu='k24', fd='k12', padding=[21, 20, 21, 20], gain=np.sqrt(2), slope=0.2, clamp=None)),
+        ('sep_up2_down1', dict(shape=(1, 3, 30, 41), up=2, down=1, fu='k12', fd=None, padding=[6, 5, 6, 5], gain=np.sqrt(2), slope=0.2, clamp=1.0)),
+        ('sep_up1_down1_crop', dict(shape=(1, 2, 70, 33), up=1, down=1, fu='k6', fd='k6', padding=[-1, 2, 3, -2], gain=np.sqrt(2), slope=0.2, clamp=None)),
     ]
 
 
@@ -116,6 +122,12 @@ def filtered_lrelu_inputs(name, kw):
             t = np.arange(12, dtype=np.float64) - 5.5
             f = np.sinc(t / 2.0) * np.kaiser(12, 6.0)
             return (f / f.sum()).astype(np.float32)
+        if k == 'k24':
+            t = np.arange(24, dtype=np.float64) - 11.5
+            f = np.sinc(t / 4.0) * np.kaiser(24, 6.0)
+            return (f / f.sum()).astype(np.float32)
+        if k == 'k6':    # asymmetric 6-tap separable filter (convolution vs correlation matters)
+            return (np.array([1, 4, 7, 5, 2, 1], np.float64) / 20.0).astype(np.float32)
         raise KeyError(k)
     return x, mk(kw['fu']), mk(kw['fd']), b
 

@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     list(net.parameters())[0].grad[0, 0] = float('nan') if rank == 0 else 1.0
     list(net.parameters())[1].grad[0] = float('inf') if rank == 1 else 1.0
     n = stepm.allreduce_gradients(list(net.parameters()), world)
-    out = [p.grad.clone() for p in net.parameters()]
+    out = [p.grad.clone().numpy() for p in net.parameters()]      # by value: a tensor would travel as a shared-memory handle that dies with this process
     q.put((rank, n, out))
     dist.destroy_process_group()
 
@@ -41,6 +41,7 @@ def test_flattened_gradient_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     (_, n0, g0), (_, n1, g1) = res
+    g0, g1 = [torch.from_numpy(a) for a in g0], [torch.from_numpy(a) for a in g1]
     assert n0 == n1 == 5 * 7 + 7 + 7 * 3 + 3
     for a, b in zip(g0, g1):
         assert torch.equal(a, b)                     # every rank ends with the same averaged gradient
@@ -49,3 +50,63 @@ def test_flattened_gradient_allreduce_gloo_world2():
     assert g0[0][0, 0].item() == 0.0
     assert g0[1][0].item() == 1e5
     assert torch.allclose(g0[2], torch.full_like(g0[2], 4.5))
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    params = list(net.parameters())
+    params[-1].requires_grad_(False)                 # a parameter that never receives a gradient: its bucket can only be reduced by finish()
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off); off += -(-p.numel() // 8) * 8
+    flat = torch.zeros(off)
+    for p, o in zip(params, offsets):
+        p.grad = flat[o:o + p.numel()].view(p.shape)
+    bk = stepm.GradBuckets(flat, offsets, [p.numel() for p in params], bucket_elems=64)
+    for i, p in enumerate(params):
+        if p.requires_grad:
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: bk.ready(i))
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(10 + rank))
+    net(x).square().sum().backward()                 # not armed: a non-final backward of the phase accumulates without any transfer
+    assert bk.launched_async == 0
+    bk.arm(world)                                    # first armed pass: nothing known about the graph, the frozen tail parameter blocks bucket 0
+    net(x).square().sum().backward()
+    first = bk.launched_async
+    bk.finish()
+    fired = set(bk.fired)
+    flat.zero_()
+    net(x).square().sum().backward()                 # this rank's own gradient, for the check
+    local = flat.clone()
+    flat.zero_()
+    bk.arm(world, expected=fired)                    # steady state: buckets stream out as they complete
+    net(x).square().sum().backward()
+    launched_during_backward = bk.launched_async
+    bk.finish()
+    q.put((rank, len(bk.bounds), (first, launched_during_backward), local.numpy(), flat.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_overlaps_and_matches_one_shot_gloo_world2():
+    """GradBuckets (training/step.py): buckets cover the flat buffer exactly once, launch in index order while the final backward is still producing
+    gradients, and the result equals ONE all-reduce of the whole buffer (training_loop.py:335-344)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, nb0, l0, loc0, red0), (_, nb1, l1, loc1, red1) = res
+    loc0, red0, loc1, red1 = (torch.from_numpy(a) for a in (loc0, red0, loc1, red1))
+    assert nb0 == nb1 and nb0 >= 3
+    assert l0 == l1 and l0[0] == 0 and l0[1] == nb0   # pass 1 learns which parameters fire; pass 2 sends every bucket while the backward runs
+    assert torch.equal(red0, red1)
+    assert torch.allclose(red0, loc0 + loc1, rtol=0, atol=0)

@@ -144,6 +144,38 @@ def test_filtered_lrelu_vs_golden(golden, name, kw):
     assert maxrel(gb.cpu().numpy(), g[name + '/db']) < 5e-5
 
 
+def test_filtered_lrelu_separable_cases_run_the_fused_kernel(golden):
+    """Separable filters must take the single-kernel route (return code 0), not the generic upfirdn2d -> act -> upfirdn2d composition; the fused kernel's
+    sign codes equal the generic route's on the region the outputs use, forward and backward agree with it, and fp16 tensors are covered."""
+    _, up, fl = _ops()
+    fl._init()
+    plugin = fl._plugin
+    for name, kw in cases.filtered_lrelu_cases():
+        x, fu, fd, b = cases.filtered_lrelu_inputs(name, kw)
+        if fu.ndim != 1 and fu.shape != (1, 1) or fd.ndim != 1 and fd.shape != (1, 1):
+            continue
+        px0, px1, py0, py1 = kw['padding']
+        for dt, tol in ((torch.float32, 1e-5), (torch.float16, 4e-3)):
+            xt = cu(x).to(dt); bt = cu(b).to(dt)
+            y, so, rc = plugin.filtered_lrelu(xt, cu(fu), cu(fd), bt, torch.empty(0, dtype=torch.uint8, device='cuda'), kw['up'], kw['down'], px0, px1, py0, py1,
+                                              0, 0, float(kw['gain']), float(kw['slope']), float(kw['clamp']) if kw['clamp'] is not None else float('inf'), False, True)
+            assert rc == 0, name
+            assert maxrel(y.float().cpu().numpy(), golden('filtered_lrelu')[name + '/y']) < tol, (name, dt)
+            if dt == torch.float32:     # sign codes vs the generic route's
+                t = xt + bt.reshape(1, -1, 1, 1)
+                t = up.upfirdn2d(t, cu(fu), up=kw['up'], padding=kw['padding'], gain=kw['up'] ** 2).contiguous()
+                so_g = plugin.filtered_lrelu_act_(t, torch.empty(0, dtype=torch.uint8, device='cuda'), 0, 0, float(kw['gain']), float(kw['slope']),
+                                                  float(kw['clamp']) if kw['clamp'] is not None else float('inf'), True)
+                sh, sw4 = so.shape[2], so.shape[3]
+                a, g_ = so.cpu().numpy(), so_g.cpu().numpy()[:, :, :sh, :sw4]
+                # compare decoded codes over the active width (the last byte of a row may hold codes of columns the outputs never use)
+                fdt = fd.shape[-1] - 1
+                swa = y.shape[3] * kw['down'] - (kw['down'] - 1) + fdt
+                dec = lambda m: np.stack([(m >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(m.shape[0], m.shape[1], m.shape[2], -1)[..., :swa]
+                mism = (dec(a) != dec(g_)).mean()
+                assert mism < 1e-3, (name, mism)      # codes differ only where the two summation orders straddle 0 / the clamp
+
+
 @pytest.mark.parametrize('kw', [dict(up=1, down=1, padding=[1, 1, 1, 1], gain=4), dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4),
                                 dict(up=1, down=2, padding=[1, 1, 1, 1], gain=1), dict(up=1, down=1, padding=[2, 2, 2, 2], gain=1),
                                 dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4, flip_filter=True)])
