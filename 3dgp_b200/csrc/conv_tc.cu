@@ -49,7 +49,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                       float* __restrict__ Y, ConvGeom g, int accumulate, int num_tiles, ConvEpi ep) {
     // Persistent: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers (2 x 128 columns) let the epilogue of
     // tile i overlap the TMA / MMA main loop of tile i+1; the smem ring and its phases run continuously across tiles.
-    constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
+    constexpr int CSTAGES = (TERMS == 3) ? (BN == 256 ? 2 : 3) : (TERMS == 2 && BN == 256) ? 3 : 4;
     constexpr uint32_t kOperand = (CBM + BN) * CBK * 2;
     constexpr uint32_t kStage = kOperand + (TERMS == 3 ? kOperand : TERMS == 2 ? CBM * CBK * 2 : 0);     // [A_hi | B_hi] [A_lo] [B_lo]
     constexpr uint32_t kAccStride = (BN <= 128) ? 128 : 256;      // TMEM columns per accumulator buffer (two buffers: 256 or all 512 columns)
@@ -195,7 +195,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 template <int BN, int TERMS>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXl, const CUtensorMap& tmWl, float* y, const ConvGeom& g,
                 int accumulate, cudaStream_t s, const ConvEpi& ep) {
-    constexpr int CSTAGES = (TERMS == 3) ? 3 : 4;
+    constexpr int CSTAGES = (TERMS == 3) ? (BN == 256 ? 2 : 3) : (TERMS == 2 && BN == 256) ? 3 : 4;
     constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1) + (TERMS == 2 ? CBM * CBK * 2 : 0);
     const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256;
     auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
@@ -212,6 +212,10 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
 }  // namespace tc
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// 256-wide tiles for the three-term form (tuning switch: gp3d_conv_set_wide3; on by default when measured faster)
+static int g_conv_wide3 = 1;
+extern "C" int gp3d_conv_set_wide3(int on) { const int old = g_conv_wide3; g_conv_wide3 = on ? 1 : 0; return old; }
 
 // General tap convolution.  taps: ntaps x (dy, dx, slab).  num_slabs = weight slabs per output channel.
 static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
@@ -248,9 +252,10 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     g.TW = pow2ceil(WoP) < 16 ? pow2ceil(WoP) : 16;
     g.TH = pow2ceil(HoP) < (128 / g.TW) ? pow2ceil(HoP) : (128 / g.TW);
     g.TN = 128 / (g.TW * g.TH);
-    // single-term launches are bound by the L2 -> SM operand stream (96 B/clk/SM at 128x128 tiles): 256-wide tiles reuse each
-    // activation tile for twice the MMAs.  The three-term form is MMA-bound already and keeps 128 (its stage would not fit twice).
-    const int BN = (!xl && Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : Cout;
+    // launches are bound by the L2 -> SM operand stream (single-term: 96 B/clk/SM at 128x128 tiles; three-term: ~48 B/clk/SM): 256-wide tiles reuse
+    // each activation tile for twice the MMAs.  The three-term form then runs a two-stage ring of 96 KB stages (24 MMAs of 128x256x16 each).
+    const bool wide3 = xl && wl && Cout % 256 == 0 && g_conv_wide3;
+    const int BN = ((!xl || wide3) && Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : Cout;
     g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN; g.tiles_co = Cout / BN;
     GP3D_CHECK_ARG((int64_t)g.tiles_x * g.tiles_y * g.tiles_n * g.tiles_co < 2147483647LL, "%s: grid too large", who);
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
@@ -293,7 +298,8 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
            : (BN == 96)  ? tc::launch_conv<96, 2>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
                          : tc::launch_conv<64, 2>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
     } else {
-        rc = (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+        rc = (BN == 256) ? tc::launch_conv<256, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
+           : (BN == 128) ? tc::launch_conv<128, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
            : (BN == 96)  ? tc::launch_conv<96, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep)
                          : tc::launch_conv<64, 3>(tmX, tmW, tmXl, tmWl, y, g, accumulate, s, ep);
     }

@@ -190,26 +190,35 @@ __global__ void __launch_bounds__(256) filtered_lrelu_fast_kernel(FlrParams p) {
     }
     __syncthreads();
 
-    // B: up-sample along x.  Work item = (input row r, phase lane rho): columns q = qs + m * UP share one coefficient set and slide one input per output.
-    for (int wi = tid; wi < IN * UP; wi += 256) {
-        const int r = wi % IN, rho = wi / IN;                       // lanes <-> consecutive rows (odd pitches: conflict-free)
-        float cf[NT], w[NT];
-        const int ilo0 = cdiv(u0 + rho - p.px0, UP);
-        const int k0 = ilo0 * UP + p.px0 - (u0 + rho);             // tap of the first contributing sample, in [0, UP)
+    // B: up-sample along x.  Work item = (input row r, phase lane rho, column segment): columns q = rho + m * UP share one coefficient set and slide
+    // one input per output.
+    {
+        constexpr int NCOL = (TIP - 1 + UP - 1) / UP;               // outputs per (row, phase)
+        constexpr int BSEG = 4;
+        constexpr int MPER = (NCOL + BSEG - 1) / BSEG;
+        for (int wi = tid; wi < IN * UP * BSEG; wi += 256) {
+            const int r = wi % IN, rs = wi / IN;                    // lanes <-> consecutive rows (odd pitches: conflict-free)
+            const int rho = rs % UP, m0 = (rs / UP) * MPER;
+            float cf[NT], w[NT];
+            const int ilo0 = cdiv(u0 + rho - p.px0, UP);
+            const int k0 = ilo0 * UP + p.px0 - (u0 + rho);         // tap of the first contributing sample, in [0, UP)
 #pragma unroll
-        for (int t = 0; t < NT; t++) cf[t] = sfu[k0 + t * UP];
-        const float* src = sIn + r * INP + (ilo0 - ix0);
+            for (int t = 0; t < NT; t++) cf[t] = sfu[k0 + t * UP];
+            const float* src = sIn + r * INP + (ilo0 - ix0) + m0;
 #pragma unroll
-        for (int t = 0; t < NT - 1; t++) w[t + 1] = src[t];
-        float* dst = sB + r * TIP + rho;
-        for (int m = 0; rho + m * UP < TIP - 1; m++) {
+            for (int t = 0; t < NT - 1; t++) w[t + 1] = src[t];
+            float* dst = sB + r * TIP + rho + m0 * UP;
+#pragma unroll 4
+            for (int m = 0; m < MPER; m++) {
+                if (rho + (m0 + m) * UP >= TIP - 1) break;
 #pragma unroll
-            for (int t = 0; t < NT - 1; t++) w[t] = w[t + 1];
-            w[NT - 1] = src[m + NT - 1];
-            float acc = 0.f;
+                for (int t = 0; t < NT - 1; t++) w[t] = w[t + 1];
+                w[NT - 1] = src[m + NT - 1];
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int t = 0; t < NT; t++) acc = fmaf(w[t], cf[t], acc);
-            dst[m * UP] = acc;
+                for (int t = 0; t < NT; t += 2) { a0 = fmaf(w[t], cf[t], a0); if (t + 1 < NT) a1 = fmaf(w[t + 1], cf[t + 1], a1); }
+                dst[m * UP] = a0 + a1;
+            }
         }
     }
     __syncthreads();
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(256) filtered_lrelu_fast_kernel(FlrParams p) {
     // sign byte combine their 2-bit codes with shuffles.
     {
         constexpr int QW = (TIP - 1 + 31) / 32 * 32;                // columns rounded to whole warps
-        constexpr int SEG = 2;                                      // row segments per (column, phase)
+        constexpr int SEG = 4;                                      // row segments per (column, phase)
         constexpr int ROWS_PER = (TI + UP * SEG - 1) / (UP * SEG);  // outputs per work item
         const float upgain = (float)(UP * UP);
         uint8_t* sp = p.s ? p.s + (int64_t)nc * p.sH * p.sW4 : nullptr;
@@ -244,9 +253,10 @@ __global__ void __launch_bounds__(256) filtered_lrelu_fast_kernel(FlrParams p) {
 #pragma unroll
                 for (int t = 0; t < NT - 1; t++) w[t] = w[t + 1];
                 w[NT - 1] = src[(m + NT - 1) * TIP];
-                float val = 0.f;
+                float val = 0.f, val1 = 0.f;
 #pragma unroll
-                for (int t = 0; t < NT; t++) val = fmaf(w[t], cf[t], val);
+                for (int t = 0; t < NT; t += 2) { val = fmaf(w[t], cf[t], val); if (t + 1 < NT) val1 = fmaf(w[t + 1], cf[t + 1], val1); }
+                val += val1;
                 const int v = v0 + r, sv = v + p.sy;
                 const bool srow = sp && sv >= 0 && sv < p.sH;
                 uint32_t code = 0;
@@ -275,51 +285,52 @@ __global__ void __launch_bounds__(256) filtered_lrelu_fast_kernel(FlrParams p) {
     }
     __syncthreads();
 
-    // D: down-sample along x.  Work item = (row r, output segment of 8): window of FD values sliding by DOWN.
-    for (int wi = tid; wi < TI * (TO / 8); wi += 256) {
+    // D: down-sample along x.  Work item = (row r, output segment of 4): window of FD values sliding by DOWN.
+    constexpr int OS = 4;
+    for (int wi = tid; wi < TI * (TO / OS); wi += 256) {
         const int r = wi % TI, seg = wi / TI;                       // lanes <-> consecutive rows (odd pitch)
         float cf[FD], w[FD];
 #pragma unroll
         for (int k = 0; k < FD; k++) cf[k] = sfd[k];
-        const float* src = sC + r * TIP + seg * 8 * DOWN;
+        const float* src = sC + r * TIP + seg * OS * DOWN;
 #pragma unroll
         for (int k = 0; k < FD - DOWN; k++) w[k + DOWN] = src[k];
 #pragma unroll
-        for (int o = 0; o < 8; o++) {
+        for (int o = 0; o < OS; o++) {
 #pragma unroll
             for (int k = 0; k < FD - DOWN; k++) w[k] = w[k + DOWN];
 #pragma unroll
             for (int k = 0; k < DOWN; k++) w[FD - DOWN + k] = src[o * DOWN + FD - DOWN + k];
-            float acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < FD; k++) acc = fmaf(w[k], cf[k], acc);
-            sD[r * DP + seg * 8 + o] = acc;
+            for (int k = 0; k < FD; k += 2) { a0 = fmaf(w[k], cf[k], a0); if (k + 1 < FD) a1 = fmaf(w[k + 1], cf[k + 1], a1); }
+            sD[r * DP + seg * OS + o] = a0 + a1;
         }
     }
     __syncthreads();
 
-    // E: down-sample along y, store.  Work item = (column q, row segment of 8).
+    // E: down-sample along y, store.  Work item = (column q, row segment of 4).
     T* yp = reinterpret_cast<T*>(p.y) + (int64_t)nc * p.yH * p.yW;
-    for (int wi = tid; wi < TO * (TO / 8); wi += 256) {
+    for (int wi = tid; wi < TO * (TO / OS); wi += 256) {
         const int q = wi % TO, seg = wi / TO;
         float cf[FD], w[FD];
 #pragma unroll
         for (int k = 0; k < FD; k++) cf[k] = sfd[k];
-        const float* src = sD + (seg * 8 * DOWN) * DP + q;
+        const float* src = sD + (seg * OS * DOWN) * DP + q;
 #pragma unroll
         for (int k = 0; k < FD - DOWN; k++) w[k + DOWN] = src[k * DP];
         const int ox = ox0 + q;
 #pragma unroll
-        for (int o = 0; o < 8; o++) {
+        for (int o = 0; o < OS; o++) {
 #pragma unroll
             for (int k = 0; k < FD - DOWN; k++) w[k] = w[k + DOWN];
 #pragma unroll
             for (int k = 0; k < DOWN; k++) w[FD - DOWN + k] = src[(o * DOWN + FD - DOWN + k) * DP];
-            float acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < FD; k++) acc = fmaf(w[k], cf[k], acc);
-            const int oy = oy0 + seg * 8 + o;
-            if (oy < p.yH && ox < p.yW) io_traits<T>::st(yp + (int64_t)oy * p.yW + ox, acc);
+            for (int k = 0; k < FD; k += 2) { a0 = fmaf(w[k], cf[k], a0); if (k + 1 < FD) a1 = fmaf(w[k + 1], cf[k + 1], a1); }
+            const int oy = oy0 + seg * OS + o;
+            if (oy < p.yH && ox < p.yW) io_traits<T>::st(yp + (int64_t)oy * p.yW + ox, a0 + a1);
         }
     }
 }

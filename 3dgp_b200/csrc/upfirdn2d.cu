@@ -25,6 +25,9 @@ int gp3d_fir4_launch(const float* x, const float* f, int flip, float gain, int N
 int gp3d_fir4_up2_launch(const float* x, const float* f, int flip, float gain, int N, int H, int W, int C, int padx0, int pady0, int outH, int outW,
                          float* y, cudaStream_t st);   // fir_tma.cu
 
+int gp3d_fir4_nchw_launch(const void* x, const float* f, void* y, int is_half, int mode, int planes, int H, int W, int outH, int outW, int flip, float gain,
+                          cudaStream_t st);            // fir_nchw_tma.cu
+
 namespace {
 
 struct UpfirdnParams {
@@ -454,6 +457,14 @@ int launch_upfirdn(UpfirdnParams& p, cudaStream_t s) {
         int64_t total = (int64_t)p.N * p.outH * p.outW * (p.C / VEC);
         upfirdn2d_cminor_kernel<T><<<gp3d_grid_for(total, 256, 8), 256, 0, s>>>(p);
         return 0;
+    }
+    if (wminor && !std::is_same<T, __nv_bfloat16>::value && p.fw == 4 && p.fh == 4 && p.upx == p.upy && p.downx == p.downy &&
+        ((p.upx == 2 && p.downx == 1 && p.padx0 == 2 && p.pady0 == 2) || (p.upx == 1 && p.downx == 2 && p.padx0 == 1 && p.pady0 == 1))) {
+        // dense NCHW planes of upsample2d / downsample2d: TMA-staged window, register-blocked taps (fir_nchw_tma.cu)
+        const bool dense = p.xsH == p.inW && p.xsC == (int64_t)p.inH * p.inW && p.xsN == (int64_t)p.C * p.inH * p.inW &&
+                           p.ysW == 1 && p.ysH == p.outW && p.ysC == (int64_t)p.outH * p.outW && p.ysN == (int64_t)p.C * p.outH * p.outW;
+        if (dense && gp3d_fir4_nchw_launch(p.x, p.f, p.y, sizeof(T) == 2, p.upx == 2 ? 0 : 1, p.N * p.C, p.inH, p.inW, p.outH, p.outW, p.flip, p.gain, s) == 0)
+            return 0;
     }
     if (wminor) {
         const int TIW = ((kTOW - 1) * p.downx + p.fw - 1) / p.upx + 2, TIH = ((kTOH - 1) * p.downy + p.fh - 1) / p.upy + 2;

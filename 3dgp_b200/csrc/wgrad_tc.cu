@@ -13,7 +13,7 @@
 
 namespace tc {
 
-constexpr int WBM = 128, WBN = 128, WBK = 64;
+constexpr int WBM = 128, WBK = 64;          // the Cin tile (WBN) is a template parameter: 128, or 256 when Cin % 256 == 0
 constexpr int kWgradThreads = 256;
 
 struct WgradGeom {
@@ -46,15 +46,18 @@ __device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int TERMS>
+template <int TERMS, int WBN>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmXh,
              const __grid_constant__ CUtensorMap tmDl, const __grid_constant__ CUtensorMap tmXl,
              float* __restrict__ dW, WgradGeom g) {
-    constexpr int STAGES = (TERMS == 3) ? 3 : 4;
+    // 256-wide Cin tiles halve the dy operand traffic per MMA (the kernel is bound by the L2 -> SM operand stream, like conv_tc.cu): the three-term
+    // form then runs a two-stage ring of 96 KB stages.
+    constexpr int STAGES = (TERMS == 3) ? (WBN == 256 ? 2 : 3) : 4;
     constexpr uint32_t kBlock = WBK * 128;                 // one 64-channel column block of 64 pixel rows: 8 KB
-    constexpr uint32_t kOperand = 2 * kBlock;              // 128 channels
-    constexpr uint32_t kPart = 2 * kOperand;               // dy tile + x tile
+    constexpr uint32_t kOperand = 2 * kBlock;              // dy tile: 128 channels
+    constexpr uint32_t kOperandB = (WBN / 64) * kBlock;    // x tile: WBN channels
+    constexpr uint32_t kPart = kOperand + kOperandB;       // dy tile + x tile
     constexpr uint32_t kStage = kPart * (TERMS == 3 ? 2 : 1);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -78,7 +81,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    if (warp == 2) tmem_alloc(tmem_slot, WBN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -100,13 +103,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
                 mbar_expect_tx(&full_bar[st], kStage);
                 tma_load_4d(sA, &tmDh, &full_bar[st], tco * WBM, acx, acy, n0);
                 tma_load_4d(sA + kBlock, &tmDh, &full_bar[st], tco * WBM + 64, acx, acy, n0);
-                tma_load_4d(sB, &tmXh, &full_bar[st], tci * WBN, bcx, bcy, n0);
-                tma_load_4d(sB + kBlock, &tmXh, &full_bar[st], tci * WBN + 64, bcx, bcy, n0);
+#pragma unroll
+                for (int cb = 0; cb < WBN / 64; cb++) tma_load_4d(sB + cb * kBlock, &tmXh, &full_bar[st], tci * WBN + cb * 64, bcx, bcy, n0);
                 if (TERMS == 3) {
                     tma_load_4d(sA + kPart, &tmDl, &full_bar[st], tco * WBM, acx, acy, n0);
                     tma_load_4d(sA + kPart + kBlock, &tmDl, &full_bar[st], tco * WBM + 64, acx, acy, n0);
-                    tma_load_4d(sB + kPart, &tmXl, &full_bar[st], tci * WBN, bcx, bcy, n0);
-                    tma_load_4d(sB + kPart + kBlock, &tmXl, &full_bar[st], tci * WBN + 64, bcx, bcy, n0);
+#pragma unroll
+                    for (int cb = 0; cb < WBN / 64; cb++) tma_load_4d(sB + kPart + cb * kBlock, &tmXl, &full_bar[st], tci * WBN + cb * 64, bcx, bcy, n0);
                 }
             }
         }
@@ -154,10 +157,25 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 128);
+    if (warp == 2) tmem_dealloc(tmem_base, WBN);
+}
+
+template <int TERMS, int WBN>
+int launch_wgrad(const CUtensorMap& tmDh, const CUtensorMap& tmXh, const CUtensorMap& tmDl, const CUtensorMap& tmXl, float* dW, const WgradGeom& g,
+                 int64_t grid, cudaStream_t s, const char* who) {
+    constexpr int STAGES = (TERMS == 3) ? (WBN == 256 ? 2 : 3) : 4;
+    constexpr size_t stage = (size_t)(TERMS == 3 ? 2 : 1) * (2 + WBN / 64) * 64 * 128;
+    const size_t smem = 1024 + STAGES * stage + 256;
+    auto kern = wgrad_kernel<TERMS, WBN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { gp3d_set_error("%s: cannot reserve %zu B of shared memory: %s", who, smem, cudaGetErrorString(e)); return (int)e; }
+    kern<<<(unsigned)grid, kWgradThreads, smem, s>>>(tmDh, tmXh, tmDl, tmXl, dW, g);
+    return 0;
 }
 
 }  // namespace tc
+
+extern "C" int gp3d_conv_set_wide3(int on);   // conv_tc.cu: the same switch selects the 256-wide tiles here (query = set + restore)
 
 static int wg_pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -206,7 +224,9 @@ extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const 
     g.TH = wg_pow2ceil(HoP) < (64 / g.TW) ? wg_pow2ceil(HoP) : (64 / g.TW);
     g.TN = 64 / (g.TW * g.TH);
     g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN;
-    g.tiles_co = (Cout + 127) / 128; g.tiles_ci = (Cin + 127) / 128;
+    int wide_on = gp3d_conv_set_wide3(1); gp3d_conv_set_wide3(wide_on);
+    const int WBN = (Cin % 256 == 0 && wide_on) ? 256 : 128;
+    g.tiles_co = (Cout + 127) / 128; g.tiles_ci = (Cin + WBN - 1) / WBN;
     const int64_t ptiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
     const int out_tiles = g.tiles_co * g.tiles_ci * ntaps;
     int sms = GP3D_NUM_SMS, dev = 0;
@@ -223,18 +243,10 @@ extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const 
         rc = encode_act_map(&tmXl, xl, N, Hx, Wx, Cin, g.TW, g.TH, g.TN, sb, who); if (rc) return rc;
     } else { tmDl = tmDh; tmXl = tmXh; }
     const int terms = dyl ? 3 : 1;
-    const size_t stage = (size_t)(terms == 3 ? 2 : 1) * 4 * 64 * 128;
-    const size_t smem = 1024 + (size_t)(terms == 3 ? 3 : 4) * stage + 256;
     const int64_t grid = (int64_t)out_tiles * g.splitk;
     cudaStream_t s = (cudaStream_t)stream;
-    if (terms == 3) {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { gp3d_set_error("%s: cannot reserve %zu B of shared memory: %s", who, smem, cudaGetErrorString(e)); return (int)e; }
-        tc::wgrad_kernel<3><<<(unsigned)grid, tc::kWgradThreads, smem, s>>>(tmDh, tmXh, tmDl, tmXl, dW, g);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { gp3d_set_error("%s: cannot reserve %zu B of shared memory: %s", who, smem, cudaGetErrorString(e)); return (int)e; }
-        tc::wgrad_kernel<1><<<(unsigned)grid, tc::kWgradThreads, smem, s>>>(tmDh, tmXh, tmDl, tmXl, dW, g);
-    }
+    rc = (terms == 3) ? (WBN == 256 ? tc::launch_wgrad<3, 256>(tmDh, tmXh, tmDl, tmXl, dW, g, grid, s, who) : tc::launch_wgrad<3, 128>(tmDh, tmXh, tmDl, tmXl, dW, g, grid, s, who))
+                      : (WBN == 256 ? tc::launch_wgrad<1, 256>(tmDh, tmXh, tmDl, tmXl, dW, g, grid, s, who) : tc::launch_wgrad<1, 128>(tmDh, tmXh, tmDl, tmXl, dW, g, grid, s, who));
+    if (rc) return rc;
     GP3D_RETURN_LAUNCH();
 }

@@ -294,6 +294,9 @@ typedef struct gp3d_conv_desc {
     const gp3d_conv_epilogue* epi;       /* optional fused epilogue */
 } gp3d_conv_desc;
 int gp3d_conv_nhwc(const gp3d_conv_desc* desc, void* stream);
+/* Tuning switch: 256-wide output-channel tiles for the three-term (bf16x3) form when Cout % 256 == 0 (two-stage ring of 96 KB stages).
+ * Returns the previous setting. */
+int gp3d_conv_set_wide3(int on);
 int gp3d_conv2d_nhwc_bf16x3_act(const void* xh, const void* xl, const void* wh, const void* wl, float* y, int N, int H, int W,
                                 int Cin, int Cout, int ksize, const gp3d_conv_epilogue* epi, void* stream);
 /* same epilogue for either precision: xl / wl both NULL = single-term bf16 (the discriminator's low-precision blocks: Conv2dLayer's

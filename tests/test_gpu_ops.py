@@ -255,3 +255,26 @@ def test_fir4_up2_tma_kernel_matches_register_tiled_kernel_bit_for_bit(shape, pa
     assert torch.equal(y.contiguous(), ref.contiguous())
     o = R.upfirdn2d(x.permute(0, 3, 1, 2).cpu().numpy(), f.cpu().numpy(), up=2, padding=[px0, px1, py0, py1], flip_filter=flip, gain=4)
     assert np.abs(y.cpu().numpy() - o).max() <= 2e-5 * np.abs(o).max()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('shape', [(2, 3, 40, 48), (1, 5, 17, 136), (3, 2, 70, 264)])
+@pytest.mark.parametrize('mode,flip', [('up', False), ('down', False), ('up', True), ('down', True)])
+def test_nchw_tma_resampling_kernels_bit_exact_on_integers(mode, flip, shape, dtype):
+    """upsample2d / downsample2d of dense NCHW planes (W % 8 == 0: the TMA-staged register-blocked kernels of csrc/fir_nchw_tma.cu) against the oracle's
+    explicit-index upfirdn2d on integer-valued data with an asymmetric integer filter: every sum is exact in fp32 / fp16, so equality is bit-exact --
+    index arithmetic, polyphase tap selection, convolution-vs-correlation and ragged tile edges included."""
+    from oracle import restated as R
+    _, up, _ = _ops()
+    rs = np.random.RandomState(shape[2] * 7 + shape[3])
+    x = rs.randint(-3, 4, size=shape).astype(np.float32)
+    f = np.outer([1, 2, 3, 1], [2, 1, 3, 1]).astype(np.float32)             # asymmetric: flips and transposes are visible
+    xt, ft = cu(x).to(dtype), cu(f)
+    if mode == 'up':
+        y = up.upsample2d(xt, ft, flip_filter=flip)
+        ref = R.upfirdn2d(x, f, up=2, padding=[2, 1, 2, 1], flip_filter=flip, gain=4)
+    else:
+        y = up.downsample2d(xt, ft, flip_filter=flip)
+        ref = R.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1], flip_filter=flip, gain=1)
+    assert y.dtype == dtype and tuple(y.shape) == ref.shape
+    assert np.array_equal(y.float().cpu().numpy(), ref)

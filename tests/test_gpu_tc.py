@@ -419,3 +419,47 @@ def test_fused_conv2d_layer_matches_unfused(terms, k, act, hyper, bias, clamp, g
         assert (outs[0][0].abs() <= clamp * gain + 1e-6).all() and (outs[0][0].abs() >= clamp * gain - 1e-6).any()     # the clamp is active in this case
     y2 = layer(x, c=c, gain=gain)
     y2.add_(1.0)                                             # in-place update of the output (DiscriminatorBlock: y.add_(x)) must be legal
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,k', [(2, 128, 256, 32, 3), (1, 256, 512, 16, 3), (4, 64, 256, 8, 1), (1, 64, 1024, 16, 3)])
+def test_three_term_conv_256_wide_tiles_equal_128_wide_tiles(N, Cin, Cout, H, k):
+    """The bf16x3 form with 256-wide output-channel tiles (two-stage ring of 96 KB stages) accumulates every output element over the same K order as the
+    128-wide form: bit-identical results, and fp32-grade against float64."""
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    _lib = importlib.import_module('3dgp_b200._lib')
+    torch.manual_seed(Cout + H)
+    x = torch.randn(N, Cin, H, H, device='cuda'); w = torch.randn(Cout, Cin, k, k, device='cuda') / (Cin * k * k) ** 0.5
+    L = _lib.lib()
+    old = L.gp3d_conv_set_wide3(1)
+    try:
+        y_wide = tc.conv2d_forward(x, w, 3)
+        L.gp3d_conv_set_wide3(0)
+        y_narrow = tc.conv2d_forward(x, w, 3)
+    finally:
+        L.gp3d_conv_set_wide3(old)
+    assert torch.equal(y_wide, y_narrow)
+    yd = torch.nn.functional.conv2d(x.double(), w.double(), padding=k // 2)
+    assert ((y_wide.double() - yd).norm() / yd.norm()).item() < 2e-5
+
+
+@pytest.mark.parametrize('terms', [3, 1])
+@pytest.mark.parametrize('N,Cin,Cout,H,k', [(2, 256, 128, 32, 3), (1, 512, 256, 16, 3), (4, 256, 64, 8, 1)])
+def test_weight_gradient_256_wide_cin_tiles(N, Cin, Cout, H, k, terms):
+    """wgrad_kernel<*, 256> (Cin % 256 == 0): same products as the 128-wide form (split-K partition differs, so the sums agree to rounding) and
+    fp32-grade (three-term) against float64."""
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    L = importlib.import_module('3dgp_b200._lib').lib()
+    torch.manual_seed(Cin + H + terms)
+    x = torch.randn(N, Cin, H, H, device='cuda'); dy = torch.randn(N, Cout, H, H, device='cuda')
+    old = L.gp3d_conv_set_wide3(1)
+    try:
+        gw_wide = tc.conv_wgrad(dy, x, k, 'conv', 1, k // 2, terms)
+        L.gp3d_conv_set_wide3(0)
+        gw_narrow = tc.conv_wgrad(dy, x, k, 'conv', 1, k // 2, terms)
+    finally:
+        L.gp3d_conv_set_wide3(old)
+    w = torch.zeros(Cout, Cin, k, k, device='cuda', dtype=torch.float64, requires_grad=True)
+    gwd = torch.autograd.grad(torch.nn.functional.conv2d(x.double(), w, padding=k // 2), w, dy.double())[0]
+    rel = lambda a: ((a.double() - gwd).norm() / gwd.norm()).item()
+    assert ((gw_wide - gw_narrow).norm() / gw_narrow.norm()).item() < 1e-5
+    assert rel(gw_wide) < (2e-5 if terms == 3 else 6e-3)

@@ -30,9 +30,11 @@ for (name, Cin, Cout, H, k) in [('b512.conv1', 128, 128, 512, 3), ('b256.conv1',
     y = torch.empty(B, H, H, Cout, device='cuda')
     L = tc._lib.lib(); st = tc._lib.stream_ptr()
     flops = 2.0 * B * H * H * Cin * Cout * k * k
-    t3 = timeit(lambda: L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, k, 0, st))
+    f3 = lambda: L.gp3d_conv2d_nhwc_bf16x3(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, k, 0, st)
+    L.gp3d_conv_set_wide3(0); t3n = timeit(f3)
+    L.gp3d_conv_set_wide3(1); t3 = timeit(f3)
     t1 = timeit(lambda: L.gp3d_conv2d_nhwc_bf16(xh.data_ptr(), wh.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, k, 0, st))
-    rows.append(dict(layer=name, B=B, Cin=Cin, Cout=Cout, H=H, k=k, gflop=flops / 1e9, ms_bf16x3=t3, ms_bf16=t1,
+    rows.append(dict(layer=name, B=B, Cin=Cin, Cout=Cout, H=H, k=k, gflop=flops / 1e9, ms_bf16x3=t3, ms_bf16x3_bn128=t3n, ms_bf16=t1,
                      tensor_tflops_bf16x3=3 * flops / t3 / 1e9, tensor_tflops_bf16=flops / t1 / 1e9,
                      frac_bf16x3=3 * flops / t3 / 1e9 / peaks['bf16_tflops'], frac_bf16=flops / t1 / 1e9 / peaks['bf16_tflops']))
     if Cin % 128 == 0 and Cout % 128 == 0:
