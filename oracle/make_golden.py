@@ -316,6 +316,14 @@ def gen_camera_adaptor(ns, report):
     np.savez_compressed(os.path.join(GOLD, 'camera_adaptor.npz'), **res)
 
 
+def gen_reference_config(ns, report):
+    """The experiment configuration the reference's launcher would save for the README's ImageNet-256 command (oracle/compose_config.py)."""
+    from oracle import compose_config as cc
+    cfg = cc.compose(os.path.join(rh.REF_ROOT, 'configs'), cc.README_IMAGENET_OVERRIDES)
+    with open(os.path.join(GOLD, 'reference_experiment_config.json'), 'w') as f:
+        json.dump(cfg, f, indent=1, sort_keys=True)
+
+
 def main():
     assert rh.available(), 'reference not found'
     os.makedirs(GOLD, exist_ok=True)
@@ -324,7 +332,8 @@ def main():
     report = {}
     only = sys.argv[1:]
     gens = dict(upfirdn2d=gen_upfirdn2d, bias_act=gen_bias_act, filtered_lrelu=gen_filtered_lrelu, render=gen_render, networks=gen_networks,
-                networks_wide=lambda ns_, rep_: gen_networks(ns_, rep_, 'wide'), camera_adaptor=gen_camera_adaptor)
+                networks_wide=lambda ns_, rep_: gen_networks(ns_, rep_, 'wide'), camera_adaptor=gen_camera_adaptor,
+                reference_config=gen_reference_config)
     for name, fn in gens.items():
         if only and name not in only:
             continue

@@ -52,13 +52,15 @@ def _delta(a, b):
     return {k: b[k] - a[k] for k in a}
 
 
-def _train_forward(G, t, cam, pp, kw, hooks=None):
+def _train_forward(G, t, cam, pp, kw, hooks=None, mlp_mode=None):
     B = t['z'].shape[0]
     noises = [torch.from_numpy(n).cuda() for n in cases.layer_noises(kw, B)]
     G.train()
     G.synthesis.nerf_noise_std = 0.0
     ws = G.mapping(t['z'], t['c'])
     ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)))
+    if mlp_mode is not None:
+        ro['mlp_mode'] = mlp_mode
     out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
     return ws, out, noises
 
@@ -139,6 +141,29 @@ def test_wide_generator_loss_gradients_vs_reference(golden, g_terms, capsys):
     # x2w16 is a measured alternative, not the default: its 2^-12 weight rounding keeps the FORWARD inside 1e-3 (5.5e-4) but perturbs enough lrelu masks
     # that parameter gradients sit at 6e-3 .. 1.5e-2 -- outside the fp32 bar, and it buys only 3 % of the step (profiles/r2_precision_modes.txt)
     assert max(errs.values()) < (3e-3 if g_terms == 3 else 3e-2), errs
+
+
+@pytest.mark.parametrize('mlp_mode', [2, 1])
+def test_wide_generator_render_mlp_arithmetic_vs_reference(golden, capsys, mlp_mode):
+    """Tri-plane MLP arithmetic of the fused ray-march inside the whole generator: 2 = 3xTF32 (fp32-grade, the default), 1 = one TF32 product
+    (10-bit operands).  Both are measured against the reference's fp32 evaluation: outputs at the 1e-3 bar, parameter gradients reported."""
+    cfg, G, D, t, cam, pp, kw = _build(fp32_D=True)
+    g = golden('networks_wide')
+    D.train(); D.requires_grad_(False)
+    ws, out, _ = _train_forward(G, t, cam, pp, kw, mlp_mode=mlp_mode)
+    e_img = maxrel(out.img.detach().cpu().numpy(), g['G/train/img']); e_dep = maxrel(out.depth.detach().cpu().numpy(), g['G/train/depth'])
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    names = cases.probe_params('G', 'wide')
+    pars = dict(G.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().cpu().numpy()), g['G/grad/' + n]) for n, gr in zip(names, gs)}
+    with capsys.disabled():
+        print(f'\n[ray-march MLP mode {mlp_mode} through G vs reference] img {e_img:.2e} depth {e_dep:.2e} worst param grad {max(errs.values()):.2e} '
+              f'(median {float(np.median(list(errs.values()))):.2e})')
+    assert e_img < TOL and e_dep < TOL
+    if mlp_mode == 2:
+        assert max(errs.values()) < 3e-3, errs
 
 
 def test_wide_discriminator_fp32_first_order_and_r1_vs_reference(golden, capsys):
