@@ -5,8 +5,10 @@
 // index arithmetic and is ISSUE-bound at 0.13-0.22 of HBM (profiles/r1_hot_kernels_details.txt: issue slots 82 % busy, DRAM 14 %).  Here
 //   * ONE 3-D TMA box {IW, IH, 1 plane} lands the haloed window in shared memory in the tensor's own element type; rows / columns outside the image
 //     are zero-filled by the TMA unit (= the padding rule): no staging instructions, no bounds logic;
-//   * the window origin is chosen so that every thread's columns start on an 8-byte (up) / 16-byte (down) boundary of its shared-memory row: vector
-//     LDS, converted to float in registers;
+//   * the innermost START coordinate of a tiled TMA load must be 16-byte aligned (c0 * elemsize % 16 == 0; anything else raises an illegal-instruction
+//     fault on sm_100a -- measured, tools/tma_probe.cu / profiles/r2_tma_box_start_probe.txt; negative aligned starts and boxes larger than the tensor
+//     are fine), so the window starts A = 16 / elemsize columns left of the first output's column instead of 1: a thread reads three (up) / four (down)
+//     aligned 4-element vectors per window row and uses elements 3 .. 8 (3 .. 12) of them, converted to float in registers;
 //   * a thread produces 8 x 2 (up) or 4 x 2 (down) outputs from a 3 x 6 / 6 x 10 register window with compile-time tap indices
 //     (7 / 26 instructions per output), stored as one 16-byte / 8-byte vector per row.
 // Taps accumulate in the order of the index contract in upfirdn2d.cu (rows ascending, then columns; gain applied last): results are bit-identical to
@@ -70,11 +72,18 @@ __device__ __forceinline__ void stage_filter16(float* sf, const float* f, int fl
 }
 
 // ---- up = 2, pad0 = 2: output (2j + px, 2i + py) = sum_{a, b in {0,1}} in[i - 1 + py + a][j - 1 + px + b] * sf[2a + py][2b + px].
-// Tile 128 x 32 outputs of one plane; window origin (ox0 / 2 - 1, oy0 / 2 - 1); thread (xg, yg): outputs x = 8 xg .. 8 xg + 7, rows 2 yg, 2 yg + 1.
-constexpr int U_TOW = 128, U_TOH = 32, U_IW = 72, U_IH = 18;
+// Tile 128 x 32 outputs of one plane; window origin (ox0 / 2 - A, oy0 / 2 - 1); thread (xg, yg): outputs x = 8 xg .. 8 xg + 7, rows 2 yg, 2 yg + 1.
+constexpr int U_TOW = 128, U_TOH = 32, U_IH = 18;
+template <class T> struct win {
+    static constexpr int A = 16 / (int)sizeof(T);          // alignment quantum of the innermost TMA start coordinate, in elements
+    static constexpr int BO = A - 4;                       // a thread's first 4-element vector starts BO columns right of its group origin
+    static constexpr int U_IW = (4 * 15 + BO + 12 + A - 1) / A * A;      // 72 (float) / 80 (half)
+    static constexpr int D_IW = (8 * 15 + BO + 16 + A - 1) / A * A;      // 136 (float) / 144 (half)
+};
 
 template <class T>
 __global__ void __launch_bounds__(256) fir4_nchw_up2_kernel(const __grid_constant__ CUtensorMap tmX, FirNchwParams p) {
+    constexpr int U_IW = win<T>::U_IW;
     __shared__ __align__(128) T tile[U_IH * U_IW];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float sf[16];
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(256) fir4_nchw_up2_kernel(const __grid_constan
     if (tid == 0) {
         mbar_expect_tx(&bar, (uint32_t)(U_IH * U_IW * sizeof(T)));
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&bar)), "r"(ox0 / 2 - 1), "r"(oy0 / 2 - 1), "r"(plane) : "memory");
+                     ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&bar)), "r"(ox0 / 2 - win<T>::A), "r"(oy0 / 2 - 1), "r"(plane) : "memory");
     }
     const int xg = tid & 15, yg = tid >> 4;
     float cf[16];
@@ -96,8 +105,11 @@ __global__ void __launch_bounds__(256) fir4_nchw_up2_kernel(const __grid_constan
     float v[3][6];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const T* row = tile + (yg + r) * U_IW + 4 * xg;
-        rowvec<T>::ld4(row, v[r]); rowvec<T>::ld2(row + 4, v[r] + 4);
+        const T* row = tile + (yg + r) * U_IW + 4 * xg + win<T>::BO;
+        float t12[12];
+        rowvec<T>::ld4(row, t12); rowvec<T>::ld4(row + 4, t12 + 4); rowvec<T>::ld4(row + 8, t12 + 8);
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[r][k] = t12[3 + k];
     }
     T* yb = reinterpret_cast<T*>(p.y) + (size_t)plane * p.outH * p.outW;
 #pragma unroll
@@ -128,11 +140,12 @@ __global__ void __launch_bounds__(256) fir4_nchw_up2_kernel(const __grid_constan
 }
 
 // ---- down = 2, pad0 = 1: output (x, y) = sum_{ky, kx} in[2y - 1 + ky][2x - 1 + kx] * sf[ky][kx].
-// Tile 64 x 32 outputs; window origin (2 ox0 - 1, 2 oy0 - 1); thread (xg, yg): outputs x = 4 xg .. 4 xg + 3, rows 2 yg, 2 yg + 1.
-constexpr int D_TOW = 64, D_TOH = 32, D_IW = 136, D_IH = 66;
+// Tile 64 x 32 outputs; window origin (2 ox0 - A, 2 oy0 - 1); thread (xg, yg): outputs x = 4 xg .. 4 xg + 3, rows 2 yg, 2 yg + 1.
+constexpr int D_TOW = 64, D_TOH = 32, D_IH = 66;
 
 template <class T>
 __global__ void __launch_bounds__(256) fir4_nchw_down2_kernel(const __grid_constant__ CUtensorMap tmX, FirNchwParams p) {
+    constexpr int D_IW = win<T>::D_IW;
     extern __shared__ __align__(128) unsigned char dsm[];
     T* tile = reinterpret_cast<T*>(dsm);
     __shared__ __align__(8) uint64_t bar;
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(256) fir4_nchw_down2_kernel(const __grid_const
     if (tid == 0) {
         mbar_expect_tx(&bar, (uint32_t)(D_IH * D_IW * sizeof(T)));
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&bar)), "r"(2 * ox0 - 1), "r"(2 * oy0 - 1), "r"(plane) : "memory");
+                     ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&bar)), "r"(2 * ox0 - win<T>::A), "r"(2 * oy0 - 1), "r"(plane) : "memory");
     }
     const int xg = tid & 15, yg = tid >> 4;
     float cf[16];
@@ -159,9 +172,11 @@ __global__ void __launch_bounds__(256) fir4_nchw_down2_kernel(const __grid_const
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
 #pragma unroll
     for (int r = 0; r < 6; r++) {                          // window rows 4 yg + r feed output row i with tap ky = r - 2 i
-        float v[10];
-        const T* row = tile + (4 * yg + r) * D_IW + 8 * xg;
-        rowvec<T>::ld8(row, v); rowvec<T>::ld2(row + 8, v + 8);
+        float t16[16], v[10];
+        const T* row = tile + (4 * yg + r) * D_IW + 8 * xg + win<T>::BO;
+        rowvec<T>::ld4(row, t16); rowvec<T>::ld4(row + 4, t16 + 4); rowvec<T>::ld4(row + 8, t16 + 8); rowvec<T>::ld4(row + 12, t16 + 12);
+#pragma unroll
+        for (int k = 0; k < 10; k++) v[k] = t16[3 + k];
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             const int ky = r - 2 * i;
@@ -215,19 +230,18 @@ int gp3d_fir4_nchw_launch(const void* x, const float* f, void* y, int is_half, i
     if (mode == 0) {
         const dim3 grid((outW + U_TOW - 1) / U_TOW, (outH + U_TOH - 1) / U_TOH, planes);
         if (grid.y > 65535 || planes > 65535) return GP3D_E_UNSUPPORTED;
-        if (is_half) { if (encode_plane_map<__half>(&tm, x, planes, H, W, U_IW, U_IH)) return GP3D_E_UNSUPPORTED; fir4_nchw_up2_kernel<__half><<<grid, 256, 0, st>>>(tm, p); }
-        else { if (encode_plane_map<float>(&tm, x, planes, H, W, U_IW, U_IH)) return GP3D_E_UNSUPPORTED; fir4_nchw_up2_kernel<float><<<grid, 256, 0, st>>>(tm, p); }
+        if (is_half) { if (encode_plane_map<__half>(&tm, x, planes, H, W, win<__half>::U_IW, U_IH)) return GP3D_E_UNSUPPORTED; fir4_nchw_up2_kernel<__half><<<grid, 256, 0, st>>>(tm, p); }
+        else { if (encode_plane_map<float>(&tm, x, planes, H, W, win<float>::U_IW, U_IH)) return GP3D_E_UNSUPPORTED; fir4_nchw_up2_kernel<float><<<grid, 256, 0, st>>>(tm, p); }
         return 0;
     }
     const dim3 grid((outW + D_TOW - 1) / D_TOW, (outH + D_TOH - 1) / D_TOH, planes);
     if (grid.y > 65535 || planes > 65535) return GP3D_E_UNSUPPORTED;
-    const size_t smem = (size_t)D_IH * D_IW * es;
     if (is_half) {
-        if (encode_plane_map<__half>(&tm, x, planes, H, W, D_IW, D_IH)) return GP3D_E_UNSUPPORTED;
-        fir4_nchw_down2_kernel<__half><<<grid, 256, smem, st>>>(tm, p);
+        if (encode_plane_map<__half>(&tm, x, planes, H, W, win<__half>::D_IW, D_IH)) return GP3D_E_UNSUPPORTED;
+        fir4_nchw_down2_kernel<__half><<<grid, 256, (size_t)D_IH * win<__half>::D_IW * 2, st>>>(tm, p);
     } else {
-        if (encode_plane_map<float>(&tm, x, planes, H, W, D_IW, D_IH)) return GP3D_E_UNSUPPORTED;
-        fir4_nchw_down2_kernel<float><<<grid, 256, smem, st>>>(tm, p);
+        if (encode_plane_map<float>(&tm, x, planes, H, W, win<float>::D_IW, D_IH)) return GP3D_E_UNSUPPORTED;
+        fir4_nchw_down2_kernel<float><<<grid, 256, (size_t)D_IH * win<float>::D_IW * 4, st>>>(tm, p);
     }
     return 0;
 }
