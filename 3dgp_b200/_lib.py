@@ -59,6 +59,7 @@ PROTOTYPES = {
     'gp3d_generate_rays': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 3),
     'gp3d_raymarch_backward': (c_int, [c_void_p, c_int] + [c_int64] * 5 + [c_void_p] * 19 + [ctypes.POINTER(RaymarchOpts), c_void_p]),
     'gp3d_modulate': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    'gp3d_to_uint8': (c_int, [c_void_p] * 2 + [c_int] * 5 + [c_int64] * 4 + [c_float] * 2 + [c_void_p]),
     'gp3d_demod_act': (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 6 + [c_float] * 3 + [c_void_p]),
     'gp3d_demod_act_bwd': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),
     'gp3d_demod_act_bwd_split': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int] * 4 + [c_float] * 2 + [c_void_p]),

@@ -380,6 +380,39 @@ extern "C" int gp3d_filtered_lrelu_act(void* x, uint8_t* si, int dtype, int N, i
     GP3D_RETURN_LAUNCH();
 }
 
+// uint8 image conversion of the metrics / snapshot path (metric_utils.py:313, training_loop.py:23-49): y = uint8(clamp(x * scale + shift, 0, 255)) for the
+// first Cy channels of a float32 [N, Cx, H, W] tensor with arbitrary strides -> NCHW-contiguous uint8 (float -> uint8 truncates, as torch's cast does).
+namespace {
+__global__ void __launch_bounds__(256) to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int N, int Cy, int HW, int W,
+                                                       int64_t sN, int64_t sC, int64_t sH, int64_t sW, float scale, float shift) {
+    const int64_t total = (int64_t)N * Cy * HW / 4;              // 4 consecutive pixels of one row per thread (W % 4 == 0)
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = v * 4;
+        const int p = (int)(e % HW); const int64_t nc = e / HW;
+        const int c = (int)(nc % Cy), n = (int)(nc / Cy);
+        const int h = p / W, w = p - h * W;
+        const float* src = x + n * sN + c * sC + h * sH + w * sW;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float t = fmaf(src[k * sW], scale, shift);
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            packed |= (uint32_t)(int)t << (8 * k);                // truncation toward zero
+        }
+        reinterpret_cast<uint32_t*>(y)[v] = packed;
+    }
+}
+}  // namespace
+
+extern "C" int gp3d_to_uint8(const float* x, uint8_t* y, int N, int Cx, int Cy, int H, int W, int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                             float scale, float shift, void* stream) {
+    GP3D_CHECK_ARG(x && y && N >= 1 && Cy >= 1 && Cy <= Cx && H >= 1 && W >= 4 && W % 4 == 0, "to_uint8: bad arguments (W must be a multiple of 4)");
+    GP3D_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 3u) == 0, "to_uint8: output must be 4-byte aligned");
+    const int64_t total = (int64_t)N * Cy * H * W / 4;
+    to_uint8_kernel<<<gp3d_grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, N, Cy, H * W, W, sN, sC, sH, sW, scale, shift);
+    GP3D_RETURN_LAUNCH();
+}
+
 extern "C" int gp3d_grad_epilogue(float* g, int64_t numel, float inv_world, float posinf, float neginf, void* stream) {
     GP3D_CHECK_ARG(g && numel >= 0, "grad_epilogue: bad arguments");
     GP3D_CHECK_ARG(gp3d_aligned16(g), "grad_epilogue: buffer must be 16-byte aligned");

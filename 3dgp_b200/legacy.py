@@ -1,0 +1,152 @@
+"""Reading the reference's network snapshots (`network-snapshot-*.pkl`, written by src/training/training_loop.py:478-484) WITHOUT the reference's
+source tree: every network in such a pickle is a `persistent_class` object (src/torch_utils/persistence.py:99-131) that reduces to
+`_reconstruct_persistent_obj(meta)` with meta = {type, version, module_src, class_name, state}; `state` is the module's `__dict__`
+(`_parameters`, `_buffers`, `_modules` -- themselves persistent objects -- plus `_init_args` / `_init_kwargs`).  The unpickler below intercepts that
+hook and every class outside torch / numpy / builtins (OmegaConf nodes, the reference's EasyDict, ...), keeps their state as plain records, flattens the
+module tree into a `state_dict` and rebuilds THIS package's Generator / Discriminator from the recorded constructor arguments.  The reference's own
+route (`exec` of the embedded module source) is deliberately not taken: the point of a snapshot here is weights + configuration."""
+import collections
+import io
+import pickle
+
+import torch
+
+from .dnnlib import EasyDict
+
+
+class _Record:
+    """State of an object whose class is not importable here."""
+    def __init__(self, *args, **kwargs):
+        self._args, self._kwargs, self._state = args, kwargs, None
+
+    def __setstate__(self, state):
+        self._state = state
+
+    def __reduce_ex__(self, protocol):          # records are read-only
+        raise pickle.PicklingError('snapshot records cannot be re-pickled')
+
+
+def _record_class(module, name):
+    return type(name, (_Record,), {'__module__': module, '_origin': f'{module}.{name}'})
+
+
+class PersistentStub:
+    """One persistent object of the snapshot: `class_name`, `state` (its __dict__)."""
+    def __init__(self, meta):
+        self.class_name = meta['class_name']
+        self.state = meta['state'] or {}
+
+
+_SAFE_PREFIXES = ('torch', 'numpy', 'collections', 'builtins', '_codecs', 'copyreg')
+
+
+class _SnapshotUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if name == '_reconstruct_persistent_obj' and module.endswith('persistence'):
+            return PersistentStub
+        if module.split('.')[0] in _SAFE_PREFIXES:
+            return super().find_class(module, name)
+        if name == 'EasyDict':
+            return EasyDict
+        return _record_class(module, name)
+
+
+def plain(node):
+    """OmegaConf containers / nodes, EasyDicts and records -> plain python (dict / list / scalars).  OmegaConf pickles a DictConfig / ListConfig as its
+    __dict__ with the children under `_content` and a ValueNode with its payload under `_val`."""
+    if isinstance(node, _Record):
+        st = node._state if isinstance(node._state, dict) else {}
+        if '_content' in st:
+            return plain(st['_content'])
+        if '_val' in st:
+            return plain(st['_val'])
+        if isinstance(node._state, dict):
+            return {k: plain(v) for k, v in st.items() if not k.startswith('_')}
+        return None
+    if isinstance(node, dict):
+        return {k: plain(v) for k, v in node.items()}
+    if isinstance(node, (list, tuple)):
+        return [plain(v) for v in node]
+    return node
+
+
+def _module_state(node):
+    """__dict__ of a module-like snapshot node: persistent object, record of a non-persistent module class, or a plain torch container."""
+    if isinstance(node, PersistentStub):
+        return node.state
+    if isinstance(node, _Record):
+        return node._state if isinstance(node._state, dict) and '_modules' in node._state else None
+    if isinstance(node, torch.nn.Module):
+        return node.__dict__
+    return None
+
+
+def module_state_dict(node, prefix=''):
+    """Flattens a snapshot module tree into an ordered {dotted name: tensor} (parameters and persistent buffers, torch.nn.Module.state_dict order)."""
+    st = _module_state(node)
+    if st is None:
+        raise RuntimeError(f'snapshot entry {prefix or "<root>"} is not a module ({getattr(node, "_origin", type(node).__name__)})')
+    out = collections.OrderedDict()
+    skip = st.get('_non_persistent_buffers_set', set()) or set()
+    for k, v in (st.get('_parameters') or {}).items():
+        if v is not None:
+            out[prefix + k] = v.detach()
+    for k, v in (st.get('_buffers') or {}).items():
+        if v is not None and k not in skip:
+            out[prefix + k] = v.detach()
+    for k, m in (st.get('_modules') or {}).items():
+        if m is not None:
+            out.update(module_state_dict(m, prefix + k + '.'))
+    return out
+
+
+def _class_name(node):
+    return node.class_name if isinstance(node, PersistentStub) else type(node).__name__
+
+
+def _init_arguments(node):
+    st = _module_state(node) or {}
+    return plain(list(st.get('_init_args') or [])), plain(st.get('_init_kwargs') or {})
+
+
+def read_snapshot(f):
+    """f: path (optionally .gz) or binary file object.  Returns {name: PersistentStub | record | plain data}: 'G', 'D', 'G_ema', 'training_set_kwargs', ..."""
+    if isinstance(f, (str, bytes)):
+        import gzip
+        opener = gzip.open if str(f).endswith('.gz') else open
+        with opener(f, 'rb') as fh:
+            return _SnapshotUnpickler(fh).load()
+    return _SnapshotUnpickler(f).load()
+
+
+def _build(node, device, init=None):
+    from .training.networks_epigraf import Generator
+    from .training.networks_discriminator import Discriminator
+    name = _class_name(node)
+    cls = {'Generator': Generator, 'Discriminator': Discriminator}.get(name)
+    if cls is None:
+        raise RuntimeError(f'snapshot holds a {name}; only Generator / Discriminator of the 3dgp model are built here')
+    args, kw = _init_arguments(node)
+    if init is not None:                   # classes the reference does not decorate carry no constructor record: the caller supplies it
+        args, kw = init
+    kw = {k: (EasyDict.init_recursively(v) if isinstance(v, dict) else v) for k, v in kw.items()}
+    net = cls(*args, **kw)
+    sd = module_state_dict(node)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f'snapshot / module mismatch for {name}: missing {list(missing)[:5]}, unexpected {list(unexpected)[:5]}')
+    return net.eval().requires_grad_(False).to(device)
+
+
+def load_network_pkl(f, device='cpu', names=('G', 'D', 'G_ema'), init=None):
+    """The reference's `legacy.load_network_pkl` role: networks of a snapshot as THIS package's modules (eval mode, no grad), other entries as plain data.
+    init: optional {name: (args, kwargs)} constructor arguments for entries whose class keeps none."""
+    data = read_snapshot(f)
+    out = {}
+    for k, v in data.items():
+        if _module_state(v) is not None:
+            if k in names:
+                out[k] = _build(v, device, (init or {}).get(k))
+        else:
+            out[k] = plain(v)
+    return out

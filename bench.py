@@ -409,6 +409,9 @@ def run_train_step(args, rank, world, local):
     gpu_base = None
     if world == 1 and not args.no_gpu_baseline and not args.small:
         gpu_base = gpu_baseline_step(tr, host, dev, dn, args)
+    ginfer = None
+    if not args.no_ginfer and not args.small:
+        ginfer = ginfer_leg(tr.G_ema, cfg, dev, dn, rank, world)
     res = dict(
         metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
         dtype='f32 storage; G convs bf16x3 on tcgen05 (three bf16 MMAs per product, fp32 accumulate: fp32-grade), tri-plane MLP 3xTF32; '
@@ -434,10 +437,33 @@ def run_train_step(args, rank, world, local):
         gpu_launches=int(launches * args.steps), clocks=clocks)
     if gpu_base is not None:
         res['gpu_baseline'] = gpu_base
+    if ginfer is not None:
+        res['ginfer'] = ginfer
     return res
 
 
 D_LOW_PRECISION_NAME = 'bf16'
+
+
+def ginfer_leg(G_ema, cfg, dev, dn, rank, world, B=64, steps=3):
+    """BASELINE configs[4] inside the default run: G_ema inference at batch 64 through the metrics loop's call pattern (metric_utils.py:303-319,
+    training/inference.py::generate_uint8: eval mode, 256x256 full-frame render, uint8 on the device), every step copying its latents / cameras from
+    pinned host memory and the uint8 images back.  Replicas only: no collective."""
+    inf = importlib.import_module('3dgp_b200.training.inference')
+    host = synthetic_batch(cfg, B, dev, seed=1000 + rank)
+    keys = ('z', 'c', 'angles', 'fov', 'radius', 'look_at')
+    res = cfg.dataset.resolution
+    out_h = torch.empty([B, 3, res, res], dtype=torch.uint8, pin_memory=True)
+
+    def step():
+        dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        cm = dn.TensorGroup(angles=dd['angles'], fov=dd['fov'], radius=dd['radius'], look_at=dd['look_at'])
+        out_h.copy_(inf.generate_uint8(G_ema, dd['z'], dd['c'], cm, noise_mode='const'), non_blocking=True)
+
+    ms, _ = timed_region(step, steps, 3, world)
+    return dict(metric='G-only inference images/s at 256x256 (end to end: H2D latents / cameras, D2H uint8 images)', value=world * B / (ms * 1e-3), unit='images/s',
+                ms_per_step=ms, batch_per_gpu=B, steps=steps, rays_per_image=res * res, d2h_bytes_per_step=int(out_h.numel()),
+                parallelism=f'replicas x{world} (no collective)')
 
 
 def gpu_baseline_step(tr, host, dev, dn, args):
@@ -480,7 +506,8 @@ def run_ginfer(args, rank, world, local):
     gp = importlib.import_module('3dgp_b200')
     cfgm = importlib.import_module('3dgp_b200.config'); dn = importlib.import_module('3dgp_b200.dnnlib')
     dev = torch.device('cuda', local)
-    B = args.batch_gpu or 16
+    inf = importlib.import_module('3dgp_b200.training.inference')
+    B = args.batch_gpu or 64                 # BASELINE configs[4]: batch 64
     cfg = cfgm.make_config(batch_size=B * world)
     torch.manual_seed(99 + rank)
     G, _ = cfgm.build_networks(cfg, dev)
@@ -491,9 +518,7 @@ def run_ginfer(args, rank, world, local):
     cam = dn.TensorGroup(angles=d['angles'], fov=d['fov'], radius=d['radius'], look_at=d['look_at'])
 
     def step():
-        with torch.no_grad():
-            img = G(d['z'], d['c'], cam, noise_mode='const')
-            return (img[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8)
+        return inf.generate_uint8(G, d['z'], d['c'], cam, noise_mode='const')        # metric_utils.py:306-313 on the fused path
 
     c0 = gp._lib.launch_count
     ms, clocks = timed_region(step, args.steps, args.warmup, world)
@@ -503,9 +528,7 @@ def run_ginfer(args, rank, world, local):
     def step_e2e():
         dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
         cm = dn.TensorGroup(angles=dd['angles'], fov=dd['fov'], radius=dd['radius'], look_at=dd['look_at'])
-        with torch.no_grad():
-            img = G(dd['z'], dd['c'], cm, noise_mode='const')
-            out_h.copy_((img[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8), non_blocking=True)
+        out_h.copy_(inf.generate_uint8(G, dd['z'], dd['c'], cm, noise_mode='const'), non_blocking=True)
 
     ms_e2e, _ = timed_region(step_e2e, args.steps, 1, world)
     fg, _ = conv_flops_per_image(cfg)
@@ -652,6 +675,7 @@ def main():
     ap.add_argument('--planes-fp16', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true')
+    ap.add_argument('--no-ginfer', action='store_true', help='skip the G-only inference leg (BASELINE configs[4]) of the default run')
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--small', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='one blocking all-reduce of the flat gradient after backward (the reference schedule) instead of overlapped buckets')
@@ -691,7 +715,7 @@ def main():
         line = dict(metric=res['metric'], value=res['value'], unit=res['unit'], n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
                     config=res['config'], roofline=res['roofline'], e2e=res['e2e'], gpu_launches=res['gpu_launches'], clocks=res['clocks'])
-        for k in ('details', 'roofline_step_tensor', 'roofline_raymarch', 'forward_backward', 'gpu_baseline'):
+        for k in ('details', 'roofline_step_tensor', 'roofline_raymarch', 'forward_backward', 'gpu_baseline', 'ginfer'):
             if k in res:
                 line[k] = res[k]
         if world == 1 and not args.no_cpu_baseline:

@@ -192,6 +192,11 @@ int gp3d_raymarch_backward(const void* planes, int planes_dtype,
  * NCHW-contiguous or channels-last (cl != 0), float32/16/bf16.
  */
 int gp3d_modulate(const void* x, const void* s, void* y, int dtype, int N, int C, int HW, int cl, void* stream);
+/* uint8 conversion of generated images (metric_utils.py:313 `(img * 127.5 + 128).clamp(0, 255).to(torch.uint8)`, training_loop.py:23-49): the first
+ * Cy channels of float32 x [N, Cx, H, W] (element strides sN, sC, sH, sW: NCHW or channels-last) -> NCHW-contiguous uint8 y [N, Cy, H, W];
+ * y = (uint8) clamp(x * scale + shift, 0, 255), truncating like torch's cast.  W % 4 == 0. */
+int gp3d_to_uint8(const float* x, uint8_t* y, int N, int Cx, int Cy, int H, int W, int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                  float scale, float shift, void* stream);
 int gp3d_demod_act(const void* x, const void* d, const void* noise, int noise_per_sample, const void* b,
                    void* y, int dtype, int N, int C, int HW, int cl,
                    int act, float alpha, float gain, float clamp, void* stream);

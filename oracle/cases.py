@@ -275,3 +275,11 @@ def probe_params(which, variant='small'):
     return ['synthesis.tri_plane_mlp.model.0.weight', 'synthesis.tri_plane_mlp.model.1.bias', 'synthesis.tri_plane_decoder.b32.conv1.weight',
             'synthesis.tri_plane_decoder.b32.torgb.affine.bias', 'synthesis.tri_plane_decoder.b4.const', 'synthesis.tri_plane_decoder.b8.conv0.noise_strength',
             'synthesis.depth_adaptor.layers.0.weight', 'mapping.fc0.weight']
+
+
+# ----------------------------------------------------------------------------------------------
+def snapshot_fill(name, shape):
+    """Low-entropy deterministic tensor content for the snapshot fixture (compresses ~100x): value depends on the parameter name and the flat index."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    salt = sum(ord(ch) for ch in name) % 11
+    return (((np.arange(n, dtype=np.int64) + salt) % 13 - 6).astype(np.float32) / 8.0).reshape(shape)

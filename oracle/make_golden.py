@@ -316,6 +316,28 @@ def gen_camera_adaptor(ns, report):
     np.savez_compressed(os.path.join(GOLD, 'camera_adaptor.npz'), **res)
 
 
+def gen_snapshot(ns, report):
+    """A network snapshot exactly as src/training/training_loop.py:478-484 pickles it (persistent_class objects), for the small golden networks, with the
+    embedded module SOURCES replaced by a placeholder (reference source code must not enter this repository; 3dgp_b200/legacy.py never reads them)."""
+    import copy
+    import pickle
+    kw = cases.net_kwargs('small')
+    Gc, Dc, m = rh.make_cfg(**kw)
+    G = rh.build_reference_G(Gc, m['img_resolution'], seed=0)
+    D = rh.build_reference_D(Dc, m['patch_res'], use_depth=True, embedding_dim=m['embedding_dim'], seed=1, fp32=True)
+    import gzip
+    for net, tag in ((G, 'G.'), (D, 'D.')):
+        net.load_state_dict({k: torch.from_numpy(cases.snapshot_fill(tag + k, tuple(v.shape))).to(v.dtype) for k, v in net.state_dict().items()})
+    G_ema = copy.deepcopy(G).eval()
+    for net in (G, D, G_ema):
+        for mod in net.modules():
+            if hasattr(type(mod), '_orig_module_src'):
+                type(mod)._orig_module_src = '# module source stripped from the fixture (oracle/make_golden.py::gen_snapshot)'
+    data = dict(G=G, D=D, G_ema=G_ema, augment_pipe=None, training_set_kwargs=dict(path='synthetic', resolution=m['img_resolution'], use_labels=True))
+    with gzip.open(os.path.join(GOLD, 'snapshot_small.pkl.gz'), 'wb') as f:
+        pickle.dump(data, f)
+
+
 def gen_reference_config(ns, report):
     """The experiment configuration the reference's launcher would save for the README's ImageNet-256 command (oracle/compose_config.py)."""
     from oracle import compose_config as cc
@@ -333,7 +355,7 @@ def main():
     only = sys.argv[1:]
     gens = dict(upfirdn2d=gen_upfirdn2d, bias_act=gen_bias_act, filtered_lrelu=gen_filtered_lrelu, render=gen_render, networks=gen_networks,
                 networks_wide=lambda ns_, rep_: gen_networks(ns_, rep_, 'wide'), camera_adaptor=gen_camera_adaptor,
-                reference_config=gen_reference_config)
+                reference_config=gen_reference_config, snapshot=gen_snapshot)
     for name, fn in gens.items():
         if only and name not in only:
             continue

@@ -1,0 +1,63 @@
+"""Reference snapshot pickles load into THIS package's modules without the reference's source tree (3dgp_b200/legacy.py).  The fixture
+tests/golden/snapshot_small.pkl.gz was written by the unmodified reference's persistence machinery (src/torch_utils/persistence.py:99-131, the
+dict layout of training_loop.py:478-484) for the small golden networks, with deterministic low-entropy weights (oracle/cases.py::snapshot_fill) and the
+embedded module sources replaced by a placeholder (oracle/make_golden.py::gen_snapshot).
+Parity note: the fixture's configuration objects are the harness's EasyDicts; a production snapshot carries OmegaConf DictConfig nodes, whose
+`_content` / `_val` layout `legacy.plain` unwraps -- that branch is exercised with hand-built records below, not with a real OmegaConf pickle
+(OmegaConf is not installed here): unpinned for that one conversion."""
+import importlib
+import os
+
+import numpy as np
+import torch
+
+from conftest import ROOT
+from oracle import cases
+
+FIXTURE = os.path.join(ROOT, 'tests', 'golden', 'snapshot_small.pkl.gz')
+
+
+def test_snapshot_networks_load_with_the_reference_weights_and_constructor_arguments():
+    lg = importlib.import_module('3dgp_b200.legacy')
+    cfgm = importlib.import_module('3dgp_b200.config')
+    kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    cfg = cfgm.make_config(**kw)
+    # the reference does not decorate `Discriminator` itself (networks_discriminator.py:201): its constructor record is not in the pickle
+    d_init = ([], dict(cfg=cfg.model.discriminator, input_resolution=cfg.training.patch.resolution, img_channels=4, block_kwargs=dict(freeze_layers=0),
+                       mapping_kwargs={}, epilogue_kwargs=dict(mbstd_group_size=4, feat_predict_dim=cfg.dataset.embedding_dim), num_fp16_res=0, conv_clamp=None))
+    nets = lg.load_network_pkl(FIXTURE, init={'D': d_init})
+    assert set(nets) >= {'G', 'D', 'G_ema', 'training_set_kwargs'}
+    assert nets['training_set_kwargs'] == dict(path='synthetic', resolution=kw['img_resolution'], use_labels=True)
+    G, D, Ge = nets['G'], nets['D'], nets['G_ema']
+    assert type(G).__module__.startswith('3dgp_b200.') and type(D).__module__.startswith('3dgp_b200.')
+    assert not G.training and not any(p.requires_grad for p in G.parameters())
+    # constructor arguments came out of the pickle
+    assert G.img_resolution == kw['img_resolution'] and G.z_dim == kw['z_dim'] and G.cfg.tri_plane.res == kw['tri_res'] and G.cfg.cmax == kw['cmax']
+    for tag, net in (('G.', G), ('D.', D), ('G.', Ge)):
+        sd = net.state_dict()
+        assert len(sd) > 20
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), cases.snapshot_fill(tag + k, tuple(v.shape))), tag + k
+
+
+def test_plain_unwraps_omegaconf_style_records():
+    """DictConfig / ListConfig pickle as their __dict__ with the children under `_content`, value nodes with the payload under `_val`."""
+    lg = importlib.import_module('3dgp_b200.legacy')
+
+    def rec(state):
+        r = lg._record_class('omegaconf.dictconfig', 'DictConfig')()
+        r.__setstate__(state)
+        return r
+    node = rec({'_metadata': object(), '_parent': None, '_content': {'res': rec({'_val': 512, '_metadata': None}), 'mlp': rec({'_content': {'hid_dim': rec({'_val': 64})}}),
+                                                                  'betas': rec({'_content': [rec({'_val': 0.0}), rec({'_val': 0.99})]})}})
+    assert lg.plain(node) == {'res': 512, 'mlp': {'hid_dim': 64}, 'betas': [0.0, 0.99]}
+
+
+def test_snapshot_reader_refuses_arbitrary_globals():
+    """The unpickler never imports classes outside torch / numpy / builtins: anything else becomes an inert record (a snapshot cannot run code here)."""
+    import io
+    import pickle
+    lg = importlib.import_module('3dgp_b200.legacy')
+    payload = pickle.dumps({'x': os.path.join})            # posixpath.join: a global outside the allow-list
+    out = lg._SnapshotUnpickler(io.BytesIO(payload)).load()
+    assert isinstance(out['x'], type) and issubclass(out['x'], lg._Record)

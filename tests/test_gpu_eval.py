@@ -1,0 +1,56 @@
+"""Eval-side pipeline on the GPU: uint8 conversion kernel, the FID2k generator call pattern (metric_utils.py:303-319) and the host -> device prefetcher."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _inf():
+    return importlib.import_module('3dgp_b200.training.inference')
+
+
+@pytest.mark.parametrize('cl', [False, True])
+@pytest.mark.parametrize('shape', [(2, 4, 16, 16), (3, 3, 8, 20), (1, 4, 64, 64)])
+def test_to_uint8_equals_the_reference_expression(shape, cl):
+    """(img[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8) (metric_utils.py:313), bit for bit, NCHW and channels-last inputs."""
+    torch.manual_seed(shape[2])
+    x = torch.randn(shape, device='cuda') * 1.5
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.99999, -5.0], device='cuda')
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = _inf().to_uint8(x)
+    ref = (x[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8)
+    assert y.is_contiguous() and torch.equal(y, ref)
+
+
+def test_generate_uint8_runs_a_snapshot_generator(golden):
+    """Snapshot pickle (reference persistence format) -> this package's G_ema -> the metrics loop's generator call -> uint8 images on the fused path."""
+    lg = importlib.import_module('3dgp_b200.legacy')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    Ge = lg.load_network_pkl(os.path.join(ROOT, 'tests', 'golden', 'snapshot_small.pkl.gz'), device='cuda', names=('G_ema',))['G_ema']
+    kw = cases.net_kwargs('small')
+    t = {k: torch.from_numpy(v).cuda() for k, v in cases.net_inputs(kw).items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    img = _inf().generate_uint8(Ge, t['z'], t['c'], cam, noise_mode='const')
+    B = t['z'].shape[0]
+    assert img.dtype == torch.uint8 and tuple(img.shape) == (B, 3, kw['img_resolution'], kw['img_resolution'])
+    with torch.no_grad():
+        ref = Ge(z=t['z'], c=t['c'], camera_params=cam, camera_angles_cond=cam.angles, noise_mode='const')
+    ref = ref if torch.is_tensor(ref) else ref.img
+    assert torch.equal(img, (ref[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8))
+
+
+def test_prefetch_loader_delivers_every_batch_in_order():
+    inf = _inf()
+    batches = [dict(img=torch.full((4, 3, 8, 8), float(i)), c=torch.arange(4) + 10 * i) for i in range(5)]
+    got = list(inf.PrefetchLoader(iter(batches), 'cuda', depth=2))
+    assert len(got) == 5
+    for i, b in enumerate(got):
+        assert b['img'].is_cuda and torch.equal(b['img'].cpu(), batches[i]['img']) and torch.equal(b['c'].cpu(), batches[i]['c'])
