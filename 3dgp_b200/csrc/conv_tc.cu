@@ -8,8 +8,20 @@
 // coordinates (the padding halo, including negative ones) are zero-filled by the TMA unit, landing in shared memory
 // directly in the 128B-swizzled K-major layout tcgen05.mma consumes.  No im2col buffer exists anywhere.
 // The B operand is the matching [BN couts][64 channels] slab of the [Cout][k*k*Cin] weight matrix (2-D TMA).
-// Pipeline, warp roles and epilogue are those of gemm_tc.cu.
+// 256 threads, warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one lane: tcgen05.mma into TMEM, tcgen05.commit frees
+// the stage), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns per warp).
 #include "tc_common.cuh"
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency); shared by every TMA user of the library.
+gp3d_encode_tiled_fn gp3d_get_encode_tiled() {
+    static gp3d_encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<gp3d_encode_tiled_fn>(p);
+    return fn;
+}
 
 namespace tc {
 

@@ -1,29 +1,9 @@
-"""Tensor-core (tcgen05 / TMEM) contraction ops of lib3dgp_b200: plain TN GEMM and NHWC implicit-GEMM convolution."""
+"""Tensor-core (tcgen05 / TMEM) contraction ops of lib3dgp_b200: NHWC implicit-GEMM convolutions and their weight gradients."""
 import weakref
 
 import torch
 
 from ... import _lib
-
-
-def gemm_bf16_tn(A, B, out=None, accumulate=False):
-    """D[M,N] (+)= A[M,K] @ B[N,K]^T ; A, B bf16 row-major contiguous, D float32.  M % 128 == N % 128 == K % 64 == 0."""
-    L = _lib.lib()
-    _lib.require_cuda(A, 'A')
-    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16:
-        raise RuntimeError('gemm_bf16_tn: operands must be bfloat16')
-    A = A.contiguous(); B = B.contiguous()
-    M, K = A.shape
-    N, K2 = B.shape
-    if K != K2:
-        raise RuntimeError('gemm_bf16_tn: inner dimensions differ')
-    if out is None:
-        out = torch.empty([M, N], dtype=torch.float32, device=A.device)
-        accumulate = False
-    with torch.cuda.device(A.device):
-        rc = L.gp3d_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, 1 if accumulate else 0, _lib.stream_ptr())
-    _lib.check(rc, 'gemm_bf16_tn')
-    return out
 
 
 def conv2d_nhwc_bf16(x, w, out=None, accumulate=False):

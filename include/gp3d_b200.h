@@ -245,12 +245,8 @@ int gp3d_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema,
                        const int* blk_seg, const float* seg_desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Dense contraction on tcgen05 / TMEM (sm_100a):  D[M][N] (+)= A[M][K] * B[N][K]^T, bf16 operands,
- * fp32 accumulate in TMEM, TMA-fed 128B-swizzled smem tiles.  This is the engine under the modulated /
- * discriminator convolutions (implicit GEMM: the conv front-end lays the im2col tiles out through TMA).
- * M % 128 == 0, N % 128 == 0, K % 64 == 0.  A,B row-major bf16 (K contiguous); D row-major float32.
- */
-int gp3d_gemm_bf16_tn(const void* A, const void* B, float* D, int M, int N, int K, int accumulate, void* stream);
+ * Dense contractions on tcgen05 / TMEM (sm_100a): implicit-GEMM convolutions -- bf16 / fp16 operands, fp32 accumulate in TMEM, TMA-fed
+ * 128B-swizzled smem tiles (the conv front-end lays the im2col tiles out through TMA; no im2col buffer exists). */
 
 /* 3x3 / 1x1 stride-1 "same" convolution as an implicit GEMM on tcgen05 (NHWC bf16 activations,
  * weights [Cout][kh][kw][Cin] bf16, fp32 NHWC output; ksize in {1, 3, 5}).  Replaces the cuDNN call of

@@ -38,9 +38,11 @@ def test_generate_uint8_runs_a_snapshot_generator(golden):
     kw = cases.net_kwargs('small')
     t = {k: torch.from_numpy(v).cuda() for k, v in cases.net_inputs(kw).items()}
     cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    Ge.synthesis.renderer.launch_counter = 0          # the stratification jitter is a fresh Philox stream per launch: replay the same one twice
     img = _inf().generate_uint8(Ge, t['z'], t['c'], cam, noise_mode='const')
     B = t['z'].shape[0]
     assert img.dtype == torch.uint8 and tuple(img.shape) == (B, 3, kw['img_resolution'], kw['img_resolution'])
+    Ge.synthesis.renderer.launch_counter = 0
     with torch.no_grad():
         ref = Ge(z=t['z'], c=t['c'], camera_params=cam, camera_angles_cond=cam.angles, noise_mode='const')
     ref = ref if torch.is_tensor(ref) else ref.img
