@@ -422,7 +422,7 @@ def run_train_step(args, rank, world, local):
         # dominant kernel of the step: the stride-1 bf16x3 tcgen05 convolution of the tri-plane decoder (forward + input gradient).
         # `achieved` = ALGORITHMIC convolution FLOPs (2*B*Cout*Cin*k^2*H*W) / live-timed launch duration.
         roofline=dict(bound='tensor', achieved=alg_tf, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s', frac=alg_tf / peaks['bf16_tflops_sustained'],
-                      traffic=traffic, kernel='conv_nhwc_bf16_kernel<128,3>', peak_source=peaks['source'] + ' (sustained bf16 GEMM: kernel timed inside a long step)',
+                      traffic=traffic, kernel='conv_nhwc_bf16_kernel<*,3> (three-term bf16x3 form: 256-wide tiles where Cout % 256 == 0, else 128 / 96)', peak_source=peaks['source'] + ' (sustained bf16 GEMM: kernel timed inside a long step)',
                       launches_timed=len(cev), mean_ms=conv_ms / n_l, algorithmic_flops_per_launch=conv_flops / n_l,
                       # bf16x3 executes three bf16 MMAs per fp32-grade product: tensor-pipe occupancy, NOT the roofline fraction
                       executed_mma_tflops=3.0 * alg_tf, executed_mma_frac_of_peak=3.0 * alg_tf / peaks['bf16_tflops_sustained'],
@@ -442,7 +442,7 @@ def run_train_step(args, rank, world, local):
     return res
 
 
-D_LOW_PRECISION_NAME = 'bf16'
+D_LOW_PRECISION_NAME = 'fp16 x fp16 forward products (bf16 x bf16 for products with a gradient operand)'
 
 
 def ginfer_leg(G_ema, cfg, dev, dn, rank, world, B=64, steps=3):
