@@ -237,7 +237,10 @@ class Trainer:
         self.D_reg_interval = D_reg_interval
         self.ema_kimg, self.ema_rampup, self.batch_size = ema_kimg, ema_rampup, batch_size
         self.micro_batch = micro_batch
-        self.overlap_allreduce = True
+        # Bucketed transfer overlapped with the final backward (GradBuckets).  OFF by default: validated on 2 ranks (gloo on CPU, NCCL on 2 x B200: same
+        # step time as the blocking form) but a 4-rank NCCL run did not complete (profiles/r2_allreduce_overlap.txt) -- the blocking flat all-reduce
+        # of training_loop.py:335-344 is the shipped schedule.
+        self.overlap_allreduce = False
         self._fired = {}         # phase -> parameters that produced gradients in its last final backward (GradBuckets.arm `expected`)
         self.cur_nimg = 0
         self.it = 0

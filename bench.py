@@ -329,7 +329,7 @@ def train_step_config(B, mb, world, small=False):
     return dict(workload=TRAIN_WORKLOAD if not small else 'train_step SMALL (debug)', batch_per_gpu=B, micro_batch=mb, global_batch=B * world,
                 phases='Gmain + Dmain every iteration, Dreg (R1) every 16th', learn_camera_dist=True,
                 l2='activations per layer (>= 134 MB/image at 512^2) larger than the 126 MB L2',
-                parallelism=f'dp{world}: flat gradient all-reduced per phase in 64 MB buckets overlapped with the backward (NCCL)')
+                parallelism=f'dp{world}: one flattened gradient all-reduce per phase (NCCL)')
 
 
 def run_train_step(args, rank, world, local):
@@ -358,7 +358,7 @@ def run_train_step(args, rank, world, local):
     # mid-training state (2500 kimg): density noise at half strength, EMD regulariser of the camera adaptor ramped in (loss.py:64-65)
     G.progressive_update(2500); loss.progressive_update(2500)
     tr = stepm.Trainer(G, D, loss, cfg, rank=rank, world_size=world, D_reg_interval=16, batch_size=B * world, micro_batch=mb)
-    tr.overlap_allreduce = not args.no_overlap
+    tr.overlap_allreduce = bool(args.overlap)
     host = synthetic_batch(cfg, B, dev, seed=rank)
     real, gen = to_step_inputs(host, dev, dn)
     torch.cuda.synchronize()
@@ -678,7 +678,7 @@ def main():
     ap.add_argument('--no-ginfer', action='store_true', help='skip the G-only inference leg (BASELINE configs[4]) of the default run')
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--small', action='store_true')
-    ap.add_argument('--no-overlap', action='store_true', help='one blocking all-reduce of the flat gradient after backward (the reference schedule) instead of overlapped buckets')
+    ap.add_argument('--overlap', action='store_true', help='experimental: 64 MB gradient buckets all-reduced during the final backward of each phase (validated on 2 ranks only)')
     ap.add_argument('--cpu-sample-batch', type=int, default=1, help='images per executed CPU step of the reference arm / cpu_baseline leg')
     args = ap.parse_args()
     rank, world, local = dist_info()
