@@ -231,9 +231,17 @@ extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const 
     const int out_tiles = g.tiles_co * g.tiles_ci * ntaps;
     int sms = GP3D_NUM_SMS, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t splitk = (2 * (int64_t)sms + out_tiles - 1) / out_tiles;
-    if (splitk > ptiles) splitk = ptiles;
-    if (splitk < 1) splitk = 1;
+    // One CTA per SM (197 KB of shared memory): the grid runs in waves of `sms` CTAs and a partial last wave costs a full CTA time.  Choose the split
+    // that minimises waves x (pixel blocks per CTA) -- e.g. 18 output tiles: split 16 (288 CTAs, two full waves) instead of 17 (306 CTAs: a third wave
+    // of 10 CTAs, +50 % time; ncu: tensor pipe 82 % while active but 55 % of the elapsed cycles, profiles/r2_conv_wide_tiles_ncu.txt).
+    int64_t splitk = 1, best = -1;
+    const int64_t smax = ptiles < 4 * (int64_t)sms ? ptiles : 4 * (int64_t)sms;
+    for (int64_t sk = 1; sk <= smax; sk++) {
+        const int64_t waves = (out_tiles * sk + sms - 1) / sms;
+        const int64_t per_cta = (ptiles + sk - 1) / sk;
+        const int64_t cost = waves * (per_cta + 6);      // pixel blocks per CTA + pipeline fill / 128 x WBN red.add epilogue (~6 block times) per wave
+        if (best < 0 || cost < best) { best = cost; splitk = sk; }
+    }
     g.splitk = (int)splitk;
     CUtensorMap tmDh, tmXh, tmDl, tmXl;
     int rc = encode_act_map(&tmDh, dyh, N, Hd, Wd, Cout, g.TW, g.TH, g.TN, sa, who, dy_format); if (rc) return rc;

@@ -10,6 +10,7 @@ Nothing but x, y and the bf16 operand pair is kept for backward; no x*styles / p
 First-order only (the reference differentiates G twice only when pl_weight > 0, which the 3dgp config sets to 0).
 """
 import ctypes
+import os
 
 import torch
 
@@ -34,7 +35,6 @@ def _nhwc(t):
     return t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
 
-import os
 G_TERMS = int(os.environ.get('GP3D_G_TERMS', '3'))     # precision of the tri-plane decoder's forward / input-gradient convolutions: 3 = bf16x3, 2 = x2w16 (ops.tc.operand_formats)
 
 

@@ -70,3 +70,42 @@ class PrefetchLoader:
             v.record_stream(torch.cuda.current_stream(self.device))
         self._stage()
         return dev
+
+
+class GraphedGenerator:
+    """CUDA-graph replay of `generate_uint8` for a fixed batch size: the metrics loop of the reference generates images in batches of
+    `batch_gen = 4` (metric_utils.py:289), where one G forward is ~2 000 kernel launches of a few microseconds each -- launch-bound on the host.
+    The whole call (mapping network, camera adaptor, tri-plane decoder, ray generation + march, depth adaptor, uint8 conversion) is captured once
+    on static input buffers and replayed; inputs are copied into the buffers, the result is the static uint8 output (clone it to keep it).
+    The stratification jitter is a Philox stream keyed by a host-side launch counter, which a graph bakes in: every replay draws the SAME jitter
+    pattern (latents and cameras still differ per batch); pass `fresh_jitter=True` to `__call__` to fall back to the eager path for a call."""
+
+    def __init__(self, G, batch, device=None, warmup=2, **G_kwargs):
+        from ..dnnlib import TensorGroup
+        self.G, self.G_kwargs = G, G_kwargs
+        dev = torch.device(device) if device is not None else next(G.parameters()).device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.z = torch.zeros([batch, G.z_dim], **f32)
+        self.c = torch.zeros([batch, G.c_dim], **f32)
+        self.cam = TensorGroup(angles=torch.zeros([batch, 3], **f32), fov=torch.full([batch], 20.0, **f32), radius=torch.ones([batch], **f32),
+                               look_at=torch.zeros([batch, 3], **f32))
+        self.cam.angles[:, 1] = 1.5707963
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                    # warm-up outside the capture: lazy initialisation, weight-operand caches, allocator pools
+            for _ in range(max(int(warmup), 1)):
+                generate_uint8(G, self.z, self.c, self.cam, **G_kwargs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = generate_uint8(G, self.z, self.c, self.cam, **G_kwargs)
+
+    @torch.no_grad()
+    def __call__(self, z, c, camera_params, fresh_jitter=False):
+        if fresh_jitter:
+            return generate_uint8(self.G, z, c, camera_params, **self.G_kwargs)
+        self.z.copy_(z, non_blocking=True); self.c.copy_(c, non_blocking=True)
+        for k in ('angles', 'fov', 'radius', 'look_at'):
+            self.cam[k].copy_(camera_params[k], non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -51,7 +51,7 @@ class DepthAdaptor(torch.nn.Module):
                     idx = np.arange(n)
                     slope = (1 - n * self.start_p) * 2 / (n * (n - 1))
                     head_idx = torch.from_numpy(np.random.choice(idx, size=(B,), p=idx * slope + self.start_p))
-                else:
-                    head_idx = torch.full([B], n - 1, dtype=torch.int64)
+                else:       # eval: the last head for every sample (networks_depth_adaptor.py:93-94); plain slicing, capturable into a CUDA graph
+                    return outs[:, n - 1] + 0.0 * outs.max()
             return outs[torch.arange(B, device=outs.device), head_idx.to(outs.device)] + 0.0 * outs.max()
         raise NotImplementedError(self.cfg.out_strategy)

@@ -23,7 +23,8 @@ def compute_cam2world_matrix(camera_params):
     look_at = spherical2cartesian(camera_params.look_at[:, 0], camera_params.look_at[:, 1], camera_params.look_at[:, 2])
     fwd = normalize(normalize(look_at - origins))
     B = fwd.shape[0]
-    up = torch.tensor([0, 1, 0], dtype=torch.float, device=fwd.device).expand_as(fwd)
+    up = torch.zeros_like(fwd)          # (0, 1, 0) built on the device: no host -> device copy, so the call can be captured into a CUDA graph
+    up[:, 1] = 1.0
     left = normalize(torch.cross(up, fwd, dim=-1))
     up = normalize(torch.cross(fwd, left, dim=-1))
     rot = torch.eye(4, device=fwd.device).unsqueeze(0).repeat(B, 1, 1)

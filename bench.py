@@ -517,7 +517,11 @@ def run_ginfer(args, rank, world, local):
     d = {k: host[k].to(dev) for k in keys}
     cam = dn.TensorGroup(angles=d['angles'], fov=d['fov'], radius=d['radius'], look_at=d['look_at'])
 
+    gg = inf.GraphedGenerator(G, B, noise_mode='const') if args.graph else None       # CUDA-graph replay of the whole generator call
+
     def step():
+        if gg is not None:
+            return gg(d['z'], d['c'], cam)
         return inf.generate_uint8(G, d['z'], d['c'], cam, noise_mode='const')        # metric_utils.py:306-313 on the fused path
 
     c0 = gp._lib.launch_count
@@ -528,7 +532,7 @@ def run_ginfer(args, rank, world, local):
     def step_e2e():
         dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
         cm = dn.TensorGroup(angles=dd['angles'], fov=dd['fov'], radius=dd['radius'], look_at=dd['look_at'])
-        out_h.copy_(inf.generate_uint8(G, dd['z'], dd['c'], cm, noise_mode='const'), non_blocking=True)
+        out_h.copy_(gg(dd['z'], dd['c'], cm) if gg is not None else inf.generate_uint8(G, dd['z'], dd['c'], cm, noise_mode='const'), non_blocking=True)
 
     ms_e2e, _ = timed_region(step_e2e, args.steps, 1, world)
     fg, _ = conv_flops_per_image(cfg)
@@ -537,7 +541,7 @@ def run_ginfer(args, rank, world, local):
     alg = raymarch_algorithmic_bytes(B, R_, cfg.model.generator.num_ray_steps, 512, 32)
     return dict(metric='G-only inference images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
                 dtype='fp32 (bf16x3 tensor-core convs, 3xTF32 tri-plane MLP)',
-                config=dict(workload='ginfer (BASELINE configs[4]: G-only inference, 256x256 full-frame render)', batch_per_gpu=B,
+                config=dict(workload='ginfer (BASELINE configs[4]: G-only inference, 256x256 full-frame render)', batch_per_gpu=B, cuda_graph=bool(args.graph),
                             rays_per_image=R_, l2='tri-planes of the batch (%.1f GB) larger than the 126 MB L2' % (B * 100.66e6 / 1e9),
                             parallelism=f'replicas x{world} (no collective)'),
                 roofline=dict(bound='tensor', achieved=B * fg / (ms * 1e-3) / 1e12, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s',
@@ -678,6 +682,7 @@ def main():
     ap.add_argument('--no-ginfer', action='store_true', help='skip the G-only inference leg (BASELINE configs[4]) of the default run')
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--small', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='ginfer: replay the generator call as a CUDA graph (training/inference.py::GraphedGenerator)')
     ap.add_argument('--overlap', action='store_true', help='experimental: 64 MB gradient buckets all-reduced during the final backward of each phase (validated on 2 ranks only)')
     ap.add_argument('--cpu-sample-batch', type=int, default=1, help='images per executed CPU step of the reference arm / cpu_baseline leg')
     args = ap.parse_args()

@@ -56,3 +56,24 @@ def test_prefetch_loader_delivers_every_batch_in_order():
     assert len(got) == 5
     for i, b in enumerate(got):
         assert b['img'].is_cuda and torch.equal(b['img'].cpu(), batches[i]['img']) and torch.equal(b['c'].cpu(), batches[i]['c'])
+
+
+def test_cuda_graph_replay_of_the_generator_equals_the_eager_call():
+    """training/inference.py::GraphedGenerator: the captured generator call replayed on new latents / cameras returns the eager result bit for bit
+    (same Philox launch offset), for several batches in a row."""
+    lg = importlib.import_module('3dgp_b200.legacy')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    inf = _inf()
+    Ge = lg.load_network_pkl(os.path.join(ROOT, 'tests', 'golden', 'snapshot_small.pkl.gz'), device='cuda', names=('G_ema',))['G_ema']
+    kw = cases.net_kwargs('small')
+    t = {k: torch.from_numpy(v).cuda() for k, v in cases.net_inputs(kw).items()}
+    B = t['z'].shape[0]
+    gg = inf.GraphedGenerator(Ge, B, noise_mode='const')
+    captured_offset = Ge.synthesis.renderer.launch_counter            # the graph baked this launch's Philox offset in
+    for rep in range(3):
+        z = t['z'] + 0.1 * rep
+        cam = dn.TensorGroup(angles=t['angles'] + 0.01 * rep, fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+        out = gg(z, t['c'], cam).clone()
+        Ge.synthesis.renderer.launch_counter = captured_offset - 1
+        ref = inf.generate_uint8(Ge, z, t['c'], cam, noise_mode='const')
+        assert torch.equal(out, ref), rep
