@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) to_uint8_kernel(const float* __restrict__
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float t = fmaf(src[k * sW], scale, shift);
+            float t = __fadd_rn(__fmul_rn(src[k * sW], scale), shift);      // two roundings, as torch's img * 127.5 + 128 (an FMA differs at x.99999 boundaries)
             t = fminf(fmaxf(t, 0.f), 255.f);
             packed |= (uint32_t)(int)t << (8 * k);                // truncation toward zero
         }

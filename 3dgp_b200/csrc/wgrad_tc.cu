@@ -234,10 +234,12 @@ extern "C" int gp3d_wgrad_taps_nhwc_fmt(const void* dyh, const void* dyl, const 
     // One CTA per SM (197 KB of shared memory): the grid runs in waves of `sms` CTAs and a partial last wave costs a full CTA time.  Choose the split
     // that minimises waves x (pixel blocks per CTA) -- e.g. 18 output tiles: split 16 (288 CTAs, two full waves) instead of 17 (306 CTAs: a third wave
     // of 10 CTAs, +50 % time; ncu: tensor pipe 82 % while active but 55 % of the elapsed cycles, profiles/r2_conv_wide_tiles_ncu.txt).
+    // At most two waves: more CTAs only add red.add traffic (a 7-wave split of the 128-channel 512^2 layer measured 4 % slower than the old 3-wave one).
     int64_t splitk = 1, best = -1;
-    const int64_t smax = ptiles < 4 * (int64_t)sms ? ptiles : 4 * (int64_t)sms;
+    const int64_t smax = ptiles < 2 * (int64_t)sms ? ptiles : 2 * (int64_t)sms;
     for (int64_t sk = 1; sk <= smax; sk++) {
         const int64_t waves = (out_tiles * sk + sms - 1) / sms;
+        if (waves > 2 && sk > 1) break;
         const int64_t per_cta = (ptiles + sk - 1) / sk;
         const int64_t cost = waves * (per_cta + 6);      // pixel blocks per CTA + pipeline fill / 128 x WBN red.add epilogue (~6 block times) per wave
         if (best < 0 || cost < best) { best = cost; splitk = sk; }
