@@ -70,6 +70,7 @@ PROTOTYPES = {
     'gp3d_modulate_bwd': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     'gp3d_grad_epilogue': (c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     'gp3d_conv_set_wide3': (c_int, [c_int]),
+    'gp3d_conv_transpose_s2_nhwc': (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_void_p] + [c_int] * 5 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'gp3d_conv2d_nhwc_bf16x3': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     'gp3d_conv_nhwc': (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),

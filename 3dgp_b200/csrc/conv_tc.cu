@@ -39,6 +39,11 @@ struct ConvGeom {
     int TW, TH, TN;              // pixel tile: TN images x TH rows x TW cols = 128
     int tiles_x, tiles_y, tiles_n, tiles_co;
     int x_fp16, w_fp16;          // operand element formats (0 bf16, 1 fp16)
+    // Phases: up to four tap sub-lists with their own output lattice offset and domain, processed by ONE launch (the polyphase form of the stride-2
+    // transposed convolution: the four launches of one layer re-read the activation tensor from DRAM four times; as phases of one launch the tiles of
+    // one pixel window are scheduled back to back and the re-reads hit L2).  nphases == 1: the plain form (phase 0 = the fields above).
+    int nphases;
+    int ph_ntaps[4], ph_tap0[4], ph_oy0[4], ph_ox0[4], ph_HoP[4], ph_WoP[4];
 };
 
 // Optional fused epilogue of the modulated-conv layer (networks_stylegan2.py:71 fma + :144 bias_act, no clamp):
@@ -76,7 +81,6 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = g.Cin / CBK;
-    const int num_kb = g.ntaps * cblocks;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW); }
     if (warp == 1 && lane == 0) {
@@ -90,9 +94,13 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile decomposition: tile = ((tn * tiles_y + ty) * tiles_x + tx) * tiles_co + tco   (cout fastest: activations reused from L2)
-    auto decode = [&](int t, int& x0, int& y0, int& n0, int& co0) {
+    // tile decomposition: tile = (((tn * tiles_y + ty) * tiles_x + tx) * nphases + phase') * tiles_co + tco   (cout, then phase fastest: activations
+    // reused from L2).  The phase is rotated with the pixel-tile index so that a persistent CTA (stride gridDim.x, a multiple of 4) does not always draw
+    // the same phase -- the phases have 1, 2, 2 and 4 taps.
+    auto decode = [&](int t, int& x0, int& y0, int& n0, int& co0, int& ph) {
         const int tco = t % g.tiles_co; t /= g.tiles_co;
+        ph = 0;
+        if (g.nphases > 1) { const int q = t; t /= g.nphases; ph = (q + t / 37) % g.nphases; }
         const int tx = t % g.tiles_x; t /= g.tiles_x;
         const int ty = t % g.tiles_y; t /= g.tiles_y;
         x0 = tx * g.TW; y0 = ty * g.TH; n0 = t * g.TN; co0 = tco * BN;
@@ -102,11 +110,12 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (lane == 0) {
             uint32_t it = 0;                                  // global k-block counter (ring position)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                int x0, y0, n0, co0;
-                decode(tile, x0, y0, n0, co0);
+                int x0, y0, n0, co0, phs;
+                decode(tile, x0, y0, n0, co0, phs);
+                const int num_kb = g.ph_ntaps[phs] * cblocks, tap0 = g.ph_tap0[phs];
                 for (int kb = 0; kb < num_kb; kb++, it++) {
                     const int st = it % CSTAGES; const uint32_t ph = (it / CSTAGES) & 1;
-                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int tl = kb / cblocks, cb = kb - tl * cblocks, tap = tap0 + tl;
                     const int cx = x0 * g.in_stride + g.tdx[tap], cy = y0 * g.in_stride + g.tdy[tap], slab = g.tslab[tap];
                     mbar_wait(&empty_bar[st], ph ^ 1);
                     unsigned char* sa = tiles + (size_t)st * kStage;
@@ -125,6 +134,9 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+                int x0_, y0_, n0_, co0_, phs;
+                decode(tile, x0_, y0_, n0_, co0_, phs);
+                const int num_kb = g.ph_ntaps[phs] * cblocks;
                 mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * kAccStride;
@@ -151,19 +163,20 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
-            int x0, y0, n0, co0;
-            decode(tile, x0, y0, n0, co0);
+            int x0, y0, n0, co0, phs;
+            decode(tile, x0, y0, n0, co0, phs);
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const int r = q * 32 + lane;                       // pixel index inside the tile: ((n*TH + h)*TW + w)
             const int wl = r % g.TW, hl = (r / g.TW) % g.TH, nl = r / (g.TW * g.TH);
             const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
-            const bool inside = (ix < g.WoP) && (iy < g.HoP) && (nn < g.N);
-            float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + g.oy0)) * g.Wout + (size_t)(ix * g.osx + g.ox0)) * g.Cout + co0;
+            const int oy0 = g.ph_oy0[phs], ox0 = g.ph_ox0[phs];
+            const bool inside = (ix < g.ph_WoP[phs]) && (iy < g.ph_HoP[phs]) && (nn < g.N);
+            float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + oy0)) * g.Wout + (size_t)(ix * g.osx + ox0)) * g.Cout + co0;
             float nz = 0.f;
             const float* drow = nullptr;
             if (ep.enabled && inside) {
-                if (ep.noise) nz = ep.noise[(ep.noise_per_sample ? (size_t)nn * g.Hout * g.Wout : 0) + (size_t)(iy * g.osy + g.oy0) * g.Wout + (size_t)(ix * g.osx + g.ox0)];
+                if (ep.noise) nz = ep.noise[(ep.noise_per_sample ? (size_t)nn * g.Hout * g.Wout : 0) + (size_t)(iy * g.osy + oy0) * g.Wout + (size_t)(ix * g.osx + ox0)];
                 if (ep.dcoef) drow = ep.dcoef + (size_t)nn * g.Cout + co0;
             }
 #pragma unroll 1
@@ -213,7 +226,7 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
     auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { gp3d_set_error("conv2d_nhwc_bf16: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    const int64_t num_tiles = (int64_t)g.tiles_n * g.tiles_y * g.tiles_x * g.tiles_co;
+    const int64_t num_tiles = (int64_t)g.tiles_n * g.tiles_y * g.tiles_x * g.tiles_co * g.nphases;
     int sms = GP3D_NUM_SMS, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t grid = num_tiles < sms ? num_tiles : sms;        // persistent: one CTA per SM
@@ -233,7 +246,9 @@ extern "C" int gp3d_conv_set_wide3(int on) { const int old = g_conv_wide3; g_con
 static int conv_impl(const void* x, const void* xl, const void* w, const void* wl, float* y, int N, int H, int W, int Cin, int Cout,
                      int num_slabs, int ntaps, const int* taps, int in_stride, int HoP, int WoP, int Hout, int Wout,
                      int osy, int osx, int oy0, int ox0, int accumulate, void* stream, const char* who, const gp3d_conv_epilogue* epi = nullptr,
-                     int w_format = 0, int x_format = 0) {
+                     int w_format = 0, int x_format = 0, int nphases = 1, const int* phases = nullptr) {
+    // phases (nphases > 1): nphases x (ntaps, first tap, oy0, ox0, HoP, WoP); the taps of all phases are concatenated in `taps`, HoP / WoP passed to this
+    // function are the LARGEST phase domain (the tile grid), oy0 / ox0 are ignored
     GP3D_CHECK_ARG(x && w && y, "%s: null pointer", who);
     GP3D_CHECK_ARG((w_format == 0 || w_format == 1) && (x_format == 0 || x_format == 1), "%s: operand formats are 0 (bf16) or 1 (fp16)", who);
     GP3D_CHECK_ARG(w_format == x_format, "%s: both operands of a tcgen05 kind::f16 product must have the same element format (got x %d, w %d)", who, x_format, w_format);
@@ -254,8 +269,23 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
         gp3d_set_error("%s: need Cin %% 64 == 0 and Cout %% 128 == 0 (or Cout in {64, 96}); got Cin=%d Cout=%d", who, Cin, Cout);
         return GP3D_E_UNSUPPORTED;
     }
-    GP3D_CHECK_ARG((HoP - 1) * osy + oy0 < Hout && (WoP - 1) * osx + ox0 < Wout, "%s: output lattice exceeds the output tensor", who);
+    GP3D_CHECK_ARG(nphases >= 1 && nphases <= 4 && (nphases == 1 || phases != nullptr), "%s: 1 .. 4 phases", who);
+    GP3D_CHECK_ARG(nphases > 1 || ((HoP - 1) * osy + oy0 < Hout && (WoP - 1) * osx + ox0 < Wout), "%s: output lattice exceeds the output tensor", who);
     tc::ConvGeom g{};
+    g.nphases = nphases;
+    if (nphases == 1) { g.ph_ntaps[0] = ntaps; g.ph_tap0[0] = 0; g.ph_oy0[0] = oy0; g.ph_ox0[0] = ox0; g.ph_HoP[0] = HoP; g.ph_WoP[0] = WoP; }
+    else {
+        int covered = 0;
+        for (int i = 0; i < nphases; i++) {
+            g.ph_ntaps[i] = phases[6 * i]; g.ph_tap0[i] = phases[6 * i + 1]; g.ph_oy0[i] = phases[6 * i + 2]; g.ph_ox0[i] = phases[6 * i + 3];
+            g.ph_HoP[i] = phases[6 * i + 4]; g.ph_WoP[i] = phases[6 * i + 5];
+            GP3D_CHECK_ARG(g.ph_ntaps[i] >= 1 && g.ph_tap0[i] == covered && g.ph_HoP[i] >= 1 && g.ph_HoP[i] <= HoP && g.ph_WoP[i] >= 1 && g.ph_WoP[i] <= WoP,
+                           "%s: bad phase %d", who, i);
+            GP3D_CHECK_ARG((g.ph_HoP[i] - 1) * osy + g.ph_oy0[i] < Hout && (g.ph_WoP[i] - 1) * osx + g.ph_ox0[i] < Wout, "%s: phase %d exceeds the output tensor", who, i);
+            covered += g.ph_ntaps[i];
+        }
+        GP3D_CHECK_ARG(covered == ntaps, "%s: the phases must partition the tap list", who);
+    }
     g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.ntaps = ntaps; g.in_stride = in_stride;
     g.x_fp16 = x_format; g.w_fp16 = w_format;
     for (int t = 0; t < ntaps; t++) { g.tdy[t] = taps[3 * t]; g.tdx[t] = taps[3 * t + 1]; g.tslab[t] = taps[3 * t + 2];
@@ -269,7 +299,7 @@ static int conv_impl(const void* x, const void* xl, const void* w, const void* w
     const bool wide3 = xl && wl && Cout % 256 == 0 && g_conv_wide3;
     const int BN = ((!xl || wide3) && Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : Cout;
     g.tiles_x = (WoP + g.TW - 1) / g.TW; g.tiles_y = (HoP + g.TH - 1) / g.TH; g.tiles_n = (N + g.TN - 1) / g.TN; g.tiles_co = Cout / BN;
-    GP3D_CHECK_ARG((int64_t)g.tiles_x * g.tiles_y * g.tiles_n * g.tiles_co < 2147483647LL, "%s: grid too large", who);
+    GP3D_CHECK_ARG((int64_t)g.tiles_x * g.tiles_y * g.tiles_n * g.tiles_co * nphases < 2147483647LL, "%s: grid too large", who);
     gp3d_encode_tiled_fn enc = gp3d_get_encode_tiled();
     if (!enc) { gp3d_set_error("cuTensorMapEncodeTiled is not available from this driver"); return GP3D_E_UNSUPPORTED; }
     CUtensorMap tmX, tmW, tmXl, tmWl;
@@ -365,4 +395,27 @@ extern "C" int gp3d_conv_nhwc(const gp3d_conv_desc* d, void* stream) {
     GP3D_CHECK_ARG(d->taps != nullptr, "conv_nhwc: null tap list");
     return conv_impl(d->xh, d->xl, d->wh, d->wl, d->y, d->N, d->H, d->W, d->Cin, d->Cout, d->num_slabs, d->ntaps, d->taps, d->in_stride,
                      d->HoP, d->WoP, d->Hout, d->Wout, d->osy, d->osx, d->oy0, d->ox0, d->accumulate, stream, "conv_nhwc", d->epi, d->w_format, d->x_format);
+}
+
+// Stride-2 transposed 3x3 convolution (padding 0): y[n][2i+ky][2j+kx][co] += x[n][i][j][ci] * w[co][ky*3+kx][ci], y = [N][2H+1][2W+1][Cout], as the four
+// polyphase tap convolutions on the input grid in ONE launch (phases of 1, 2, 2 and 4 taps; conv2d_resample.py:113-126 runs this as conv_transpose2d).
+extern "C" int gp3d_conv_transpose_s2_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, int w_format, int x_format, float* y,
+                                           int N, int H, int W, int Cin, int Cout, void* stream) {
+    int taps[27], phases[24], nt = 0, np = 0;
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            const int first = nt;
+            // output row 2i + a: a == 0 -> (input offset 0, ky 0), (-1, ky 2); a == 1 -> (0, ky 1); same along x
+            const int nky = a == 0 ? 2 : 1, nkx = b == 0 ? 2 : 1;
+            for (int iy = 0; iy < nky; iy++)
+                for (int ix = 0; ix < nkx; ix++) {
+                    const int dy = (a == 0 && iy == 1) ? -1 : 0, ky = a == 0 ? (iy == 0 ? 0 : 2) : 1;
+                    const int dx = (b == 0 && ix == 1) ? -1 : 0, kx = b == 0 ? (ix == 0 ? 0 : 2) : 1;
+                    taps[3 * nt] = dy; taps[3 * nt + 1] = dx; taps[3 * nt + 2] = ky * 3 + kx; nt++;
+                }
+            phases[6 * np] = nt - first; phases[6 * np + 1] = first; phases[6 * np + 2] = a; phases[6 * np + 3] = b;
+            phases[6 * np + 4] = H + 1 - a; phases[6 * np + 5] = W + 1 - b; np++;
+        }
+    return conv_impl(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, nt, taps, 1, H + 1, W + 1, 2 * H + 1, 2 * W + 1, 2, 2, 0, 0, 0, stream,
+                     "conv_transpose_s2_nhwc", nullptr, w_format, x_format, 4, phases);
 }

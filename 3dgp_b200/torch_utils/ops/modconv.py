@@ -39,17 +39,12 @@ G_TERMS = int(os.environ.get('GP3D_G_TERMS', '3'))     # precision of the tri-pl
 
 
 def _conv_fwd(xh, xl, wh, wl, N, H, W, Cin, Cout, k, up):
-    """Raw convolution of the up-sampling layers: stride-2 transposed conv as four polyphase tap convolutions -> [N, 2H+1, 2W+1, Cout]."""
+    """Raw convolution of the up-sampling layers: stride-2 transposed conv as four polyphase tap convolutions (phases of one launch) -> [N, 2H+1, 2W+1, Cout]."""
     dev = xh.device
     assert up == 2
     Ho, Wo = 2 * H + 1, 2 * W + 1
     y = torch.empty([N, Ho, Wo, Cout], dtype=torch.float32, device=dev)
-    for a in (0, 1):
-        kys = [(0, 0), (-1, 2)] if a == 0 else [(0, 1)]
-        for b in (0, 1):
-            kxs = [(0, 0), (-1, 2)] if b == 0 else [(0, 1)]
-            taps = [(dy, dx, ky * 3 + kx) for (dy, ky) in kys for (dx, kx) in kxs]
-            tc._taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Ho, Wo, 2, 2, a, b)
+    tc.conv_transpose_s2_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout)
     return y
 
 

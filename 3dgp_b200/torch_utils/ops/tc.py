@@ -173,6 +173,18 @@ def conv_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, H
     _lib.check(rc, what)
 
 
+def conv_transpose_s2_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout):
+    """Stride-2 transposed 3x3 conv (padding 0) -> y [N, 2H+1, 2W+1, Cout]: the four polyphase tap convolutions as phases of ONE launch
+    (gp3d_conv_transpose_s2_nhwc).  wh / wl: [Cout][9][Cin]."""
+    L = _lib.lib()
+    launch = lambda: L.gp3d_conv_transpose_s2_nhwc(xh.data_ptr(), _lib.ptr(xl), wh.data_ptr(), _lib.ptr(wl), 1 if wh.dtype == torch.float16 else 0,
+                                                   1 if xh.dtype == torch.float16 else 0, y.data_ptr(), N, H, W, Cin, Cout, _lib.stream_ptr())
+    flops = 2.0 * N * Cin * Cout * ((H + 1) * (W + 1) + 2 * (H + 1) * W + 2 * H * (W + 1) + 4 * H * W)       # taps x domain of the four phases
+    with torch.cuda.device(y.device):
+        rc = timed(flops, launch) if xl is not None else launch()
+    _lib.check(rc, 'conv_transpose_s2_nhwc')
+
+
 def same_taps(k):
     return [(ky - k // 2, kx - k // 2, ky * k + kx) for ky in range(k) for kx in range(k)]
 
@@ -222,12 +234,15 @@ def conv_transpose2d_s2_forward(x, w, output_padding, terms, x_is_grad=False, w_
     xh, xl, wh, wl = _prep(x, w, 'tr2', lambda w_: w_.permute(1, 2, 3, 0), terms, x_is_grad, w_is_grad)           # [Cout,3,3,Cin]
     alloc = torch.zeros if (output_padding[0] or output_padding[1]) else torch.empty
     y = alloc([N, Hout, Wout, Cout], dtype=torch.float32, device=x.device)
-    for a in (0, 1):
-        kys = [(0, 0), (-1, 2)] if a == 0 else [(0, 1)]         # (input offset, ky)
-        for b in (0, 1):
-            kxs = [(0, 0), (-1, 2)] if b == 0 else [(0, 1)]
-            taps = [(dy, dx, ky * 3 + kx) for (dy, ky) in kys for (dx, kx) in kxs]
-            _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Hout, Wout, 2, 2, a, b)
+    if not (output_padding[0] or output_padding[1]):
+        conv_transpose_s2_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout)
+    else:       # a padded output tensor is larger than 2H+1: the four phases as separate lattice launches
+        for a in (0, 1):
+            kys = [(0, 0), (-1, 2)] if a == 0 else [(0, 1)]         # (input offset, ky)
+            for b in (0, 1):
+                kxs = [(0, 0), (-1, 2)] if b == 0 else [(0, 1)]
+                taps = [(dy, dx, ky * 3 + kx) for (dy, ky) in kys for (dx, kx) in kxs]
+                _taps_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, 9, taps, 1, H + 1 - a, W + 1 - b, Hout, Wout, 2, 2, a, b)
     y = y.permute(0, 3, 1, 2)
     return y if x.dtype == torch.float32 else y.to(x.dtype)
 

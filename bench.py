@@ -410,7 +410,7 @@ def run_train_step(args, rank, world, local):
     if world == 1 and not args.no_gpu_baseline and not args.small:
         gpu_base = gpu_baseline_step(tr, host, dev, dn, args)
     ginfer = None
-    if not args.no_ginfer and not args.small:
+    if world == 1 and not args.no_ginfer and not args.small:      # replicas only: measured at N = 1 (use --workload ginfer under torchrun for N > 1)
         ginfer = ginfer_leg(tr.G_ema, cfg, dev, dn, rank, world)
     res = dict(
         metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,

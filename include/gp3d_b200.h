@@ -295,6 +295,12 @@ typedef struct gp3d_conv_desc {
     const gp3d_conv_epilogue* epi;       /* optional fused epilogue */
 } gp3d_conv_desc;
 int gp3d_conv_nhwc(const gp3d_conv_desc* desc, void* stream);
+/* Stride-2 transposed 3x3 convolution, padding 0 (what conv2d_resample.py:113-126 runs as conv_transpose2d for the up-sampling layers):
+ *   y[n][2i+ky][2j+kx][co] += x[n][i][j][ci] * w[co][ky*3+kx][ci],   y = [N][2H+1][2W+1][Cout] float32 (fully written),
+ * evaluated as its four polyphase tap convolutions (1, 2, 2 and 4 taps) by ONE launch: the phases of a pixel window are scheduled back to back, so the
+ * activation tensor is read from DRAM once instead of four times.  Operands / precision as gp3d_conv_desc (xl / wl / formats). */
+int gp3d_conv_transpose_s2_nhwc(const void* xh, const void* xl, const void* wh, const void* wl, int w_format, int x_format, float* y,
+                                int N, int H, int W, int Cin, int Cout, void* stream);
 /* Tuning switch: 256-wide output-channel tiles for the three-term (bf16x3) form when Cout % 256 == 0 (two-stage ring of 96 KB stages).
  * Returns the previous setting. */
 int gp3d_conv_set_wide3(int on);
