@@ -255,7 +255,9 @@ class Trainer:
         mbs = list(self._micro_batches(real, gen))
         for j, (r_mb, g_mb) in enumerate(mbs):                 # gradient accumulation, training_loop.py:329-330
             # the last backward of the phase streams its gradient buckets into the all-reduce while it is still running
-            arm = (lambda: opt.buckets.arm(self.world_size, expected=self._fired.get(name))) if (self.flat and self.world_size > 1 and self.overlap_allreduce and j == len(mbs) - 1) else None
+            # (never in the first two iterations: first-use kernel loading / allocator growth must not interleave with collectives already spinning on peers)
+            arm = (lambda: opt.buckets.arm(self.world_size, expected=self._fired.get(name))) if (self.flat and self.world_size > 1 and self.overlap_allreduce
+                                                                                                     and self.it >= 2 and j == len(mbs) - 1) else None
             stats = self.loss.accumulate_gradients(phase=name, real_data=r_mb, gen_data=g_mb, gain=gain, cur_nimg=self.cur_nimg, render_opts=render_opts,
                                                    final_backward=arm)
         module.requires_grad_(False)
