@@ -37,15 +37,34 @@ class PersistentStub:
         self.state = meta['state'] or {}
 
 
-_SAFE_PREFIXES = ('torch', 'numpy', 'collections', 'builtins', '_codecs', 'copyreg')
+# Globals a snapshot legitimately needs (tensors, containers, numpy scalars); everything else -- including builtins such as eval / getattr and torch
+# functions outside this list -- unpickles as an inert record.  NOTE: tensor storages are restored by torch.storage._load_from_bytes, i.e. by torch.load on
+# an embedded byte string: a snapshot is as trustworthy as a torch.load of the same file (the reference reads it with plain pickle.load).
+_ALLOWED = {
+    'collections': {'OrderedDict', 'defaultdict'},
+    'copyreg': {'_reconstructor'},
+    '_codecs': {'encode'},
+    'builtins': {'set', 'frozenset', 'slice', 'range', 'complex', 'bytearray', 'bytes', 'object', 'dict', 'list', 'tuple', 'int', 'float', 'str', 'bool'},
+    'torch._utils': {'_rebuild_tensor', '_rebuild_tensor_v2', '_rebuild_parameter', '_rebuild_parameter_with_state'},
+    'torch.storage': {'_load_from_bytes'},
+    'torch': {'Size', 'device', 'FloatStorage', 'HalfStorage', 'BFloat16Storage', 'DoubleStorage', 'LongStorage', 'IntStorage', 'ShortStorage', 'CharStorage',
+              'ByteStorage', 'BoolStorage', 'float32', 'float16', 'bfloat16', 'float64', 'int64', 'int32', 'int16', 'int8', 'uint8', 'bool'},
+    'numpy': {'ndarray', 'dtype'},
+    'numpy.core.multiarray': {'_reconstruct', 'scalar'},
+    'numpy._core.multiarray': {'_reconstruct', 'scalar'},
+}
 
 
 class _SnapshotUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if name == '_reconstruct_persistent_obj' and module.endswith('persistence'):
             return PersistentStub
-        if module.split('.')[0] in _SAFE_PREFIXES:
+        if name in _ALLOWED.get(module, ()):
             return super().find_class(module, name)
+        if module.startswith('torch.nn.modules.'):            # plain torch containers / layers inside the module tree (ModuleList, Sequential, Embedding ...)
+            cls = super().find_class(module, name)
+            if isinstance(cls, type) and issubclass(cls, torch.nn.Module):
+                return cls
         if name == 'EasyDict':
             return EasyDict
         return _record_class(module, name)

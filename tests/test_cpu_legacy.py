@@ -5,6 +5,7 @@ embedded module sources replaced by a placeholder (oracle/make_golden.py::gen_sn
 Parity note: the fixture's configuration objects are the harness's EasyDicts; a production snapshot carries OmegaConf DictConfig nodes, whose
 `_content` / `_val` layout `legacy.plain` unwraps -- that branch is exercised with hand-built records below, not with a real OmegaConf pickle
 (OmegaConf is not installed here): unpinned for that one conversion."""
+import collections
 import importlib
 import os
 
@@ -54,10 +55,13 @@ def test_plain_unwraps_omegaconf_style_records():
 
 
 def test_snapshot_reader_refuses_arbitrary_globals():
-    """The unpickler never imports classes outside torch / numpy / builtins: anything else becomes an inert record (a snapshot cannot run code here)."""
+    """The unpickler resolves only an explicit allow-list of globals (tensor rebuild hooks, containers, numpy scalars, torch.nn module classes): anything
+    else -- os / posixpath functions, builtins such as eval or getattr, other torch functions -- becomes an inert record class instead of being imported."""
     import io
     import pickle
     lg = importlib.import_module('3dgp_b200.legacy')
-    payload = pickle.dumps({'x': os.path.join})            # posixpath.join: a global outside the allow-list
-    out = lg._SnapshotUnpickler(io.BytesIO(payload)).load()
-    assert isinstance(out['x'], type) and issubclass(out['x'], lg._Record)
+    for obj in (os.path.join, eval, getattr, torch.load, torch.hub.load):
+        out = lg._SnapshotUnpickler(io.BytesIO(pickle.dumps({'x': obj}))).load()
+        assert isinstance(out['x'], type) and issubclass(out['x'], lg._Record), obj
+    ok = lg._SnapshotUnpickler(io.BytesIO(pickle.dumps({'t': torch.arange(3.0), 'd': collections.OrderedDict(a=1), 's': {1, 2}}))).load()
+    assert torch.equal(ok['t'], torch.arange(3.0)) and ok['d'] == {'a': 1} and ok['s'] == {1, 2}
