@@ -78,6 +78,8 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint64_t* acc_full = empty_bar + CSTAGES;       // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // epilogue staging: 4 warps x [32 pixel rows][36 floats] (pitch 36: 16-byte aligned rows, conflict-free STS.128 / LDS.128)
+    float* stg_all = reinterpret_cast<float*>(smem + (size_t)CSTAGES * kStage + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = g.Cin / CBK;
@@ -167,10 +169,71 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             decode(tile, x0, y0, n0, co0, phs);
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
+            const int oy0 = g.ph_oy0[phs], ox0 = g.ph_ox0[phs];
+            if (g.TN == 1) {
+                // ---- coalesced epilogue (one image per tile).  A TMEM row is a pixel, so lane i holds 32 channels of pixel i: stored directly, one
+                // instruction scatters 16 bytes into 32 different 128-byte lines (measured: the stores cost 18 % of the 128-channel 512^2 layers and half of
+                // toRGB, profiles/r2_conv_epilogue_stores.txt).  The 32 x 32 chunk is transposed through shared memory instead: 8 lanes write the 128
+                // contiguous bytes of one pixel, a warp instruction covers 4 whole lines.
+                float* stg = stg_all + (size_t)q * 32 * 36;
+                const int cg = lane & 7;                                   // 4-channel group of this lane inside a 32-channel chunk
+                int off[8]; uint32_t in_mask = 0; float nzv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = q * 32 + 4 * i + (lane >> 3);            // pixel of this lane in store instruction i
+                    const int wl = r % g.TW, hl = r / g.TW;
+                    const int ix = x0 + wl, iy = y0 + hl;
+                    const bool in = (ix < g.ph_WoP[phs]) && (iy < g.ph_HoP[phs]) && (n0 < g.N);
+                    in_mask |= (in ? 1u : 0u) << i;
+                    off[i] = ((hl * g.osy) * g.Wout + wl * g.osx) * g.Cout;
+                    nzv[i] = 0.f;
+                    if (ep.enabled && ep.noise && in)
+                        nzv[i] = ep.noise[(ep.noise_per_sample ? (size_t)n0 * g.Hout * g.Wout : 0) + (size_t)(iy * g.osy + oy0) * g.Wout + (size_t)(ix * g.osx + ox0)];
+                }
+                float* ybase = Y + (((size_t)n0 * g.Hout + (size_t)(y0 * g.osy + oy0)) * g.Wout + (size_t)(x0 * g.osx + ox0)) * g.Cout + co0;
+                const float* drow = (ep.enabled && ep.dcoef && n0 < g.N) ? ep.dcoef + (size_t)n0 * g.Cout + co0 : nullptr;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + buf * kAccStride + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    float4 dv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ep.enabled) {
+                        if (drow) dv = *reinterpret_cast<const float4*>(drow + c + 4 * cg);
+                        if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + co0 + c + 4 * cg);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float4 o = *reinterpret_cast<const float4*>(stg + (4 * i + (lane >> 3)) * 36 + 4 * cg);
+                        if (!((in_mask >> i) & 1u)) continue;
+                        if (ep.enabled) {
+                            const float nz = nzv[i];
+                            o.x = fmaf(o.x, dv.x, nz) + bv.x; o.y = fmaf(o.y, dv.y, nz) + bv.y; o.z = fmaf(o.z, dv.z, nz) + bv.z; o.w = fmaf(o.w, dv.w, nz) + bv.w;
+                            if (ep.act == 3) {
+                                o.x = (o.x > 0.f) ? o.x : o.x * ep.alpha; o.y = (o.y > 0.f) ? o.y : o.y * ep.alpha;
+                                o.z = (o.z > 0.f) ? o.z : o.z * ep.alpha; o.w = (o.w > 0.f) ? o.w : o.w * ep.alpha;
+                            }
+                            o.x *= ep.gain; o.y *= ep.gain; o.z *= ep.gain; o.w *= ep.gain;
+                            if (ep.clamp > 0.f) {
+                                o.x = fminf(fmaxf(o.x, -ep.clamp), ep.clamp); o.y = fminf(fmaxf(o.y, -ep.clamp), ep.clamp);
+                                o.z = fminf(fmaxf(o.z, -ep.clamp), ep.clamp); o.w = fminf(fmaxf(o.w, -ep.clamp), ep.clamp);
+                            }
+                        }
+                        float4* dst = reinterpret_cast<float4*>(ybase + off[i] + c + 4 * cg);
+                        if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                        *dst = o;
+                    }
+                    __syncwarp();                                          // the staging rows are rewritten by the next chunk
+                }
+            } else {
+            // ---- several images per tile (tensors smaller than 128 pixels per image): a lane stores its own pixel row
             const int r = q * 32 + lane;                       // pixel index inside the tile: ((n*TH + h)*TW + w)
             const int wl = r % g.TW, hl = (r / g.TW) % g.TH, nl = r / (g.TW * g.TH);
             const int ix = x0 + wl, iy = y0 + hl, nn = n0 + nl;
-            const int oy0 = g.ph_oy0[phs], ox0 = g.ph_ox0[phs];
             const bool inside = (ix < g.ph_WoP[phs]) && (iy < g.ph_HoP[phs]) && (nn < g.N);
             float* yrow = Y + (((size_t)nn * g.Hout + (size_t)(iy * g.osy + oy0)) * g.Wout + (size_t)(ix * g.osx + ox0)) * g.Cout + co0;
             float nz = 0.f;
@@ -207,6 +270,7 @@ conv_nhwc_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     *dst = o;
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);       // this warp's quarter of the buffer is free again
@@ -222,7 +286,7 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMa
                 int accumulate, cudaStream_t s, const ConvEpi& ep) {
     constexpr int CSTAGES = (TERMS == 3) ? (BN == 256 ? 2 : 3) : (TERMS == 2 && BN == 256) ? 3 : 4;
     constexpr uint32_t kStage = (CBM + BN) * CBK * 2 * (TERMS == 3 ? 2 : 1) + (TERMS == 2 ? CBM * CBK * 2 : 0);
-    const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256;
+    const size_t smem = 1024 + (size_t)CSTAGES * kStage + 256 + 4 * 32 * 36 * sizeof(float);      // ring + barriers + epilogue staging
     auto kern = conv_nhwc_bf16_kernel<BN, TERMS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { gp3d_set_error("conv2d_nhwc_bf16: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
