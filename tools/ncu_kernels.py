@@ -56,12 +56,22 @@ ema = torch.nn.Linear(8192, 8192, bias=False).to(dev).requires_grad_(False)
 opt = stepm.FlatAdam(net, lr=2e-3, betas=(0.0, 0.99), ema_module=ema)
 opt.zero_grad(); opt.flat_g.normal_(); opt.active.update(range(len(opt.params)))
 opt.step(ema_beta=0.99)
-# ray-march forward + backward, config 3 at B=8
+# toRGB of the 512^2 block: 128 -> 96 channels, 1x1, bf16x3 with the fused epilogue (store-heavy: 2 k-blocks per 48 KB output tile)
+N, H, C, Co = B, 512, 128, 96
+x = torch.randn(N, H, H, C, device=dev); w = torch.randn(Co, 1, 1, C, device=dev) / 12
+xh, xl = tc.split_bf16(x); wh, wl = tc.split_bf16(w)
+y = torch.empty(N, H, H, Co, device=dev)
+bb = torch.zeros(Co, device=dev)
+epi = _lib.ConvEpilogue(None, None, bb.data_ptr(), 0, 1, 0.2, 1.0)
+_lib.check(L.gp3d_conv2d_nhwc_bf16x3_act(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), y.data_ptr(), N, H, H, C, Co, 1, ctypes.byref(epi), s), 'torgb')
+# ray-march forward + backward, config 3 at B=8 (rays generated in the kernel)
+dn = importlib.import_module('3dgp_b200.dnnlib'); ru = importlib.import_module('3dgp_b200.training.rendering_utils')
 inp = bench.raymarch_inputs(B, dev, seed=0)
 dd = {k: (v.to(dev) if k != 'planes' else v) for k, v in inp.items()}
 pl = rmod.planes_channel_minor(dd['planes']).requires_grad_(True)
 ws = [dd[k].clone().requires_grad_(True) for k in ('w1', 'b1', 'w2', 'b2')]
-rgb, depth, _, _ = rmod.render_rays(pl, *ws, dd['ray_o'], dd['ray_d'], num_steps=48, ray_start=0.75, ray_end=1.25, box_size=1.0, density_noise=0.5, seed=1, mlp_mode=2)
+c2w = ru.compute_cam2world_matrix(dn.TensorGroup(angles=dd['angles'], radius=torch.ones(B, device=dev), look_at=dd['look_at']))
+rgb, depth, _, _ = rmod.render_camera(pl, *ws, c2w, dd['fov'], (64, 64), num_steps=48, ray_start=0.75, ray_end=1.25, box_size=1.0, density_noise=0.5, seed=1, mlp_mode=2)
 torch.autograd.grad([rgb, depth], [pl] + ws, [torch.ones_like(rgb), torch.ones_like(depth)])
 torch.cuda.synchronize()
 print('done')
