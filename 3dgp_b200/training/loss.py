@@ -5,8 +5,10 @@ Phases: Gmain, Dmain, Dreg (lazy R1) exactly as training_loop.py:321-331 drives 
 (:142-232): Lipschitz (off in 3dgp.yaml), earth-mover distance between prior and posterior per camera coordinate, and the pull of the mean
 origin angles to the prior mean.  The reference calls POT (`ot.dist` + `ot.emd2`, environment.yml:38, unpinned version) for the EMD; POT is not
 installed here, so the term is restated: for two equally weighted 1-D samples of the same size and a convex cost the optimal plan matches
-order statistics, hence emd2 == mean((sort(a) - sort(b))^2), differentiated with the plan held fixed exactly as `ot.emd2` does.
-PARITY UNPINNED for this one term (no POT to compare against)."""
+order statistics, hence emd2 == mean((sort(a) - sort(b))^2), differentiated with the plan held fixed exactly as `ot.emd2` does (`emd2_1d`).
+POT itself is absent, so the term is pinned against an independent EXACT solver of the same transport problem instead (uniform weights and equal
+sample counts make it an assignment problem: scipy's `linear_sum_assignment` on the squared-distance matrix `ot.dist` builds; value and gradient,
+tests/test_cpu_oracle.py::test_emd_restatement_equals_the_exact_assignment_solution)."""
 import numpy as np
 import torch
 
@@ -25,6 +27,13 @@ def maybe_blur(img, blur_sigma):
         f = torch.arange(-blur_size, blur_size + 1, device=img.device).div(blur_sigma).square().neg().exp2()
         img = upfirdn2d.filter2d(img, f / f.sum())
     return img
+
+
+def emd2_1d(a, b):
+    """Per-column squared-Euclidean earth-mover distance between two equally weighted samples a, b [n, k] -> [1, k]: what
+    `ot.emd2(1/n, 1/n, ot.dist(a[:, [i]], b[:, [i]]))` returns for every column i (loss.py:195-197).  On the line the monotone (sorted) matching is
+    optimal for a convex cost; autograd through the gather keeps the plan fixed, like POT's gradient of emd2 with respect to the cost matrix."""
+    return (a.sort(dim=0).values - b.sort(dim=0).values).square().mean(dim=0, keepdim=True)
 
 
 class StyleGAN2Loss:
@@ -88,7 +97,7 @@ class StyleGAN2Loss:
             total = total + lip
         if ccfg.emd.enabled and self.emd_multiplier > 0.0:                                                             # :182-216
             prior_raw, post_raw = prior_posterior(ccfg.emd.num_samples)
-            emd = (post_raw.sort(dim=0).values - prior_raw.detach().sort(dim=0).values).square().mean(dim=0, keepdim=True)   # [1, 8], see the module docstring
+            emd = emd2_1d(post_raw, prior_raw.detach())   # [1, 8]; the prior sample is a leaf without parameters behind it
             emd = self.emd_multiplier * weighted(emd, (ccfg.emd.origin, ccfg.emd.radius, ccfg.emd.fov, ccfg.emd.look_at))
             stats['Loss/camera_dist/emd_loss'] = emd.detach()
             total = total + emd
