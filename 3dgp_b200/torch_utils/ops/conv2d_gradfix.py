@@ -80,8 +80,10 @@ def no_weight_gradients(disable=True):
     old = weight_gradients_disabled
     if disable:
         weight_gradients_disabled = True
-    yield
-    weight_gradients_disabled = old
+    try:
+        yield
+    finally:        # an exception inside the block must not leave weight gradients off for the rest of the run
+        weight_gradients_disabled = old
 
 
 def _tuple2(v):
