@@ -20,6 +20,12 @@ def split(x_nhwc, styles=None, want_lo=True, pad_to=None, fp16=False):
     return x, (torch.zeros_like(x) if want_lo else None)
 
 
+def _sum(hi, lo):
+    """hi (+ lo) as a float64 array: operand pairs are summed in float64 (they may be bf16 tensors written by the emulated backward kernels)."""
+    v = hi.to(torch.float64)
+    return (v + lo.to(torch.float64) if lo is not None else v).numpy()
+
+
 def _shifted(x, dy, dx, stride, HoP, WoP):
     """x[n][iy*stride+dy][ix*stride+dx][:] for (iy, ix) in [0,HoP) x [0,WoP), zero outside the tensor -> [N, HoP, WoP, C]."""
     N, H, W, C = x.shape
@@ -35,8 +41,8 @@ def _shifted(x, dy, dx, stride, HoP, WoP):
 def conv_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0, epi=None, what=''):
     """y[n][iy*osy+oy0][ix*osx+ox0][co] = sum_t sum_ci x[n][iy*in_stride+dy_t][ix*in_stride+dx_t][ci] * w[co][slab_t][ci]  (gp3d_conv_taps_nhwc)."""
     assert epi is None, 'the fused epilogue is not part of the tap algebra under test'
-    x = (xh + (xl if xl is not None else 0)).numpy().reshape(N, H, W, Cin)
-    w = (wh + (wl if wl is not None else 0)).numpy().reshape(Cout, slabs, Cin)
+    x = _sum(xh, xl).reshape(N, H, W, Cin)
+    w = _sum(wh, wl).reshape(Cout, slabs, Cin)
     assert tuple(y.shape) == (N, Hout, Wout, Cout)
     acc = np.zeros([N, HoP, WoP, Cout], dtype=np.float64)
     for (dy, dx, slab) in taps:
@@ -48,8 +54,8 @@ def conv_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, H
 
 def conv_transpose_s2_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout):
     """y[n][2i+ky][2j+kx][co] += x[n][i][j][ci] * w[co][ky*3+kx][ci], y [N][2H+1][2W+1][Cout] fully written  (gp3d_conv_transpose_s2_nhwc)."""
-    x = (xh + (xl if xl is not None else 0)).numpy().reshape(N, H, W, Cin)
-    w = (wh + (wl if wl is not None else 0)).numpy().reshape(Cout, 9, Cin)
+    x = _sum(xh, xl).reshape(N, H, W, Cin)
+    w = _sum(wh, wl).reshape(Cout, 9, Cin)
     out = np.zeros([N, 2 * H + 1, 2 * W + 1, Cout], dtype=np.float64)
     for ky in range(3):
         for kx in range(3):
@@ -59,8 +65,8 @@ def conv_transpose_s2_launch(xh, xl, wh, wl, y, N, H, W, Cin, Cout):
 
 def wgrad_launch(dh, dl, xh, xl, dW, N, Hd, Wd, Cy, Hx, Wx, Cx, slabs, taps, sa, sb, HoP, WoP):
     """dW[co][slab_t][ci] += sum_{n,iy,ix} dy[n][iy*sa+ay_t][ix*sa+ax_t][co] * x[n][iy*sb+by_t][ix*sb+bx_t][ci]  (gp3d_wgrad_taps_nhwc_fmt)."""
-    d = (dh + (dl if dl is not None else 0)).numpy().reshape(N, Hd, Wd, Cy)
-    x = (xh + (xl if xl is not None else 0)).numpy().reshape(N, Hx, Wx, Cx)
+    d = _sum(dh, dl).reshape(N, Hd, Wd, Cy)
+    x = _sum(xh, xl).reshape(N, Hx, Wx, Cx)
     assert tuple(dW.shape) == (Cy, slabs, Cx)
     acc = dW.to(torch.float64).numpy().copy()
     for (ay, ax, by, bx, slab) in taps:
@@ -68,3 +74,136 @@ def wgrad_launch(dh, dl, xh, xl, dW, N, Hd, Wd, Cy, Hx, Wx, Cx, slabs, taps, sa,
         b = _shifted(x, by, bx, sb, HoP, WoP).reshape(-1, Cx)
         acc[:, slab, :] += a.T @ b
     dW.copy_(torch.from_numpy(acc).to(dW.dtype))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Pointer-level entry points used by the fused layer nodes (3dgp_b200/torch_utils/ops/modconv.py).  CPU tensors hand out host addresses from
+# data_ptr(), so the same ctypes call sites can be served by numpy views of those addresses.
+import ctypes
+
+
+def _f32(ptr, *shape):
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_float)), shape=(n,)).reshape(shape)
+
+
+def _store_bf16_pair(hi_ptr, lo_ptr, v, C_pad):
+    """v [..., C] float64 -> bf16 (hi, lo) with hi + lo ~= v, zero-padded to C_pad channels (gp3d_split_pad / *_bwd_split contract)."""
+    lead, C = v.shape[:-1], v.shape[-1]
+    full = np.zeros(list(lead) + [C_pad], dtype=np.float32); full[..., :C] = v
+    t = torch.from_numpy(full)
+    hi = t.to(torch.bfloat16)
+    n = full.size
+    np.ctypeslib.as_array(ctypes.cast(int(hi_ptr), ctypes.POINTER(ctypes.c_int16)), shape=(n,))[:] = hi.view(torch.int16).numpy().reshape(-1)
+    if lo_ptr:
+        lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+        np.ctypeslib.as_array(ctypes.cast(int(lo_ptr), ctypes.POINTER(ctypes.c_int16)), shape=(n,))[:] = lo.view(torch.int16).numpy().reshape(-1)
+
+
+def _act(v, act, alpha, gain, clamp):
+    alpha, gain, clamp = float(np.float32(alpha)), float(np.float32(gain)), float(np.float32(clamp))       # `float` parameters of the C ABI
+    if act == 3:
+        v = np.where(v > 0, v, v * alpha)
+    else:
+        assert act == 1
+    v = v * gain
+    return np.clip(v, -clamp, clamp) if clamp > 0 else v
+
+
+def _epilogue(v, epi, N, H, W, C):
+    """act(v * dcoef[n][c] + noise[n?][y][x] + bias[c]) * gain on v [N, H, W, C]  (gp3d_conv_epilogue)."""
+    if epi.dcoef:
+        v = v * _f32(epi.dcoef, N, 1, 1, C)
+    if epi.noise:
+        v = v + (_f32(epi.noise, N, H, W, 1) if epi.noise_per_sample else _f32(epi.noise, 1, H, W, 1))
+    if epi.bias:
+        v = v + _f32(epi.bias, 1, 1, 1, C)
+    return _act(v, epi.act, epi.alpha, epi.gain, epi.clamp)
+
+
+def conv_launch_epi(xh, xl, wh, wl, y, N, H, W, Cin, Cout, slabs, taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0, epi=None, what=''):
+    """conv_launch with the optional fused epilogue; operands may be bf16 pairs written by the emulated backward kernels (summed in float64)."""
+    x, w = torch.from_numpy(_sum(xh, xl)), torch.from_numpy(_sum(wh, wl))
+    yn = y if y.dim() == 4 and tuple(y.shape) == (N, Hout, Wout, Cout) else y.permute(0, 2, 3, 1)      # _ConvBiasAct passes an NCHW-shaped channels-last tensor
+    tmp = torch.zeros([N, Hout, Wout, Cout], dtype=torch.float64)
+    conv_launch(x, None, w, None, tmp, N, H, W, Cin, Cout, slabs, taps, in_stride, HoP, WoP, Hout, Wout, osy, osx, oy0, ox0)
+    v = tmp.numpy()
+    if epi is not None:
+        assert (HoP, WoP, osy, osx, oy0, ox0) == (Hout, Wout, 1, 1, 0, 0)
+        v = _epilogue(v, epi, N, Hout, Wout, Cout)
+    yn.copy_(torch.from_numpy(v).to(y.dtype))
+
+
+class FakeLib:
+    """Stands in for the ctypes CDLL: the entry points ops/modconv.py calls directly, served from host memory per include/gp3d_b200.h."""
+
+    def __getattr__(self, name):            # anything else (bias_act, upfirdn2d, ...) is not part of the node under test
+        raise AttributeError(f'abi_emulator.FakeLib: {name} is not emulated')
+
+    @staticmethod
+    def gp3d_fir4_nhwc(x, f, flip, gain, N, H, W, C, padx0, padx1, pady0, pady1, y, hi, lo, epi, stream):
+        from oracle import restated as R
+        xv = _f32(x, N, H, W, C).astype(np.float64)
+        fv = _f32(f, 4, 4).astype(np.float32)
+        out = R.upfirdn2d(np.ascontiguousarray(xv.transpose(0, 3, 1, 2)), fv, up=1, down=1, padding=[padx0, padx1, pady0, pady1], flip_filter=bool(flip), gain=gain)
+        out = np.asarray(out, dtype=np.float64).transpose(0, 2, 3, 1)
+        Ho, Wo = H + pady0 + pady1 - 3, W + padx0 + padx1 - 3
+        assert out.shape == (N, Ho, Wo, C)
+        if y:
+            e = getattr(epi, '_obj', None)        # ctypes.byref(struct) keeps the structure in _obj; None = no epilogue
+            if e is not None:
+                out = _epilogue(out, e, N, Ho, Wo, C)
+            _f32(y, N, Ho, Wo, C)[:] = out
+        else:
+            _store_bf16_pair(hi, lo, out, C)
+        return 0
+
+    @staticmethod
+    def gp3d_demod_act_bwd_split(dy, y, d, noise, noise_scale, nps, b, dc, dc_hi, dc_lo, C_pad, g_d, g_b, g_ns, N, HW, C, act, alpha, gain, stream):
+        dyv, yv = _f32(dy, N, HW, C).astype(np.float64), _f32(y, N, HW, C).astype(np.float64)
+        slope = np.where(yv > 0, 1.0, alpha) if act == 3 else np.ones_like(yv)
+        dt = dyv * gain * slope
+        dv = _f32(d, N, 1, C).astype(np.float64) if d else np.ones([N, 1, C])
+        dcv = dt * dv
+        if g_b:
+            _f32(g_b, C)[:] += dt.sum(axis=(0, 1))
+        nz = None
+        if noise:
+            nz = (_f32(noise, N, HW, 1) if nps else _f32(noise, 1, HW, 1)).astype(np.float64)
+            if g_ns:
+                _f32(g_ns, 1)[:] += (dt * nz).sum()
+        if g_d:      # the pre-demodulation conv value rebuilt from the saved output: y = act(c*d + noise*ns + b) * gain
+            t = yv / gain / slope
+            if nz is not None:
+                t = t - nz * float(_f32(noise_scale, 1)[0])
+            if b:
+                t = t - _f32(b, 1, 1, C)
+            _f32(g_d, N, C)[:] += (dt * (t / dv)).sum(axis=1)
+        if dc:
+            _f32(dc, N, HW, C)[:] = dcv
+        else:
+            _store_bf16_pair(dc_hi, dc_lo, dcv, C_pad)
+        return 0
+
+    @staticmethod
+    def gp3d_act_bwd_split(dy, y, dc, dc_hi, dc_lo, C_pad, g_b, N, HW, C, act, alpha, gain, clamp, stream):
+        alpha, gain, clamp = float(np.float32(alpha)), float(np.float32(gain)), float(np.float32(clamp))   # `float` parameters: a clipped y equals float32(clamp)
+        dyv, yv = _f32(dy, N, HW, C).astype(np.float64), _f32(y, N, HW, C).astype(np.float64)
+        slope = np.where(yv > 0, 1.0, alpha) if act == 3 else np.ones_like(yv)
+        dt = dyv * gain * slope
+        if clamp > 0:
+            dt = np.where(np.abs(yv) < clamp, dt, 0.0)
+        if g_b:
+            _f32(g_b, C)[:] += dt.sum(axis=(0, 1))
+        if dc:
+            _f32(dc, N, HW, C)[:] = dt
+        else:
+            _store_bf16_pair(dc_hi, dc_lo, dt, C_pad)
+        return 0
+
+    @staticmethod
+    def gp3d_modulate_bwd(dxs, x, s, dx, g_s, N, HW, C, stream):
+        d, xv, sv = _f32(dxs, N, HW, C).astype(np.float64), _f32(x, N, HW, C).astype(np.float64), _f32(s, N, 1, C).astype(np.float64)
+        _f32(dx, N, HW, C)[:] = d * sv
+        _f32(g_s, N, C)[:] += (d * xv).sum(axis=1)
+        return 0
