@@ -65,6 +65,9 @@ class PrefetchLoader:
         if not self.queue:
             raise StopIteration
         dev, ev, _pinned = self.queue.pop(0)
+        # host wait first: once a batch is handed out its pinned source is free again -- a producer that recycles a ring of pinned buffers
+        # (training/dataset.py::BatchStream, ring length >= depth + 1) may refill it.  The copy was issued `depth` iterations ago: this does not stall.
+        ev.synchronize()
         torch.cuda.current_stream(self.device).wait_event(ev)
         for v in dev.values():
             v.record_stream(torch.cuda.current_stream(self.device))

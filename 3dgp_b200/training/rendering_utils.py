@@ -72,6 +72,15 @@ def sample_camera_params(cfg, batch_size, device='cpu', origin_angles=None):
     return TensorGroup(angles=angles, fov=fov, radius=radius, look_at=look_at)
 
 
+def get_mean_sampling_value(cfg):
+    """Mean of a scalar prior (rendering_utils.py:170-176): fov, origin radius."""
+    if cfg.dist in ('normal', 'truncnorm'):
+        return cfg.mean
+    if cfg.dist == 'uniform':
+        return (cfg.max + cfg.min) / 2
+    raise NotImplementedError(f'mean of distribution `{cfg.dist}`')
+
+
 def get_mean_angles_values(angles_cfg):
     """Mean (yaw, pitch, roll) of an origin-angle prior (rendering_utils.py:180-190)."""
     if angles_cfg.dist == 'normal':

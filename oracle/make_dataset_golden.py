@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY (build container): writes the tiny training-set fixture and what the UNMODIFIED reference reads from it.
+
+    python oracle/make_dataset_golden.py
+
+  tests/golden/tiny_dataset.zip          12 RGB PNGs (16 x 16) in two class folders + dataset.json (labels, camera angles), the layout dataset_tool.py writes
+  tests/golden/dataset_golden.npz        items of src/training/dataset.py::ImageFolderDataset (mirror on / off, max_size subset, custom-angle statistics) and
+                                         index sequences of src/torch_utils/misc.py::InfiniteSampler for several (rank, replicas, seed)
+The reference decodes depth maps with pyspng, which is not installed here: depth decoding is not part of this golden."""
+import io
+import json
+import os
+import sys
+import zipfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+ZIP = os.path.join(GOLD, 'tiny_dataset.zip')
+
+
+def dataset_cfg(mirror, dist='uniform', c_dim=3):
+    return dict(c_dim=c_dim, use_embeddings=False, mirror=mirror,
+                camera=dict(fov=dict(dist='uniform', min=10.0, max=45.0),
+                            origin=dict(radius=dict(dist='normal', mean=1.0, std=0.0),
+                                        angles=dict(dist=dist, yaw=dict(min=-1.57, max=1.57, mean=0.0, std=0.4),
+                                                    pitch=dict(min=0.785398163, max=2.35619449, mean=1.57, std=0.2)))))
+
+
+def write_fixture():
+    import PIL.Image
+    rs = np.random.RandomState(20240)
+    labels, angles = [], []
+    with zipfile.ZipFile(ZIP, 'w', zipfile.ZIP_STORED) as z:
+        for i in range(12):
+            name = f'{i % 3:05d}/img{i:08d}.png'
+            img = rs.randint(0, 256, size=(16, 16, 3)).astype(np.uint8)
+            b = io.BytesIO(); PIL.Image.fromarray(img, 'RGB').save(b, format='png', compress_level=0, optimize=False)
+            z.writestr(zipfile.ZipInfo(name, date_time=(2020, 1, 1, 0, 0, 0)), b.getvalue())
+            labels.append([name, int(i % 3)])
+            angles.append([name, [float(rs.uniform(-1.5, 1.5)), float(rs.uniform(0.8, 2.3)), 0.0]])
+        z.writestr(zipfile.ZipInfo('dataset.json', date_time=(2020, 1, 1, 0, 0, 0)), json.dumps(dict(labels=labels, camera_angles=angles)))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    write_fixture()
+    ns = ref_harness.load()
+    sys.path.insert(0, ref_harness.REF_ROOT)
+    from src.training.dataset import ImageFolderDataset
+    from src.torch_utils.misc import InfiniteSampler
+    out = {}
+    variants = {'plain': dict(cfg=dataset_cfg(False)), 'mirror': dict(cfg=dataset_cfg(True)), 'subset': dict(cfg=dataset_cfg(True), max_size=7, random_seed=3),
+                'custom': dict(cfg=dataset_cfg(True, dist='custom'))}
+    for tag, kw in variants.items():
+        kw = dict(kw); kw['cfg'] = ns.dnnlib.EasyDict.init_recursively(kw['cfg'])
+        ds = ImageFolderDataset(path=ZIP, resolution=16, use_depth=False, **kw)
+        out[f'{tag}/len'] = np.int64(len(ds))
+        out[f'{tag}/image_shape'] = np.array(ds.image_shape)
+        out[f'{tag}/label_shape'] = np.array(ds.label_shape)
+        out[f'{tag}/mean_camera_params'] = np.asarray(ds.mean_camera_params, dtype=np.float64)
+        out[f'{tag}/num_classes'] = np.int64(ds.compute_num_classes())
+        items = [ds[i] for i in range(len(ds))]
+        for k in ('image', 'label', 'camera_angles', 'depth', 'embedding'):
+            out[f'{tag}/{k}'] = np.stack([it[k] for it in items])
+        out[f'{tag}/raw_idx'] = np.array([ds.get_details(i).raw_idx for i in range(len(ds))])
+        out[f'{tag}/xflip'] = np.array([ds.get_details(i).xflip for i in range(len(ds))])
+        if tag == 'mirror':
+            for (rank, rep, seed, shuffle) in [(0, 1, 0, True), (1, 2, 0, True), (3, 4, 7, True), (0, 2, 5, False)]:
+                # torch >= 2.2 dropped Sampler.__init__(data_source), which the reference's constructor still calls (misc.py:118): set the fields it
+                # would set and run its UNMODIFIED __iter__
+                smp = InfiniteSampler.__new__(InfiniteSampler)
+                smp.dataset, smp.rank, smp.num_replicas, smp.shuffle, smp.seed, smp.window_size = ds, rank, rep, shuffle, seed, 0.5
+                it = iter(smp)
+                out[f'sampler/{rank}_{rep}_{seed}_{int(shuffle)}'] = np.array([int(next(it)) for _ in range(100)])
+        ds.close()
+    np.savez_compressed(os.path.join(GOLD, 'dataset_golden.npz'), **out)
+    print('wrote', ZIP, os.path.getsize(ZIP), 'bytes;', len(out), 'golden arrays')
+
+
+if __name__ == '__main__':
+    main()

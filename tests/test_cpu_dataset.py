@@ -1,0 +1,143 @@
+"""Training-set reader (3dgp_b200/training/dataset.py) against what the UNMODIFIED reference reads from the same files
+(tests/golden/dataset_golden.npz, written by oracle/make_dataset_golden.py through src/training/dataset.py::ImageFolderDataset and
+src/torch_utils/misc.py::InfiniteSampler).  Byte / index work: every comparison is bit-exact."""
+import importlib
+import io
+import json
+import os
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+dsmod = importlib.import_module('3dgp_b200.training.dataset')
+dn = importlib.import_module('3dgp_b200.dnnlib')
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+ZIP = os.path.join(GOLD, 'tiny_dataset.zip')
+
+
+def _cfg(mirror, dist='uniform', c_dim=3):
+    return dn.EasyDict.init_recursively(dict(
+        c_dim=c_dim, use_embeddings=False, mirror=mirror,
+        camera=dict(fov=dict(dist='uniform', min=10.0, max=45.0),
+                    origin=dict(radius=dict(dist='normal', mean=1.0, std=0.0),
+                                angles=dict(dist=dist, yaw=dict(min=-1.57, max=1.57, mean=0.0, std=0.4),
+                                            pitch=dict(min=0.785398163, max=2.35619449, mean=1.57, std=0.2))))))
+
+
+VARIANTS = {'plain': dict(cfg=_cfg(False)), 'mirror': dict(cfg=_cfg(True)), 'subset': dict(cfg=_cfg(True), max_size=7, random_seed=3),
+            'custom': dict(cfg=_cfg(True, dist='custom'))}
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(GOLD, 'dataset_golden.npz'))
+
+
+@pytest.mark.parametrize('tag', sorted(VARIANTS))
+def test_items_equal_the_reference_bit_for_bit(gold, tag):
+    ds = dsmod.ImageFolderDataset(path=ZIP, resolution=16, use_depth=False, **VARIANTS[tag])
+    assert len(ds) == int(gold[f'{tag}/len'])
+    assert ds.image_shape == list(gold[f'{tag}/image_shape']) and ds.label_shape == list(gold[f'{tag}/label_shape'])
+    assert ds.resolution == 16 and ds.num_channels == 3 and ds.has_labels and ds.has_onehot_labels and ds.label_dim == 3
+    assert ds.compute_num_classes() == int(gold[f'{tag}/num_classes']) and ds.name == 'tiny_dataset'
+    np.testing.assert_array_equal(np.asarray(ds.mean_camera_params, dtype=np.float64), gold[f'{tag}/mean_camera_params'])
+    items = [ds[i] for i in range(len(ds))]
+    for k in ('image', 'label', 'camera_angles', 'depth', 'embedding'):
+        got = np.stack([it[k] for it in items])
+        assert got.dtype == gold[f'{tag}/{k}'].dtype and got.shape == gold[f'{tag}/{k}'].shape, k
+        np.testing.assert_array_equal(got, gold[f'{tag}/{k}'], err_msg=k)
+    np.testing.assert_array_equal([ds.get_details(i).raw_idx for i in range(len(ds))], gold[f'{tag}/raw_idx'])
+    np.testing.assert_array_equal([ds.get_details(i).xflip for i in range(len(ds))], gold[f'{tag}/xflip'])
+    ds.close()
+
+
+def test_sampler_order_equals_the_reference(gold):
+    n = int(gold['mirror/len'])
+    keys = [k for k in gold.files if k.startswith('sampler/')]
+    assert len(keys) == 4
+    for k in keys:
+        rank, rep, seed, shuffle = [int(v) for v in k.split('/')[1].split('_')]
+        it = dsmod.infinite_order(n, rank=rank, num_replicas=rep, shuffle=bool(shuffle), seed=seed)
+        np.testing.assert_array_equal([next(it) for _ in range(100)], gold[k], err_msg=k)
+
+
+def test_rank_shards_are_disjoint_and_cover_the_stream():
+    n, rep = 24, 4
+    whole = dsmod.infinite_order(n, 0, 1, True, 9)
+    ref = [next(whole) for _ in range(200)]
+    shards = [dsmod.infinite_order(n, r, rep, True, 9) for r in range(rep)]
+    inter = [next(shards[t % rep]) for t in range(200)]
+    assert inter == ref                                            # rank r sees elements r, r + R, ... of the one global stream
+
+
+def test_directory_layout_and_missing_metadata(tmp_path):
+    with zipfile.ZipFile(ZIP) as z:
+        z.extractall(tmp_path / 'tiny_dataset')
+    a = dsmod.ImageFolderDataset(path=ZIP, cfg=_cfg(False))
+    b = dsmod.ImageFolderDataset(path=str(tmp_path / 'tiny_dataset'), cfg=_cfg(False))
+    assert len(a) == len(b) == 12
+    for i in (0, 5, 11):
+        np.testing.assert_array_equal(a[i]['image'], b[i]['image']); np.testing.assert_array_equal(a[i]['label'], b[i]['label'])
+    os.remove(tmp_path / 'tiny_dataset' / 'dataset.json')
+    c = dsmod.ImageFolderDataset(path=str(tmp_path / 'tiny_dataset'), cfg=_cfg(False, c_dim=0))
+    assert not c.has_labels and c[0]['label'].shape == (0,) and np.all(c[0]['camera_angles'] == 0)
+    with pytest.raises(AssertionError):                            # labels requested, none stored (dataset.py:66-68)
+        dsmod.ImageFolderDataset(path=str(tmp_path / 'tiny_dataset'), cfg=_cfg(False)).get_label(0)
+    with pytest.raises(IOError):
+        dsmod.ImageFolderDataset(path=ZIP, resolution=32, cfg=_cfg(False))
+    with pytest.raises(IOError):
+        dsmod.ImageFolderDataset(path=str(tmp_path / 'nothing.txt'), cfg=_cfg(False))
+
+
+def test_depth_maps_8_and_16_bit_and_mirror(tmp_path):
+    import PIL.Image
+    root = tmp_path / 'dd'; os.makedirs(root)
+    rs = np.random.RandomState(1)
+    d16 = rs.randint(0, 65536, size=(8, 8)).astype(np.uint16); d8 = rs.randint(0, 256, size=(8, 8)).astype(np.uint8)
+    for name, d in (('a', d16), ('b', d8)):
+        PIL.Image.fromarray(rs.randint(0, 256, size=(8, 8, 3)).astype(np.uint8), 'RGB').save(root / f'{name}.png')
+        PIL.Image.fromarray(d).save(root / f'{name}_depth.png')
+    ds = dsmod.ImageFolderDataset(path=str(root), use_depth=True, cfg=_cfg(True, c_dim=0))
+    assert len(ds) == 4 and ds.has_depth                            # the depth files are not counted as images; mirror doubles the set
+    np.testing.assert_array_equal(ds[0]['depth'], d16.astype(np.int32)[None])
+    np.testing.assert_array_equal(ds[1]['depth'], (d8.astype(np.int32) * 256)[None])           # 8-bit maps are scaled to the 16-bit range (dataset.py:319-320)
+    np.testing.assert_array_equal(ds[2]['depth'], d16.astype(np.int32)[None][:, :, ::-1])      # mirrored copy
+    assert ds[0]['depth'].dtype == np.int32
+
+
+def test_batch_stream_fills_pinned_style_buffers_in_sampler_order():
+    ds = dsmod.ImageFolderDataset(path=ZIP, cfg=_cfg(True))
+    stream = dsmod.BatchStream(ds, batch=5, rank=1, num_replicas=2, seed=4, workers=3, depth=3, pin=False)
+    order = dsmod.infinite_order(len(ds), 1, 2, True, 4)
+    seen = []
+    for _ in range(7):                                              # more batches than ring slots: buffers are reused
+        b = next(stream)
+        idx = [next(order) for _ in range(5)]
+        assert stream.last_indices == idx
+        assert b['image'].dtype == torch.uint8 and tuple(b['image'].shape) == (5, 3, 16, 16) and b['depth'].dtype == torch.int32
+        for r, i in enumerate(idx):
+            it = ds[i]
+            np.testing.assert_array_equal(b['image'][r].numpy(), it['image']); np.testing.assert_array_equal(b['label'][r].numpy(), it['label'])
+            np.testing.assert_array_equal(b['camera_angles'][r].numpy(), it['camera_angles'])
+        seen.append(b['image'].clone())
+    assert not torch.equal(seen[0], seen[3])                        # slot 0 was refilled with a different batch
+    x = dsmod.device_inputs(b)
+    assert x.img.dtype == torch.float32 and float(x.img.min()) >= -1.0 and float(x.img.max()) <= 1.0
+    np.testing.assert_array_equal(x.img.numpy(), b['image'].numpy().astype(np.float32) / 127.5 - 1.0)     # training_loop.py:300
+    stream.close(); ds.close()
+
+
+def test_decode_errors_surface_to_the_consumer(tmp_path):
+    root = tmp_path / 'bad'; os.makedirs(root)
+    import PIL.Image
+    PIL.Image.fromarray(np.zeros((8, 8, 3), np.uint8), 'RGB').save(root / 'a.png')
+    PIL.Image.fromarray(np.zeros((4, 4, 3), np.uint8), 'RGB').save(root / 'b.png')      # wrong size
+    ds = dsmod.ImageFolderDataset(path=str(root), cfg=_cfg(False, c_dim=0))
+    stream = dsmod.BatchStream(ds, batch=2, shuffle=False, workers=2, pin=False)
+    with pytest.raises(IOError):
+        next(stream)
+    stream.close()

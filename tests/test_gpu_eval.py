@@ -66,6 +66,34 @@ def test_prefetch_loader_delivers_every_batch_in_order():
         assert b['img'].is_cuda and torch.equal(b['img'].cpu(), batches[i]['img']) and torch.equal(b['c'].cpu(), batches[i]['c'])
 
 
+def test_training_set_stream_reaches_the_device_unchanged():
+    """training/dataset.py::BatchStream (worker threads decoding into pinned batch buffers, the reference sampler's order) -> PrefetchLoader (H2D on a side
+    stream) -> device_inputs (training_loop.py:300-304 on the device): every delivered batch equals the items the dataset returns on the host, although
+    the ring's pinned buffers are refilled while earlier copies are in flight."""
+    inf = _inf()
+    dsmod = importlib.import_module('3dgp_b200.training.dataset')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    cfg = dn.EasyDict.init_recursively(dict(c_dim=3, use_embeddings=False, mirror=True, camera=dict(
+        fov=dict(dist='uniform', min=10.0, max=45.0), origin=dict(radius=dict(dist='normal', mean=1.0, std=0.0),
+        angles=dict(dist='uniform', yaw=dict(min=-1.57, max=1.57), pitch=dict(min=0.785398163, max=2.35619449))))))
+    ds = dsmod.ImageFolderDataset(path=os.path.join(ROOT, 'tests', 'golden', 'tiny_dataset.zip'), cfg=cfg)
+    stream = dsmod.BatchStream(ds, batch=6, seed=2, workers=4, depth=4)
+    assert stream.ring[0]['image'].is_pinned()
+    order = dsmod.infinite_order(len(ds), 0, 1, True, 2)
+    loader = inf.PrefetchLoader(stream, 'cuda', depth=2)
+    for _ in range(9):
+        b = next(loader)
+        idx = [next(order) for _ in range(6)]
+        x = dsmod.device_inputs(b)
+        assert x.img.is_cuda and x.img.dtype == torch.float32
+        want = np.stack([ds[i]['image'] for i in idx])
+        assert torch.equal(b['image'].cpu(), torch.from_numpy(want))
+        assert torch.equal(x.img.cpu(), torch.from_numpy(want).to(torch.float32) / 127.5 - 1.0)
+        assert torch.equal(b['label'].cpu(), torch.from_numpy(np.stack([ds[i]['label'] for i in idx])))
+        assert torch.equal(b['camera_angles'].cpu(), torch.from_numpy(np.stack([ds[i]['camera_angles'] for i in idx])))
+    stream.close()
+
+
 def test_cuda_graph_replay_of_the_generator_equals_the_eager_call():
     """training/inference.py::GraphedGenerator: the captured generator call replayed on new latents / cameras returns the eager result (same Philox launch offset;
     bit for bit up to cuDNN's own run-to-run differences, see _same_images), for several batches in a row."""
