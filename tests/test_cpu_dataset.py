@@ -141,3 +141,28 @@ def test_decode_errors_surface_to_the_consumer(tmp_path):
     with pytest.raises(IOError):
         next(stream)
     stream.close()
+
+
+def test_embeddings_memmap_and_generator_side_batch(tmp_path):
+    """Pre-extracted feature embeddings (the knowledge-distillation targets, dataset.py:355-362) follow the file -> row table of their description;
+    `training_loop.sample_gen_batch` draws the generator's conditioning from the training set (training_loop.py:305-319)."""
+    from util import write_training_set
+    tl = importlib.import_module('3dgp_b200.training.training_loop')
+    root = str(tmp_path / 'set')
+    extra = write_training_set(root, n=10, res=8, c_dim=4, depth=True, emb_dim=6, seed=3)
+    emb, rows = extra.pop('_embeddings'), extra.pop('_rows')
+    cfg = _cfg(True, dist='custom', c_dim=4); cfg.update(extra)
+    ds = dsmod.ImageFolderDataset(path=root, use_depth=True, cfg=cfg)
+    assert len(ds) == 20 and ds.has_depth
+    for i in (0, 3, 13):
+        raw = int(ds.get_details(i).raw_idx)
+        np.testing.assert_array_equal(ds[i]['embedding'], emb[rows[ds._image_fnames[raw]]])
+    full = dn.EasyDict.init_recursively(dict(camera=dict(cfg.camera, look_at=dict(radius=dict(dist='uniform', min=0.0, max=0.2),
+                                             angles=dict(dist='spherical_uniform', yaw=dict(min=-3.14, max=3.14), pitch=dict(min=0.0, max=3.14))))))
+    rng = np.random.RandomState(5)
+    g = tl.sample_gen_batch(full, ds, 8, torch.device('cpu'), z_dim=16, gpc_spoof_p=0.5, rng=rng)
+    pick = [np.random.RandomState(5).randint(len(ds))]              # first draw of the same stream
+    assert tuple(g.z.shape) == (8, 16) and tuple(g.c.shape) == (8, 4) and float(g.c.sum()) == 8.0
+    np.testing.assert_array_equal(g.c[0].numpy(), ds.get_label(pick[0]))
+    np.testing.assert_allclose(g.camera_params.angles[0].numpy(), ds.get_camera_angles(pick[0]), rtol=0, atol=0)      # `custom`: cameras sit on dataset angles
+    assert tuple(g.camera_params.look_at.shape) == (8, 3) and tuple(g.camera_angles_cond.shape) == (8, 3)

@@ -182,3 +182,36 @@ def test_training_step_with_learned_camera_distribution():
     assert all(torch.isfinite(v).all() for v in stats.values())
     assert 'Loss/camera_dist/emd_loss' in stats and 'Loss/camera_dist/force_mean' in stats
     assert not torch.equal(w0, ca.look_at_adaptor.main[0].weight)
+
+
+def test_training_iterations_on_a_training_set_read_from_disk(tmp_path):
+    """training/training_loop.py::training_iterations: the reference loop's per-iteration data path (training_loop.py:296-366) end to end on the small
+    config -- PNG / depth / label / camera-angle / embedding files -> worker threads -> pinned ring -> H2D prefetch -> device normalisation ->
+    generator-side batch drawn from the training set -> Trainer.step (Gmain, Dmain with the distillation term, lazy R1)."""
+    from util import write_training_set
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    dsmod = importlib.import_module('3dgp_b200.training.dataset')
+    tl = importlib.import_module('3dgp_b200.training.training_loop')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0, batch_size=4)
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = cfgm.build_networks(cfg, 'cuda', fp32_D=True)
+    root = str(tmp_path / 'train')
+    extra = write_training_set(root, n=12, res=kw['img_resolution'], c_dim=kw['c_dim'], depth=True, emb_dim=kw['embedding_dim'])
+    extra.pop('_embeddings'); extra.pop('_rows')
+    dcfg = dn.EasyDict.init_recursively(dict(c_dim=kw['c_dim'], mirror=True, camera=cfg.camera, **extra))
+    ds = dsmod.ImageFolderDataset(path=root, resolution=kw['img_resolution'], use_depth=True, cfg=dcfg)
+    assert len(ds) == 24 and ds.label_dim == kw['c_dim']
+    loss = lossm.StyleGAN2Loss(cfg, 'cuda', G, D, r1_gamma=1.0)
+    tr = stepm.Trainer(G, D, loss, cfg, D_reg_interval=16)
+    w0 = G.synthesis.tri_plane_decoder.b8.conv0.weight.detach().clone(); d0 = D.b16.conv0.weight.detach().clone()
+    all_stats = list(tl.training_iterations(tr, ds, 'cuda', 3, batch=4, workers=3))
+    assert len(all_stats) == 3 and tr.it == 3 and tr.cur_nimg == 12
+    for st in all_stats:
+        assert all(torch.isfinite(v).all() for v in st.values())
+    assert 'Loss/D/r1_penalty' in all_stats[0] and 'Loss/D/r1_penalty' not in all_stats[1]
+    assert not torch.equal(w0, G.synthesis.tri_plane_decoder.b8.conv0.weight) and not torch.equal(d0, D.b16.conv0.weight)
