@@ -207,3 +207,45 @@ class FakeLib:
         _f32(dx, N, HW, C)[:] = d * sv
         _f32(g_s, N, C)[:] += (d * xv).sum(axis=1)
         return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Plugin-level stand-ins (the pybind11 surface of the reference: bias_act.cpp:94-97, upfirdn2d.cpp:102-105) for the Python wrappers
+# 3dgp_b200/torch_utils/ops/{upfirdn2d, bias_act}.py -- their autograd Functions (adjoint padding, gradient-of-gradient chain) run unchanged on top.
+class Upfirdn2dPlugin:
+    @staticmethod
+    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+        from oracle import restated as R
+        y = R.upfirdn2d(x.detach().to(torch.float64).numpy(), f.detach().to(torch.float32).numpy(), up=[upx, upy], down=[downx, downy],
+                        padding=[padx0, padx1, pady0, pady1], flip_filter=bool(flip), gain=gain)
+        y = torch.from_numpy(np.ascontiguousarray(y)).to(x.dtype)
+        return y.contiguous(memory_format=torch.channels_last) if (x.stride(1) == 1 and x.shape[1] > 1) else y
+
+
+class BiasActPlugin:
+    @staticmethod
+    def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
+        assert act in (1, 3), 'only linear / lrelu are emulated (the activations on the 3DGP path)'
+        alpha, gain, clamp = float(np.float32(alpha)), float(np.float32(gain)), float(np.float32(clamp))
+        shape = [-1 if i == dim else 1 for i in range(x.dim())]
+        v = x.to(torch.float64)
+        if grad == 0:
+            if b.numel():
+                v = v + b.to(torch.float64).reshape(shape)
+            if act == 3:
+                v = torch.where(v > 0, v, v * alpha)
+            v = v * gain
+            if clamp >= 0:
+                v = v.clamp(-clamp, clamp)
+        elif grad == 1:                      # x is dy here; the slope and the clamp mask come from the saved OUTPUT (bias_act.cu: yref)
+            y = yref.to(torch.float64)
+            if act == 3:
+                v = torch.where(y > 0, v, v * alpha)
+            v = v * gain
+            if clamp >= 0:
+                v = torch.where(y.abs() < clamp, v, torch.zeros_like(v))
+        else:
+            raise AssertionError('second-order term of a piecewise-linear activation is never requested (has_2nd_grad = False)')
+        out = torch.empty_like(x)
+        out.copy_(v.to(x.dtype))
+        return out

@@ -127,3 +127,74 @@ def test_fused_conv2d_layer_forward_and_gradients_vs_oracle(monkeypatch, k, act,
         assert float((yr.detach().abs() >= clamp * 0.5 - 1e-6).float().mean()) > 0.02, 'the clamp never engaged: the case does not test its mask'
     for name, a, b in zip(['x'] + (['c'] if hyper else []) + names, got, ref):
         assert _l2rel(a, b) < (2e-4 if terms == 3 else 1e-2), (name, _l2rel(a, b))      # 16: ONE bf16 gradient operand (2^-9) by design
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# One discriminator block (networks_discriminator.py:67-90) incl. its down-sampling layers (conv2d_resample: FIR then stride-2 conv, FIR-decimate then
+# 1x1 conv) and the R1-style double backward (loss.py:238-253), on emulated plugins + the emulated tensor-core ABI.
+
+def _oracle_block(sd, x, c, down):
+    s = float(np.sqrt(0.5))
+    y = R.conv2d_layer(sd, 'skip.', x, down=down, gain=s)
+    h = R.conv2d_layer(sd, 'conv0.', x, activation='lrelu')
+    h = R.conv2d_layer(sd, 'conv1.', h, activation='lrelu', down=down, gain=s, c=c)
+    return y + h
+
+
+@pytest.mark.parametrize('down,second_order', [(2, False), (1, False), (2, True)])
+def test_discriminator_block_first_order_and_r1_double_backward_vs_oracle(monkeypatch, down, second_order):
+    nd = importlib.import_module('3dgp_b200.training.networks_discriminator')
+    upf = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    bact = importlib.import_module('3dgp_b200.torch_utils.ops.bias_act')
+    gradfix = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    monkeypatch.setattr(modconv, 'conv_act_eligible', lambda x, w, k, up, dn, pad, act, cin, cout: up == 1 and dn == 1 and k in (1, 3) and cin % 64 == 0 and cout % 64 == 0)
+    monkeypatch.setattr(upf, '_plugin', emu.Upfirdn2dPlugin); monkeypatch.setattr(upf, '_init', lambda: True)
+    monkeypatch.setattr(bact, '_plugin', emu.BiasActPlugin); monkeypatch.setattr(bact, '_init', lambda: True)
+    # the public wrappers refuse CPU tensors (the product has no CPU path): enter below the guard, at the autograd Functions they dispatch to
+    monkeypatch.setattr(upf, 'upfirdn2d', lambda x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda':
+                        upf._upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f))
+    monkeypatch.setattr(bact, 'bias_act', lambda x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda':
+                        bact._bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b))
+    monkeypatch.setattr(gradfix, 'conv2d', lambda input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1:
+                        gradfix._conv(False, weight.shape, gradfix._tuple2(stride), gradfix._tuple2(padding), (0, 0), gradfix._tuple2(dilation), groups,
+                                      gradfix._terms_for(input.dtype)).apply(input, weight, bias))
+    torch.manual_seed(7)
+    C, B, cd = 64, 2, 10
+    blk = nd.DiscriminatorBlock(None, C, C, C, resolution=8, img_channels=4, first_layer_idx=2, down=down, c_dim=cd, hyper_mod=True, conv_clamp=None, use_fp16=False)
+    with torch.no_grad():
+        for n_, p_ in blk.named_parameters():
+            if n_.endswith('bias'):
+                p_.normal_(0, 0.2)
+    x = torch.randn(B, C, 8, 8, requires_grad=True); c = torch.randn(B, cd)
+    names = [n for n, _ in blk.named_parameters()]
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    for n in names:
+        sd[n].requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    before = dict(tc.stats)
+    if not second_order:
+        y = blk(x, None, c=c)
+        probe = torch.randn_like(y)
+        got = torch.autograd.grad((y * probe).sum(), [x] + list(blk.parameters()), allow_unused=True)      # fromrgb exists but is idle in an inner block
+        assert tc.stats['fused'] - before['fused'] == (1 if down == 2 else 3), 'stride-1 layers of the block run as fused first-order nodes'
+        yr = _oracle_block(sd, xr, c, down)
+        ref = torch.autograd.grad((yr * probe).sum(), [xr] + [sd[n] for n in names], allow_unused=True)
+    else:       # R1: gradient of the squared input-gradient norm w.r.t. the weights, weight gradients off inside the inner pass (loss.py:245-249)
+        with layers.first_order_only(False):
+            y = blk(x, None, c=c)
+        assert tc.stats['fused'] == before['fused'], 'the twice-differentiable composition must be used under first_order_only(False)'
+        with gradfix.no_weight_gradients():
+            gx, = torch.autograd.grad(y.sum(), [x], create_graph=True)
+        got = torch.autograd.grad(gx.square().sum(), list(blk.parameters()), allow_unused=True)
+        got = [x.grad] + list(got)
+        yr = _oracle_block(sd, xr, c, down)
+        gxr, = torch.autograd.grad(yr.sum(), [xr], create_graph=True)
+        ref = [None] + list(torch.autograd.grad(gxr.square().sum(), [sd[n] for n in names], allow_unused=True))
+        assert _l2rel(gx.detach(), gxr.detach()) < 1e-4
+    assert tc.stats['aten'] == before['aten'], 'a 64-channel convolution of the block fell back to ATen'
+    assert _l2rel(y.detach(), yr.detach()) < 1e-5
+    for name, a, b in zip(['x'] + names, got, ref):
+        if b is None or float(b.abs().max()) == 0.0:
+            assert a is None or float(a.abs().max()) < 1e-6, name
+            continue
+        assert _l2rel(a, b) < 3e-4, (name, _l2rel(a, b))
