@@ -249,3 +249,88 @@ class BiasActPlugin:
         out = torch.empty_like(x)
         out.copy_(v.to(x.dtype))
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Fused ray-march entry points (gp3d_raymarch_forward / _forward_cam / _backward, gp3d_generate_rays) served by the oracle's renderer: the host wrapper
+# 3dgp_b200/torch_utils/ops/raymarch.py (plane layout + strides, option codes, output shapes, gradient routing, camera chain) runs unchanged on top.
+def _planes_view(ptr, B, C, P, psB, psP, psC, psY, psX):
+    """[B, 3, C, P, P] float32 view of the plane tensor behind `ptr` with the element strides the ABI receives."""
+    extent = (B - 1) * psB + 2 * psP + (C - 1) * psC + (P - 1) * psY + (P - 1) * psX + 1
+    base = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_float)), shape=(extent,))
+    return np.lib.stride_tricks.as_strided(base, shape=(B, 3, C, P, P), strides=tuple(4 * s for s in (psB, psP, psC, psY, psX)))
+
+
+def _render_args(o, w1, b1, w2, b2, uc, uf, sc, sf):
+    B, R, N, C, H = o.B, o.R, o.N, o.C, o.H
+    t = lambda p, *s: torch.from_numpy(_f32(p, *s).copy())
+    assert uc and uf, 'the in-kernel Philox stream is not emulated: inject u_coarse / u_fine'
+    return dict(w1=t(w1, H, C), b1=t(b1, H), w2=t(w2, 4, H), b2=t(b2, 4), u_coarse=t(uc, B, R, N), u_fine=t(uf, B, R, N),
+                sn_coarse=t(sc, B, R, N) if sc else None, sn_fine=t(sf, B, R, N) if sf else None)
+
+
+def _render(planes, a, ray_o, ray_d, o):
+    from oracle import restated as R
+    return R.render(planes, a['w1'], a['b1'], a['w2'], a['b2'], ray_o, ray_d, a['u_coarse'], a['u_fine'], o.ray_start, o.ray_end, o.box_half, o.N,
+                    sn_coarse=a['sn_coarse'], sn_fine=a['sn_fine'], noise_std=o.noise_std, use_inf_depth=bool(o.use_inf_depth), last_back=bool(o.last_back),
+                    white_back_end_idx=o.white_back_end_idx, clamp_mode={0: 'softplus', 1: 'relu'}[o.clamp_mode])
+
+
+def _store_outputs(res, rgb, depth, wsum, tfin, B, R):
+    _f32(rgb, B, R, 3)[:] = res[0].detach().numpy(); _f32(depth, B, R)[:] = res[1].detach().numpy()
+    _f32(wsum, B, R)[:] = res[2].detach().numpy(); _f32(tfin, B, R)[:] = res[3].detach().numpy()
+
+
+def _raymarch_forward(planes, planes_dtype, psB, psP, psC, psY, psX, ray_o, ray_d, w1, b1, w2, b2, uc, uf, sc, sf, rgb, depth, wsum, tfin, opts, stream):
+    o = opts._obj
+    assert planes_dtype == 0, 'float32 planes only in the emulation'
+    pl = torch.from_numpy(_planes_view(planes, o.B, o.C, o.P, psB, psP, psC, psY, psX).copy())
+    a = _render_args(o, w1, b1, w2, b2, uc, uf, sc, sf)
+    ro, rd = torch.from_numpy(_f32(ray_o, o.B, o.R, 3).copy()), torch.from_numpy(_f32(ray_d, o.B, o.R, 3).copy())
+    _store_outputs(_render(pl, a, ro, rd, o), rgb, depth, wsum, tfin, o.B, o.R)
+    return 0
+
+
+def _generate_rays(c2w, fov, ps, po, B, h, w, ray_o, ray_d, stream):
+    from oracle import restated as R
+    t = lambda p, *s: torch.from_numpy(_f32(p, *s).copy())
+    ro, rd = R.sample_rays(t(c2w, B, 4, 4), t(fov, B), (w, h), t(ps, B, 2) if ps else None, t(po, B, 2) if po else None)
+    _f32(ray_o, B, h * w, 3)[:] = ro.numpy(); _f32(ray_d, B, h * w, 3)[:] = rd.numpy()
+    return 0
+
+
+def _raymarch_forward_cam(planes, planes_dtype, psB, psP, psC, psY, psX, cam, w1, b1, w2, b2, uc, uf, sc, sf, rgb, depth, wsum, tfin, opts, stream):
+    o, c = opts._obj, cam._obj
+    R_ = c.img_h * c.img_w
+    assert o.R == R_
+    ro = torch.empty([o.B, R_, 3]); rd = torch.empty([o.B, R_, 3])
+    _generate_rays(c.c2w, c.fov, c.patch_scales, c.patch_offsets, o.B, c.img_h, c.img_w, ro.data_ptr(), rd.data_ptr(), None)
+    return _raymarch_forward(planes, planes_dtype, psB, psP, psC, psY, psX, ro.data_ptr(), rd.data_ptr(), w1, b1, w2, b2, uc, uf, sc, sf,
+                             rgb, depth, wsum, tfin, opts, stream)
+
+
+def _raymarch_backward(planes, planes_dtype, psB, psP, psC, psY, psX, ray_o, ray_d, w1, b1, w2, b2, uc, uf, sc, sf, g_rgb, g_depth,
+                       g_planes, g_w1, g_b1, g_w2, g_b2, g_ray_o, g_ray_d, opts, stream):
+    """Gradients are ACCUMULATED into the (zero-filled) MLP / plane buffers and WRITTEN to the ray buffers, as the kernel does."""
+    o = opts._obj
+    B, R_, C, P, H = o.B, o.R, o.C, o.P, o.H
+    with torch.enable_grad():               # called from inside an autograd Function's backward, where grad mode is off
+        pl = torch.from_numpy(_planes_view(planes, B, C, P, psB, psP, psC, psY, psX).copy()).requires_grad_(True)
+        a = _render_args(o, w1, b1, w2, b2, uc, uf, sc, sf)
+        for k in ('w1', 'b1', 'w2', 'b2'):
+            a[k].requires_grad_(True)
+        ro = torch.from_numpy(_f32(ray_o, B, R_, 3).copy()).requires_grad_(True); rd = torch.from_numpy(_f32(ray_d, B, R_, 3).copy()).requires_grad_(True)
+        res = _render(pl, a, ro, rd, o)
+        gr, gd = torch.from_numpy(_f32(g_rgb, B, R_, 3).copy()), torch.from_numpy(_f32(g_depth, B, R_).copy())
+        grads = torch.autograd.grad([res[0], res[1]], [pl, a['w1'], a['b1'], a['w2'], a['b2'], ro, rd], [gr, gd])
+    _planes_view(g_planes, B, C, P, psB, psP, psC, psY, psX)[...] += grads[0].numpy()
+    _f32(g_w1, H, C)[:] += grads[1].numpy(); _f32(g_b1, H)[:] += grads[2].numpy(); _f32(g_w2, 4, H)[:] += grads[3].numpy(); _f32(g_b2, 4)[:] += grads[4].numpy()
+    if g_ray_o:
+        _f32(g_ray_o, B, R_, 3)[:] = grads[5].numpy(); _f32(g_ray_d, B, R_, 3)[:] = grads[6].numpy()
+    return 0
+
+
+FakeLib.gp3d_raymarch_forward = staticmethod(_raymarch_forward)
+FakeLib.gp3d_raymarch_forward_cam = staticmethod(_raymarch_forward_cam)
+FakeLib.gp3d_raymarch_backward = staticmethod(_raymarch_backward)
+FakeLib.gp3d_generate_rays = staticmethod(_generate_rays)

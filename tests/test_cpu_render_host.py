@@ -1,0 +1,111 @@
+"""Host wrapper of the fused ray-march (3dgp_b200/torch_utils/ops/raymarch.py) on a machine without a GPU: the four C-ABI entry points are served by the
+oracle's renderer through the pointers / strides / option structure the wrapper hands over (tests/abi_emulator.py), and the results are compared with
+the goldens the UNMODIFIED reference produced (tests/golden/render.npz: tri_plane_renderer.py:126-170 and its autograd).  What this pins without a GPU:
+the channel-minor plane layout and the strides that describe it, option codes, output shapes, the routing of the seven gradients, the in-kernel
+camera path (cam2world / fov / patch transform -> rays) and its chain to d(cam2world), d(fov)."""
+import contextlib
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator as emu
+from conftest import ROOT
+from oracle import cases, restated as R
+from util import maxrel, l2rel
+
+rm = importlib.import_module('3dgp_b200.torch_utils.ops.raymarch')
+_lib = importlib.import_module('3dgp_b200._lib')
+
+
+@pytest.fixture(autouse=True)
+def emulated_abi(monkeypatch):
+    fake = emu.FakeLib()
+    monkeypatch.setattr(_lib, 'lib', lambda: fake)
+    monkeypatch.setattr(_lib, 'stream_ptr', lambda: None)
+    monkeypatch.setattr(_lib, 'require_cuda', lambda t, name='tensor': None)
+    monkeypatch.setattr(torch.cuda, 'device', lambda _d: contextlib.nullcontext())
+    monkeypatch.setattr(R, 'DIFFERENTIABLE', True)
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'render.npz'))
+
+
+def _run(kw, inp, layout, requires_grad=False):
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    planes = t['planes']
+    if layout == 'channel_minor':       # what the tri-plane decoder emits: [B, P, P, 3C] storage behind the [B, 3, C, P, P] view
+        planes = rm.planes_channel_minor(planes)
+        assert planes.stride(2) == 1
+    args = [planes] + [t[k] for k in ('w1', 'b1', 'w2', 'b2', 'ray_o', 'ray_d')]
+    if requires_grad:
+        args = [a.clone().requires_grad_(True) if i else a.detach().requires_grad_(True) for i, a in enumerate(args)]
+    out = rm.render_rays(*args, num_steps=kw['N'], ray_start=kw['ray_start'], ray_end=kw['ray_end'], box_size=2 * kw['box_half'],
+                         u_coarse=t['u_coarse'], u_fine=t['u_fine'], sn_coarse=t.get('sn_coarse'), sn_fine=t.get('sn_fine'),
+                         density_noise=kw.get('noise_std', 0.0), use_inf_depth=kw.get('use_inf_depth', True), last_back=kw.get('last_back', False),
+                         white_back_end_idx=kw.get('white_back_end_idx', 0), clamp_mode=kw.get('clamp_mode', 'softplus'), mlp_mode=0)
+    return out, args
+
+
+@pytest.mark.parametrize('layout', ['nchw', 'channel_minor'])
+@pytest.mark.parametrize('name,kw', cases.render_cases(), ids=[c[0] for c in cases.render_cases()])
+def test_render_wrapper_forward_and_gradients_vs_reference_golden(gold, name, kw, layout):
+    inp = cases.render_inputs(name, kw)
+    (rgb, depth, wsum, tfin), args = _run(kw, inp, layout, requires_grad=True)
+    assert tuple(depth.shape) == (kw['B'], kw['R'], 1) and tuple(wsum.shape) == (kw['B'], kw['R'], 1) and tuple(tfin.shape) == (kw['B'], kw['R'])
+    assert maxrel(rgb.detach().numpy(), gold[name + '/rgb']) < 2e-5 and maxrel(depth.detach().squeeze(-1).numpy(), gold[name + '/depth']) < 2e-5
+    assert maxrel(wsum.squeeze(-1).numpy(), gold[name + '/wsum']) < 2e-5 and maxrel(tfin.numpy(), gold[name + '/tfinal']) < 2e-5
+    assert not wsum.requires_grad and not tfin.requires_grad
+    g_rgb = torch.from_numpy(cases.cotangent(rgb.shape, 21)); g_dep = torch.from_numpy(cases.cotangent(depth.shape, 22))
+    grads = torch.autograd.grad([rgb, depth], args, [g_rgb, g_dep])
+    for nm, gr in zip(['g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2', 'g_ray_o', 'g_ray_d'], grads):
+        if nm == 'g_planes' and (name + '/g_planes') not in gold.files:
+            assert l2rel(gr.contiguous().flatten()[::97].numpy(), gold[name + '/g_planes_probe']) < 1e-4
+            continue
+        assert gr.shape == gold[name + '/' + nm].shape and l2rel(gr.contiguous().numpy(), gold[name + '/' + nm]) < 1e-4, nm
+
+
+def test_camera_path_equals_explicit_rays_and_chains_to_the_camera():
+    name, kw = cases.render_cases()[0]
+    kw = dict(kw, R=36)                                   # 6 x 6 ray grid
+    inp = cases.render_inputs(name, kw)
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    B = kw['B']
+    rs = np.random.RandomState(3)
+    ang = torch.tensor(rs.uniform([-1.0, 1.0, 0.0], [1.0, 2.0, 0.0], size=(B, 3)), dtype=torch.float32)
+    c2w = R.compute_cam2world_matrix(ang, torch.ones(B), torch.tensor(rs.uniform(-0.1, 0.1, size=(B, 3)), dtype=torch.float32) * 0 + torch.tensor([[0.5, 1.5, 0.1]] * B))
+    fov = torch.tensor(rs.uniform(15, 40, size=B), dtype=torch.float32)
+    ps = torch.tensor(rs.uniform(0.4, 0.9, size=(B, 2)), dtype=torch.float32); po = torch.tensor(rs.uniform(0.0, 0.1, size=(B, 2)), dtype=torch.float32)
+    common = dict(num_steps=kw['N'], ray_start=kw['ray_start'], ray_end=kw['ray_end'], box_size=2 * kw['box_half'], u_coarse=t['u_coarse'], u_fine=t['u_fine'])
+    ro, rd = rm.generate_rays(c2w, fov, (6, 6), ps, po)
+    ro_ref, rd_ref = R.sample_rays(c2w, fov, (6, 6), ps, po)
+    assert maxrel(ro.numpy(), ro_ref.numpy()) < 1e-6 and maxrel(rd.numpy(), rd_ref.numpy()) < 1e-6
+    w = [t[k] for k in ('w1', 'b1', 'w2', 'b2')]
+    c2g, fvg = c2w.clone().requires_grad_(True), fov.clone().requires_grad_(True)
+    a = rm.render_camera(t['planes'], *w, c2g, fvg, (6, 6), ps, po, **common, mlp_mode=0)
+    b = rm.render_rays(t['planes'], *w, ro, rd, **common)
+    assert maxrel(a[0].detach().numpy(), b[0].numpy()) < 1e-6 and maxrel(a[1].detach().numpy(), b[1].numpy()) < 1e-6
+    # d(cam2world), d(fov): against autograd through the oracle's ray generator + renderer
+    g_c2w, g_fov = torch.autograd.grad(a[0].square().sum() + a[1].sum(), [c2g, fvg])
+    c2r, fvr = c2w.clone().requires_grad_(True), fov.clone().requires_grad_(True)
+    ro_r, rd_r = R.sample_rays(c2r, fvr, (6, 6), ps, po)
+    out = R.render(t['planes'], *w, ro_r, rd_r, t['u_coarse'], t['u_fine'], kw['ray_start'], kw['ray_end'], kw['box_half'], kw['N'])
+    r_c2w, r_fov = torch.autograd.grad(out[0].square().sum() + out[1].sum(), [c2r, fvr])
+    assert l2rel(g_c2w[:, :3].numpy(), r_c2w[:, :3].numpy()) < 1e-4 and l2rel(g_fov.numpy(), r_fov.numpy()) < 1e-4
+
+
+def test_wrapper_rejects_malformed_inputs():
+    name, kw = cases.render_cases()[0]
+    inp = cases.render_inputs(name, kw)
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    common = dict(num_steps=kw['N'], ray_start=0.75, ray_end=1.25, box_size=1.0)
+    with pytest.raises(RuntimeError, match='B\\*R\\*N'):
+        rm.render_rays(t['planes'], t['w1'], t['b1'], t['w2'], t['b2'], t['ray_o'], t['ray_d'], u_coarse=t['u_coarse'][:, :, :-1], u_fine=t['u_fine'], **common)
+    with pytest.raises(RuntimeError, match='2 layers'):
+        rm.render_rays(t['planes'], t['w1'][:, :-1], t['b1'], t['w2'], t['b2'], t['ray_o'], t['ray_d'], u_coarse=t['u_coarse'], u_fine=t['u_fine'], **common)
+    with pytest.raises(RuntimeError, match='float32 or float16'):
+        rm.render_rays(t['planes'].double(), t['w1'], t['b1'], t['w2'], t['b2'], t['ray_o'], t['ray_d'], u_coarse=t['u_coarse'], u_fine=t['u_fine'], **common)
