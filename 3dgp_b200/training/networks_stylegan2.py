@@ -4,6 +4,7 @@ upfirdn2d); the dense contraction goes through conv2d_resample -> conv2d_gradfix
 import numpy as np
 import torch
 
+from .. import _lib
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, modconv, upfirdn2d
 
 fused_layer_enabled = True   # route eligible training-path layers through the fused modulated-conv node (ops/modconv.py)
@@ -140,8 +141,7 @@ class SynthesisBlock(torch.nn.Module):
 
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, layer_noises=None, **layer_kwargs):
         w_iter = iter(ws.unbind(dim=1))
-        if ws.device.type != 'cuda':
-            raise RuntimeError('3dgp_b200 SynthesisBlock: CUDA tensors only')
+        _lib.require_cuda(ws, 'ws')          # no CPU path
         dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
         mf = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
         if fused_modconv is None:

@@ -1,0 +1,141 @@
+"""Whole networks on a machine WITHOUT a GPU: the product's Generator / Discriminator modules run on the emulated C ABI (tests/abi_emulator.py: numpy /
+oracle restatements of the header's contract behind the product's own call sites) and are compared with the goldens the UNMODIFIED reference produced
+at tensor-core-eligible widths (tests/golden/networks_wide.npz, oracle/make_golden.py networks_wide).  Same weights, latents, cameras, patch parameters
+and injected noise as tests/test_gpu_networks_wide.py; the routing counters prove that the path taken is the fused one the GPU run takes.
+Together with the GPU suite (kernels == contract) this closes  reference == host logic o contract  without a device."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator as emu
+from conftest import ROOT
+from oracle import cases
+from util import maxrel, l2rel
+
+pr = cases.grad_probe
+
+
+@pytest.fixture(autouse=True)
+def emulated(monkeypatch):
+    tc = emu.install(monkeypatch)
+    yield
+    tc.invalidate_weight_cache()
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'networks_wide.npz'))
+
+
+def _build():
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_wide_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    G.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, G.state_dict(), seed=100))
+    D.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, D.state_dict(), seed=200))
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(meta['net_kwargs']).items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    pp = dict(scales=t['patch_scales'], offsets=t['patch_offsets'])
+    return cfg, G, D, t, cam, pp, meta['net_kwargs']
+
+
+def test_generator_training_forward_on_the_emulated_abi_matches_the_reference(gold):
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    cfg, G, D, t, cam, pp, kw = _build()
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    G.train(); G.synthesis.nerf_noise_std = 0.0
+    blocks = {}
+    dec = G.synthesis.tri_plane_decoder
+    hs = [getattr(dec, f'b{r}').register_forward_hook(lambda m, a, o, r=r: blocks.__setitem__(r, (o[0].detach(), o[1].detach()))) for r in dec.block_resolutions]
+    s0 = dict(tc.stats)
+    with torch.no_grad():
+        ws = G.mapping(t['z'], t['c'])
+        ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)), mlp_mode=0)
+        out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
+    for h in hs:
+        h.remove()
+    d = {k: tc.stats[k] - s0[k] for k in s0}
+    assert d['fused'] == 14 and d['tc'] == 2 and d['aten'] == 4, d            # the routing tests/test_gpu_networks_wide.py asserts on the GPU
+    assert maxrel(ws.numpy(), gold['G/ws']) < 1e-5
+    errs = {}
+    for r, (x, img) in blocks.items():
+        errs[f'b{r}.x'] = maxrel(pr(x.contiguous().numpy()), gold[f'G/block/b{r}/x']); errs[f'b{r}.img'] = maxrel(pr(img.contiguous().numpy()), gold[f'G/block/b{r}/img'])
+    errs['img'] = maxrel(out.img.numpy(), gold['G/train/img']); errs['depth'] = maxrel(out.depth.numpy(), gold['G/train/depth'])
+    assert max(errs.values()) < 1e-4, errs                                     # float64 contractions on float32 storage: re-association level
+
+
+def test_discriminator_first_order_and_r1_on_the_emulated_abi_match_the_reference(gold):
+    """Dmain (fused first-order nodes) and Dreg (the twice-differentiable composition, weight gradients off inside the inner pass: loss.py:238-253) with
+    the routing counters of the GPU run."""
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    layers = importlib.import_module('3dgp_b200.training.layers')
+    cfg, G, D, t, cam, pp, kw = _build()
+    D.train()
+    B = t['z'].shape[0]
+    names = cases.probe_params('D', 'wide')
+    pars = dict(D.named_parameters())
+    blocks = {}
+    hs = [getattr(D, f'b{r}').register_forward_hook(lambda m, a, o, r=r: blocks.__setitem__(r, o.detach())) for r in D.block_resolutions]
+    img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
+    s0 = dict(tc.stats)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    d = {k: tc.stats[k] - s0[k] for k in s0}
+    for h in hs:
+        h.remove()
+    assert d['fused'] == 9 and d['tc'] == 6 and d['aten'] == 2, d
+    ferr = {f'b{r}': maxrel(pr(x.contiguous().numpy()), gold[f'D/block/b{r}']) for r, x in blocks.items()}
+    ferr['logits'] = maxrel(logits.detach().numpy(), gold['D/logits']); ferr['feats'] = maxrel(feats.detach().numpy(), gold['D/feats'])
+    assert max(ferr.values()) < 1e-4, ferr
+    embs = torch.from_numpy(cases.cotangent((B, kw['embedding_dim']), 31))
+    loss1 = torch.nn.functional.softplus(-logits).mean() + (feats - embs).norm(dim=1).mean()
+    assert abs(loss1.item() - float(gold['D/loss1'][0])) < 1e-4 * abs(float(gold['D/loss1'][0]))
+    gs = torch.autograd.grad(loss1, [img] + [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().numpy()), gold['D/grad1/' + n]) for n, gr in zip(names, gs[1:])}
+    errs['img'] = l2rel(gs[0].numpy(), gold['D/grad1/img'])
+    assert max(errs.values()) < 5e-4, errs            # the emulated backward kernels hand bf16 (hi, lo) pairs on: ~2^-16 per product
+    img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
+    s0 = dict(tc.stats)
+    with layers.first_order_only(False):
+        logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    d = {k: tc.stats[k] - s0[k] for k in s0}
+    assert d['fused'] == 0 and d['tc'] == 15 and d['aten'] == 2, d
+    with cg.no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().numpy()), gold['D/grad/' + n]) for n, gr in zip(names, gs)}
+    errs['r1(img)'] = l2rel(r1.detach().numpy(), gold['D/r1_grads'])
+    assert max(errs.values()) < 5e-4, errs
+
+
+def test_generator_loss_gradients_on_the_emulated_abi_match_the_reference(gold):
+    """Gmain: softplus(-D(G(z))) through the fused D nodes, the ray-march wrapper's backward and the fused decoder nodes, against the reference's autograd."""
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    cfg, G, D, t, cam, pp, kw = _build()
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    G.train(); G.synthesis.nerf_noise_std = 0.0
+    D.train(); D.requires_grad_(False)
+    s0 = dict(tc.stats)
+    ws = G.mapping(t['z'], t['c'])
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)), mlp_mode=0)
+    out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    d = {k: tc.stats[k] - s0[k] for k in s0}
+    assert d['fused'] == 14 + 9 and d['tc'] == 2 + 6 and d['aten'] == 4 + 2, d
+    loss = torch.nn.functional.softplus(-logits).mean()
+    assert abs(loss.item() - float(gold['G/loss'][0])) < 1e-4 * max(1.0, abs(float(gold['G/loss'][0])))
+    names = cases.probe_params('G', 'wide')
+    pars = dict(G.named_parameters())
+    gs = torch.autograd.grad(loss, [pars[n] for n in names])
+    errs = {n: l2rel(pr(gr.contiguous().numpy()), gold['G/grad/' + n]) for n, gr in zip(names, gs)}
+    assert max(errs.values()) < 1e-3, errs            # measured 4e-5 .. 1.2e-4, noise_strength 5.6e-4 (bf16 (hi, lo) pairs handed on by the emulated backward)
