@@ -72,6 +72,24 @@ def test_generator_training_forward_on_the_emulated_abi_matches_the_reference(go
     assert max(errs.values()) < 1e-4, errs                                     # float64 contractions on float32 storage: re-association level
 
 
+def test_generator_eval_forward_on_the_emulated_abi_matches_the_reference(gold):
+    """The G-inference path (metric_utils.py:303-319): eval mode, const noise, full-frame render at img_resolution, no patch."""
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    cfg, G, D, t, cam, pp, kw = _build()
+    G.eval()
+    B = t['z'].shape[0]
+    ue = cases.eval_variates(kw, B)
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=torch.from_numpy(ue['u_coarse']), u_fine=torch.from_numpy(ue['u_fine']), mlp_mode=0)
+    s0 = dict(tc.stats)
+    with torch.no_grad():
+        ws = G.mapping(t['z'], t['c'])
+        oe = G.synthesis(ws, cam, render_opts=ro, noise_mode='const')
+    d = {k: tc.stats[k] - s0[k] for k in s0}
+    assert d['fused'] == 14 and d['aten'] == 4, d
+    assert maxrel(pr(oe.img.contiguous().numpy()), gold['G/eval/img']) < 1e-4
+    assert maxrel(pr(oe.depth.contiguous().numpy()), gold['G/eval/depth']) < 1e-4
+
+
 def test_discriminator_first_order_and_r1_on_the_emulated_abi_match_the_reference(gold):
     """Dmain (fused first-order nodes) and Dreg (the twice-differentiable composition, weight gradients off inside the inner pass: loss.py:238-253) with
     the routing counters of the GPU run."""
