@@ -223,31 +223,60 @@ class Upfirdn2dPlugin:
 
 
 class BiasActPlugin:
+    """bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp) for all nine activations and gradient orders 0 / 1 / 2, following the formula
+    table of the reference kernel (bias_act.cu:23-147; restated in csrc/bias_act.cu::act_eval / bias_act_one), in float64."""
+
     @staticmethod
     def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
-        assert act in (1, 3), 'only linear / lrelu are emulated (the activations on the 3DGP path)'
+        A, G = int(act), int(grad)
         alpha, gain, clamp = float(np.float32(alpha)), float(np.float32(gain)), float(np.float32(clamp))
         shape = [-1 if i == dim else 1 for i in range(x.dim())]
-        v = x.to(torch.float64)
-        if grad == 0:
-            if b.numel():
-                v = v + b.to(torch.float64).reshape(shape)
-            if act == 3:
-                v = torch.where(v > 0, v, v * alpha)
-            v = v * gain
-            if clamp >= 0:
-                v = v.clamp(-clamp, clamp)
-        elif grad == 1:                      # x is dy here; the slope and the clamp mask come from the saved OUTPUT (bias_act.cu: yref)
-            y = yref.to(torch.float64)
-            if act == 3:
-                v = torch.where(y > 0, v, v * alpha)
-            v = v * gain
-            if clamp >= 0:
-                v = torch.where(y.abs() < clamp, v, torch.zeros_like(v))
+        f64 = lambda t: t.to(torch.float64) if t.numel() else None
+        v, xr, yr, dyv = x.to(torch.float64), f64(xref), f64(yref), f64(dy)
+        bb = b.to(torch.float64).reshape(shape) if b.numel() else 0.0
+        if G == 0:
+            v = v + bb
+        elif xr is not None:
+            xr = xr + bb
+        yy = (yr / gain if gain != 0 else torch.zeros_like(yr)) if yr is not None else None
+        ER, HER = 80.0, 40.0
+        sS, sA = 1.0507009873554804934193349852946, 1.6732632423543772848170429916717
+        W = torch.where
+        if A == 1:
+            y = v if G <= 1 else torch.zeros_like(v)
+        elif A == 2:
+            y = W(v > 0, v, torch.zeros_like(v)) if G == 0 else (W(yy > 0, v, torch.zeros_like(v)) if G == 1 else torch.zeros_like(v))
+        elif A == 3:
+            y = W(v > 0, v, v * alpha) if G == 0 else (W(yy > 0, v, v * alpha) if G == 1 else torch.zeros_like(v))
+        elif A == 4:
+            y = torch.tanh(v) if G == 0 else (v * (1 - yy * yy) if G == 1 else v * (1 - yy * yy) * (-2 * yy))
+        elif A == 5:
+            y = torch.sigmoid(v) if G == 0 else (v * yy * (1 - yy) if G == 1 else v * yy * (1 - yy) * (1 - 2 * yy))
+        elif A == 6:
+            y = W(v >= 0, v, torch.expm1(v.clamp(max=0))) if G == 0 else (W(yy >= 0, v, v * (yy + 1)) if G == 1 else W(yy >= 0, torch.zeros_like(v), v * (yy + 1)))
+        elif A == 7:
+            y = (W(v >= 0, sS * v, sS * sA * torch.expm1(v.clamp(max=0))) if G == 0 else
+                 (W(yy >= 0, v * sS, v * (yy + sS * sA)) if G == 1 else W(yy >= 0, torch.zeros_like(v), v * (yy + sS * sA))))
+        elif A == 8:
+            if G == 0:
+                y = W(v > ER, v, torch.log1p(torch.exp(v.clamp(max=ER))))
+            else:
+                c = torch.exp(-yy)
+                y = v * (1 - c) if G == 1 else v * c * (1 - c)
+        elif A == 9:
+            if G == 0:
+                y = v * torch.sigmoid(v)
+            else:
+                c = torch.exp(xr.clamp(max=ER)); d = c + 1
+                y = W(xr > HER, v, v * c * (xr + d) / (d * d)) if G == 1 else W(xr > HER, torch.zeros_like(v), v * c * (xr * (2 - d) + 2 * d) / (d * d * d))
+                yr = xr * torch.sigmoid(xr) * gain
         else:
-            raise AssertionError('second-order term of a piecewise-linear activation is never requested (has_2nd_grad = False)')
+            raise AssertionError(f'unknown activation index {A}')
+        y = y * gain * (dyv if dyv is not None else 1.0)
+        if clamp >= 0:
+            y = y.clamp(-clamp, clamp) if G == 0 else W((yr > -clamp) & (yr < clamp), y, torch.zeros_like(y))
         out = torch.empty_like(x)
-        out.copy_(v.to(x.dtype))
+        out.copy_(y.to(x.dtype))
         return out
 
 
@@ -264,9 +293,17 @@ def _planes_view(ptr, B, C, P, psB, psP, psC, psY, psX):
 def _render_args(o, w1, b1, w2, b2, uc, uf, sc, sf):
     B, R, N, C, H = o.B, o.R, o.N, o.C, o.H
     t = lambda p, *s: torch.from_numpy(_f32(p, *s).copy())
-    assert uc and uf, 'the in-kernel Philox stream is not emulated: inject u_coarse / u_fine'
-    return dict(w1=t(w1, H, C), b1=t(b1, H), w2=t(w2, 4, H), b2=t(b2, 4), u_coarse=t(uc, B, R, N), u_fine=t(uf, B, R, N),
-                sn_coarse=t(sc, B, R, N) if sc else None, sn_fine=t(sf, B, R, N) if sf else None)
+    # variates that are not injected come from the kernel's Philox stream keyed by (seed, offset): here a numpy stream with the same key, so that the
+    # backward launch regenerates what the forward drew (the VALUES differ from the kernel's; parity tests always inject)
+    rs = np.random.RandomState([int(o.seed) & 0x7fffffff, int(o.offset) & 0x7fffffff])
+    draw_u = lambda: torch.from_numpy(rs.uniform(0, 1, size=(B, R, N)).astype(np.float32))
+    draw_n = lambda: torch.from_numpy(rs.standard_normal((B, R, N)).astype(np.float32))
+    u_c = t(uc, B, R, N) if uc else draw_u()
+    u_f = t(uf, B, R, N) if uf else draw_u()
+    noisy = o.noise_std > 0
+    s_c = t(sc, B, R, N) if sc else (draw_n() if noisy else None)
+    s_f = t(sf, B, R, N) if sf else (draw_n() if noisy else None)
+    return dict(w1=t(w1, H, C), b1=t(b1, H), w2=t(w2, 4, H), b2=t(b2, 4), u_coarse=u_c, u_fine=u_f, sn_coarse=s_c, sn_fine=s_f)
 
 
 def _render(planes, a, ray_o, ray_d, o):

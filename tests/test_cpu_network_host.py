@@ -157,3 +157,36 @@ def test_generator_loss_gradients_on_the_emulated_abi_match_the_reference(gold):
     gs = torch.autograd.grad(loss, [pars[n] for n in names])
     errs = {n: l2rel(pr(gr.contiguous().numpy()), gold['G/grad/' + n]) for n, gr in zip(names, gs)}
     assert max(errs.values()) < 1e-3, errs            # measured 4e-5 .. 1.2e-4, noise_strength 5.6e-4 (bf16 (hi, lo) pairs handed on by the emulated backward)
+
+
+def test_one_training_iteration_of_the_real_modules_on_the_emulated_abi():
+    """training/step.py::Trainer.step on CPU modules (its torch.optim path) with the product's loss (Gmain with the camera-adaptor regularisers, Dmain
+    with the distillation term, lazy R1): every phase runs through the host logic the GPU step uses; stats finite, parameters and G_ema move."""
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss')
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0, learn_camera_dist=True, batch_size=4)
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(meta['net_kwargs']).items()}
+    B = t['z'].shape[0]
+    loss = lossm.StyleGAN2Loss(cfg, 'cpu', G, D, r1_gamma=1.0)
+    loss.progressive_update(5000)
+    tr = stepm.Trainer(G, D, loss, cfg, D_reg_interval=16, batch_size=B)
+    assert not tr.flat                                                          # CPU modules: the torch.optim branch of the trainer
+    res = kw['img_resolution']
+    real = dn.EasyDict(img=torch.rand(B, 3, res, res) * 2 - 1, depth=torch.rand(B, 1, res, res) * 2 - 1, c=t['c'], embs=torch.randn(B, kw['embedding_dim']),
+                       camera_angles=t['angles'])
+    gen = dn.EasyDict(z=t['z'], c=t['c'], camera_params=dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at']))
+    w0 = G.synthesis.tri_plane_decoder.b8.conv0.weight.detach().clone(); d0 = D.b16.conv0.weight.detach().clone()
+    e0 = tr.G_ema.synthesis.tri_plane_decoder.b8.conv0.weight.detach().clone()
+    stats = tr.step(real, gen)
+    assert all(torch.isfinite(torch.as_tensor(v)).all() for v in stats.values()), stats
+    assert 'Loss/D/r1_penalty' in stats and 'Loss/camera_dist/emd_loss' in stats and 'Loss/camera_dist/force_mean' in stats
+    assert not torch.equal(w0, G.synthesis.tri_plane_decoder.b8.conv0.weight) and not torch.equal(d0, D.b16.conv0.weight)
+    assert not torch.equal(e0, tr.G_ema.synthesis.tri_plane_decoder.b8.conv0.weight)
+    stats = tr.step(real, gen)
+    assert 'Loss/D/r1_penalty' not in stats and tr.it == 2 and tr.cur_nimg == 2 * B
