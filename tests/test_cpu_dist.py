@@ -110,3 +110,63 @@ def test_bucketed_gradient_allreduce_overlaps_and_matches_one_shot_gloo_world2()
     assert l0 == l1 and l0[0] == 0 and l0[1] == nb0   # pass 1 learns which parameters fire; pass 2 sends every bucket while the backward runs
     assert torch.equal(red0, red1)
     assert torch.allclose(red0, loc0 + loc1, rtol=0, atol=0)
+
+
+def _trainer_worker(rank, world, port, q):
+    """One optimisation step of the REAL Generator / Discriminator / loss on each rank (CPU modules on the emulated C ABI, tests/abi_emulator.py), gloo
+    carrying the per-phase gradient all-reduce: ranks start from different initialisations and see different data."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import json
+    import sys
+    import numpy as np
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, 'tests'))
+    import abi_emulator as emu
+    from oracle import cases
+    emu.install(pytest.MonkeyPatch())
+    torch.set_num_threads(4)
+    cfgm = importlib.import_module('3dgp_b200.config'); dn = importlib.import_module('3dgp_b200.dnnlib')
+    lossm = importlib.import_module('3dgp_b200.training.loss'); stepm = importlib.import_module('3dgp_b200.training.step')
+    meta = json.load(open(os.path.join(root, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0, batch_size=4 * world)
+    torch.manual_seed(100 + rank); np.random.seed(100 + rank)               # rank-specific initialisation: Trainer must broadcast rank 0's (training_loop.py:176-179)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    probe = lambda m: float(sum(p.detach().double().sum() for p in m.parameters()))
+    before = (probe(G), probe(D))
+    loss = lossm.StyleGAN2Loss(cfg, 'cpu', G, D, r1_gamma=1.0)
+    tr = stepm.Trainer(G, D, loss, cfg, rank=rank, world_size=world, D_reg_interval=16, batch_size=4 * world)
+    synced = (probe(G), probe(D))
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(meta['net_kwargs']).items()}
+    B, res = t['z'].shape[0], kw['img_resolution']
+    g = torch.Generator().manual_seed(7 + rank)                              # rank-specific data
+    real = dn.EasyDict(img=torch.rand(B, 3, res, res, generator=g) * 2 - 1, depth=torch.rand(B, 1, res, res, generator=g) * 2 - 1, c=t['c'],
+                       embs=torch.randn(B, kw['embedding_dim'], generator=g), camera_angles=t['angles'])
+    gen = dn.EasyDict(z=torch.randn(B, kw['z_dim'], generator=g), c=t['c'],
+                      camera_params=dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at']))
+    stats = tr.step(real, gen)
+    finite = all(bool(torch.isfinite(torch.as_tensor(v)).all()) for v in stats.values())
+    q.put((rank, before, synced, (probe(G), probe(D)), probe(tr.G_ema), finite))
+    dist.destroy_process_group()
+
+
+def test_real_networks_stay_replicated_over_one_step_gloo_world2():
+    """The data-parallel invariant of training_loop.py:176-179 + :335-344 on the real modules: after the start-up broadcast and one iteration on
+    different data, every rank holds the same G, D and G_ema."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, b0, s0, a0, e0, f0), (_, b1, s1, a1, e1, f1) = res
+    assert f0 and f1
+    assert b0 != b1                                   # different initialisations ...
+    assert s0 == s1 == b0                             # ... replaced by rank 0's parameters
+    assert a0 == a1 and a0 != s0                      # one step on different data: identical parameters on both ranks, and they moved
+    assert e0 == e1
