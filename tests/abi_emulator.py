@@ -416,3 +416,51 @@ def install(monkeypatch):
     monkeypatch.setattr(modconv, 'conv_act_eligible', lambda x, *a, **k: cel(_AsCuda(x), *a, **k))
     monkeypatch.setattr(R, 'DIFFERENTIABLE', True)
     return tc
+
+
+class FilteredLreluPlugin:
+    """filtered_lrelu_plugin (filtered_lrelu.cpp:16-298) with NO specialised kernel: `filtered_lrelu` answers return code -1, so the Python wrapper takes
+    the reference's generic route upfirdn2d -> filtered_lrelu_act_ -> upfirdn2d (filtered_lrelu.py:223-229); `filtered_lrelu_act_` applies the
+    sign-coded leaky ReLU in place and writes / reads the packed 2-bit sign tensor (0 positive, 1 negative, 2 clamped; four codes per byte along x,
+    element (x, y) at sign coordinate (x + sx, y + sy): filtered_lrelu.cu:1136-1145)."""
+
+    @staticmethod
+    def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns):
+        return torch.empty([0], dtype=x.dtype), torch.empty([0], dtype=torch.uint8), -1
+
+    @staticmethod
+    def filtered_lrelu_act_(x, si, sx, sy, gain, slope, clamp, writeSigns):
+        N, C, H, W = x.shape
+        gain, slope = float(np.float32(gain)), float(np.float32(slope))
+        clamp = float(np.float32(clamp)) if (clamp is not None and clamp >= 0 and clamp != float('inf')) else -1.0
+        v = x.detach().to(torch.float64).numpy()
+        if writeSigns:
+            code = np.zeros(v.shape, dtype=np.uint8)
+            neg = v < 0
+            v = np.where(neg, v * slope, v) * gain
+            code[neg] = 1
+            if clamp >= 0:
+                big = np.abs(v) > clamp
+                v = np.where(big, np.copysign(clamp, v), v)
+                code[big] = 2
+            sw = (W + 15) & ~15
+            full = np.zeros([N, C, H, sw], dtype=np.uint8); full[..., :W] = code
+            packed = (full[..., 0::4] | (full[..., 1::4] << 2) | (full[..., 2::4] << 4) | (full[..., 3::4] << 6)).astype(np.uint8)
+            so = torch.from_numpy(packed)
+        elif si.numel() > 0:
+            s = si.numpy()
+            sh, sw = s.shape[2], s.shape[3] * 4
+            dec = np.stack([(s >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(N, C, sh, sw)
+            ys, xs = np.arange(H) + sy, np.arange(W) + sx
+            code = np.zeros([N, C, H, W], dtype=np.uint8)                           # outside the sign tensor: code 0 (positive)
+            vy, vx = (ys >= 0) & (ys < sh), (xs >= 0) & (xs < sw)
+            code[np.ix_(np.arange(N), np.arange(C), np.nonzero(vy)[0], np.nonzero(vx)[0])] = dec[np.ix_(np.arange(N), np.arange(C), ys[vy], xs[vx])]
+            v = v * np.where(code == 0, gain, np.where(code == 1, gain * slope, 0.0))
+            so = si
+        else:
+            v = np.where(v < 0, v * slope, v) * gain
+            if clamp >= 0:
+                v = np.clip(v, -clamp, clamp)
+            so = si
+        x.copy_(torch.from_numpy(v).to(x.dtype))
+        return so

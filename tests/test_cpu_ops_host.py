@@ -66,3 +66,21 @@ def test_upfirdn2d_wrapper_forward_and_adjoint_vs_reference_golden(name, kw):
     yu = up.upfirdn2d(u, ft, up=kw['up'], down=kw['down'], padding=kw['padding'], flip_filter=kw['flip_filter'], gain=kw['gain'])
     lhs, rhs = float((yu.double() * v.double()).sum()), float((u.double() * gx.double()).sum())
     assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize('name,kw', cases.filtered_lrelu_cases(), ids=[c[0] for c in cases.filtered_lrelu_cases()])
+def test_filtered_lrelu_wrapper_generic_route_vs_reference_golden(monkeypatch, name, kw):
+    """filtered_lrelu.py's autograd Function on a plugin WITHOUT a specialised kernel (return code -1): the generic route and its backward -- the same op
+    with up / down swapped, the adjoint padding and the stored sign codes read back at the shifted offsets (filtered_lrelu.py:252-263) -- against y / dx / db
+    of the reference's `_filtered_lrelu_ref`."""
+    fl = importlib.import_module('3dgp_b200.torch_utils.ops.filtered_lrelu')
+    monkeypatch.setattr(fl, '_plugin', emu.FilteredLreluPlugin); monkeypatch.setattr(fl, '_init', lambda: True)
+    x, fu, fd, b = cases.filtered_lrelu_inputs(name, kw)
+    g = _gold('filtered_lrelu')
+    xt = torch.from_numpy(x).requires_grad_(True); bt = torch.from_numpy(b).requires_grad_(True)
+    F_ = fl._filtered_lrelu_cuda(up=kw['up'], down=kw['down'], padding=kw['padding'], gain=kw['gain'], slope=kw['slope'], clamp=kw['clamp'], flip_filter=False)
+    y = F_.apply(xt, torch.from_numpy(fu), torch.from_numpy(fd), bt, None, 0, 0)        # the public wrapper refuses CPU tensors; this is what it dispatches to
+    assert maxrel(y.detach().numpy(), g[name + '/y']) < 1e-5
+    dy = torch.from_numpy(cases.cotangent(y.shape, 13))
+    gx, gb = torch.autograd.grad(y, [xt, bt], dy)
+    assert maxrel(gx.numpy(), g[name + '/dx']) < 2e-5 and maxrel(gb.numpy(), g[name + '/db']) < 2e-5
