@@ -464,3 +464,16 @@ class FilteredLreluPlugin:
             so = si
         x.copy_(torch.from_numpy(v).to(x.dtype))
         return so
+
+
+def _to_uint8(x, y, N, Cx, Cy, H, W, sN, sC, sH, sW, scale, shift, stream):
+    """gp3d_to_uint8: y[n, c, h, w] = (uint8) clamp(x[n, c, h, w] * scale + shift, 0, 255) for the first Cy channels, x addressed by element strides."""
+    extent = (N - 1) * sN + (Cx - 1) * sC + (H - 1) * sH + (W - 1) * sW + 1
+    base = np.ctypeslib.as_array(ctypes.cast(int(x), ctypes.POINTER(ctypes.c_float)), shape=(extent,))
+    xv = np.lib.stride_tricks.as_strided(base, shape=(N, Cx, H, W), strides=(4 * sN, 4 * sC, 4 * sH, 4 * sW))[:, :Cy]
+    v = np.clip(xv * np.float32(scale) + np.float32(shift), 0, 255).astype(np.uint8)          # float32 arithmetic and a truncating cast, like torch's
+    np.ctypeslib.as_array(ctypes.cast(int(y), ctypes.POINTER(ctypes.c_uint8)), shape=(N * Cy * H * W,))[:] = v.reshape(-1)
+    return 0
+
+
+FakeLib.gp3d_to_uint8 = staticmethod(_to_uint8)

@@ -190,3 +190,28 @@ def test_one_training_iteration_of_the_real_modules_on_the_emulated_abi():
     assert not torch.equal(e0, tr.G_ema.synthesis.tri_plane_decoder.b8.conv0.weight)
     stats = tr.step(real, gen)
     assert 'Loss/D/r1_penalty' not in stats and tr.it == 2 and tr.cur_nimg == 2 * B
+
+
+def test_snapshot_generator_to_uint8_images_on_the_emulated_abi():
+    """Eval-side chain on CPU: reference-format snapshot pickle -> legacy.load_network_pkl -> inference.generate_uint8 (camera adaptor, G_ema, uint8
+    conversion) == the module called directly + the reference expression of metric_utils.py:313."""
+    lg = importlib.import_module('3dgp_b200.legacy')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    inf = importlib.import_module('3dgp_b200.training.inference')
+    Ge = lg.load_network_pkl(os.path.join(ROOT, 'tests', 'golden', 'snapshot_small.pkl.gz'), device='cpu', names=('G_ema',))['G_ema']
+    kw = cases.net_kwargs('small')
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(kw).items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    Ge.synthesis.renderer.launch_counter = 0
+    img = inf.generate_uint8(Ge, t['z'], t['c'], cam, noise_mode='const')
+    B = t['z'].shape[0]
+    assert img.dtype == torch.uint8 and tuple(img.shape) == (B, 3, kw['img_resolution'], kw['img_resolution'])
+    Ge.synthesis.renderer.launch_counter = 0
+    with torch.no_grad():
+        ref = Ge(z=t['z'], c=t['c'], camera_params=cam, camera_angles_cond=cam.angles, noise_mode='const')
+    ref = ref if torch.is_tensor(ref) else ref.img
+    assert torch.equal(img, (ref[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8))
+    for cl in (False, True):          # NCHW and channels-last inputs of the conversion, 4-channel input -> first 3 channels
+        x = torch.randn(2, 4, 8, 12) * 1.5
+        xin = x.contiguous(memory_format=torch.channels_last) if cl else x
+        assert torch.equal(inf.to_uint8(xin, channels=3), (x[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8))
