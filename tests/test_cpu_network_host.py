@@ -215,3 +215,65 @@ def test_snapshot_generator_to_uint8_images_on_the_emulated_abi():
         x = torch.randn(2, 4, 8, 12) * 1.5
         xin = x.contiguous(memory_format=torch.channels_last) if cl else x
         assert torch.equal(inf.to_uint8(xin, channels=3), (x[:, :3] * 127.5 + 128).clamp(0, 255).to(torch.uint8))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The SMALL networks (32-channel layers: below the tensor-core kernels' channel granularity) take the UNFUSED composition -- x * styles ->
+# conv2d_resample (stride-2 transposed conv + FIR for the up-sampling layers, FIR + stride-2 conv for the down-sampling ones) -> fma -> bias_act,
+# the grouped-conv inference form, ATen convolutions -- i.e. the other half of the module code.  Same goldens as tests/test_gpu_networks.py.
+
+def _build_small():
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    kw = dict(meta['net_kwargs']); kw.pop('learn_camera_dist', None)
+    cfg = cfgm.make_config(**kw, kd_weight=1.0)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    G.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, G.state_dict(), seed=100))
+    D.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, D.state_dict(), seed=200))
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(meta['net_kwargs']).items()}
+    cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    return cfg, G, D, t, cam, dict(scales=t['patch_scales'], offsets=t['patch_offsets']), meta['net_kwargs']
+
+
+def test_small_networks_unfused_composition_on_the_emulated_abi_match_the_reference():
+    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
+    cg = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'networks.npz'))
+    cfg, G, D, t, cam, pp, kw = _build_small()
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    G.train(); G.synthesis.nerf_noise_std = 0.0
+    s0 = dict(tc.stats)
+    ws = G.mapping(t['z'], t['c'])
+    ro = dict(concat_depth=True, return_depth=True, u_coarse=t['u_coarse'], u_fine=t['u_fine'], depth_head_idx=torch.from_numpy(cases.depth_heads(B)), mlp_mode=0)
+    out = G.synthesis(ws, cam, patch_params=pp, render_opts=ro, noise_mode='random', layer_noises=noises)
+    assert tc.stats['fused'] == s0['fused'] and tc.stats['tc'] == s0['tc'], 'no layer of the small network is wide enough for the tensor-core kernels'
+    assert maxrel(ws.detach().numpy(), gold['G/ws']) < 1e-5
+    assert maxrel(out.img.detach().numpy(), gold['G/train/img']) < 1e-4 and maxrel(out.depth.detach().numpy(), gold['G/train/depth']) < 1e-4
+    # Gmain gradients through D
+    D.train()
+    logits, _ = D(out.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    assert abs(loss.item() - float(gold['G/loss'][0])) < 1e-4 * max(1.0, abs(float(gold['G/loss'][0])))
+    names = cases.probe_params('G'); pars = dict(G.named_parameters())
+    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
+        assert l2rel(gr.numpy(), gold['G/grad/' + n]) < 5e-4, n
+    # eval: grouped-conv (fused_modconv) inference form, const noise, full frame
+    G.eval()
+    ue = cases.eval_variates(kw, B)
+    with torch.no_grad():
+        oe = G.synthesis(ws.detach(), cam, render_opts=dict(concat_depth=True, return_depth=True, u_coarse=torch.from_numpy(ue['u_coarse']),
+                                                            u_fine=torch.from_numpy(ue['u_fine']), mlp_mode=0), noise_mode='const')
+    assert maxrel(oe.img.numpy(), gold['G/eval/img']) < 1e-4 and maxrel(oe.depth.numpy(), gold['G/eval/depth']) < 1e-4
+    # D forward + R1 double backward
+    img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    assert maxrel(logits.detach().numpy(), gold['D/logits']) < 1e-4 and maxrel(feats.detach().numpy(), gold['D/feats']) < 1e-4
+    with cg.no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    assert l2rel(r1.detach().numpy(), gold['D/r1_grads']) < 1e-4
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    names = cases.probe_params('D'); pars = dict(D.named_parameters())
+    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
+        assert l2rel(gr.numpy(), gold['D/grad/' + n]) < 5e-4, n
