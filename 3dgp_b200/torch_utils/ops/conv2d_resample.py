@@ -25,12 +25,8 @@ Contract = collections.namedtuple('Contract', 'stride pad transposed mirrored')
 
 
 def _filter_margins(taps, factor, upsampling):
-    """Padding that centres a `taps`-wide FIR on the `factor`-times finer (up) or coarser (down) lattice: (leading, trailing)."""
-    if factor == 1:
-        return 0, 0
-    if upsampling:
-        return (taps + factor - 1) // 2, (taps - factor) // 2
-    return (taps - factor + 1) // 2, (taps - factor) // 2
+    """Centring margins of the resampling filter; none when the factor is 1 (no filter is applied on that side)."""
+    return upfirdn2d._margins(taps, factor, upsampling) if factor > 1 else (0, 0)
 
 
 @functools.lru_cache(maxsize=None)

@@ -84,3 +84,30 @@ def test_filtered_lrelu_wrapper_generic_route_vs_reference_golden(monkeypatch, n
     dy = torch.from_numpy(cases.cotangent(y.shape, 13))
     gx, gb = torch.autograd.grad(y, [xt, bt], dy)
     assert maxrel(gx.numpy(), g[name + '/dx']) < 2e-5 and maxrel(gb.numpy(), g[name + '/db']) < 2e-5
+
+
+@pytest.mark.parametrize('taps', [[1, 3, 3, 1], [1, 2, 1], [1, 4, 6, 4, 1], [1, 1, 2, 3, 3, 2, 1, 1]], ids=lambda t: f'f{len(t)}')
+@pytest.mark.parametrize('pad', [0, [1, 2], [2, 0, -1, 1]], ids=lambda p: f'p{p}'.replace(' ', ''))
+def test_resampling_helpers_and_the_spec_algebra_vs_oracle(taps, pad):
+    """filter2d / upsample2d / downsample2d (centring margins of upfirdn2d.py:277-387) against the oracle; FirSpec.out_extent is the extent the plugin
+    returns; the adjoint of the adjoint restores the spec whenever the forward pass dropped nothing (exact multiples)."""
+    from oracle import restated as R
+    up = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
+    f = up.setup_filter(taps)                              # 8 taps -> separable (two passes), shorter -> 2-D
+    fnp = R.setup_filter(taps)
+    assert np.array_equal(f.numpy(), fnp)
+    x = torch.from_numpy(cases.cotangent((2, 3, 10, 12), 21))
+    for name, kw in (('filter2d', {}), ('upsample2d', dict(up=2)), ('upsample2d', dict(up=[2, 1])), ('downsample2d', dict(down=2)), ('downsample2d', dict(down=[1, 2]))):
+        got = getattr(up, name)(x, f, padding=pad, flip_filter=True, **kw)
+        want = getattr(R, name)(x.numpy(), fnp, padding=pad, flip_filter=True, **kw)
+        assert tuple(got.shape) == want.shape, (name, kw)
+        assert maxrel(got.numpy(), want) < 1e-5, (name, kw)
+    fw, fh = up._get_filter_size(f)
+    for u, d in ((1, 1), (2, 1), (1, 2), (3, 2)):
+        spec = up._upfirdn2d_cuda(up=u, down=d, padding=pad, flip_filter=False, gain=2)
+        y = spec.apply(x, f)
+        assert tuple(y.shape[2:]) == spec.out_extent(10, 12, fh, fw)
+        adj = spec.adjoint((10, 12), tuple(y.shape[2:]), (fh, fw))
+        assert adj.up == spec.down and adj.down == spec.up and adj.flip != spec.flip and adj.out_extent(*y.shape[2:], fh, fw) == (10, 12)
+        if d == 1:
+            assert adj.adjoint(tuple(y.shape[2:]), (10, 12), (fh, fw)) == spec
