@@ -4,6 +4,8 @@
 First and second order gradients are supported through the same grad=1 / grad=2 kernel forms the reference uses
 (bias_act.py:142-207).  There is no `impl='ref'` branch in the product: CPU tensors raise.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -46,67 +48,88 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b)
 
 
-_cache = dict()
+class ActSpec(collections.namedtuple('ActSpec', 'dim act alpha gain clamp')):
+    """Static half of one bias_act call, with defaults resolved (clamp = -1 when off).  The kernel has three forms selected by `order`:
+    0: y = clamp(act(x + b) * gain);  1: dx from dy;  2: the second-order term d(dx)/dx.  Forms 1 and 2 read x or y -- whichever the
+    activation's derivative is cheapest to express in (`ref` column of the table) -- so only those are kept for backward."""
+    __slots__ = ()
+
+    @property
+    def entry(self):
+        return activation_funcs[self.act]
+
+    @property
+    def is_identity(self):
+        return self.act == 'linear' and self.gain == 1 and self.clamp < 0
+
+    def kernel(self, t, b, x, y, dy, order):
+        return _plugin.bias_act(t, b, x, y, dy, order, self.dim, self.entry.cuda_idx, self.alpha, self.gain, self.clamp)
+
+    def reduce_to_bias(self, g):
+        return g.sum([i for i in range(g.ndim) if i != self.dim])
+
+    def apply(self, x, b):
+        return _BiasActNode.apply(x, b, self)
+
+
+def _layout_of(t):
+    """Channel-minor 4-D tensors stay channel-minor through the op and its gradients; everything else is made dense row-major."""
+    return torch.channels_last if (t.ndim == 4 and t.stride(1) == 1 and t.shape[1] > 1) else torch.contiguous_format
+
+
+class _BiasActNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, b, spec):
+        ctx.spec, ctx.layout = spec, _layout_of(x)
+        x = x.contiguous(memory_format=ctx.layout)
+        nul = _null(x)
+        bias = nul if b is None else b.contiguous()
+        y = x if (spec.is_identity and b is None) else spec.kernel(x, bias, nul, nul, nul, 0)
+        e = spec.entry
+        needs_x = ('x' in e.ref) or e.has_2nd_grad
+        ctx.save_for_backward(x if needs_x else nul, bias if needs_x else nul, y if 'y' in e.ref else nul)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        x, b, y = ctx.saved_tensors
+        dx = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dy = dy.contiguous(memory_format=ctx.layout)
+            dx = dy if spec.is_identity else _BiasActGradNode.apply(dy, x, b, y, spec)
+        if ctx.needs_input_grad[1]:
+            db = spec.reduce_to_bias(dx)
+        return dx, db, None
+
+
+class _BiasActGradNode(torch.autograd.Function):
+    """dx = dy * act'(.) * gain (zero where clamped): linear in dy, so its gradient w.r.t. dy is itself; w.r.t. x (and b) the order-2 kernel form."""
+
+    @staticmethod
+    def forward(ctx, dy, x, b, y, spec):
+        ctx.spec, ctx.layout = spec, _layout_of(dy)
+        dx = spec.kernel(dy, b, x, y, _null(dy), 1)
+        ctx.save_for_backward(dy if spec.entry.has_2nd_grad else _null(dy), x, b, y)
+        return dx
+
+    @staticmethod
+    def backward(ctx, d_dx):
+        spec = ctx.spec
+        d_dx = d_dx.contiguous(memory_format=ctx.layout)
+        dy, x, b, y = ctx.saved_tensors
+        d_dy = d_x = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_dy = _BiasActGradNode.apply(d_dx, x, b, y, spec)
+        if spec.entry.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            d_x = spec.kernel(d_dx, b, x, y, dy, 2)
+            if ctx.needs_input_grad[2]:
+                d_b = spec.reduce_to_bias(d_x)
+        return d_dy, d_x, d_b, None, None
 
 
 def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
+    """Object with `.apply(x, b)` (the reference's private entry point of the same name, bias_act.py:118-207)."""
     assert clamp is None or clamp >= 0
-    spec = activation_funcs[act]
-    alpha = float(alpha if alpha is not None else spec.def_alpha)
-    gain = float(gain if gain is not None else spec.def_gain)
-    clamp = float(clamp if clamp is not None else -1)
-    key = (dim, act, alpha, gain, clamp)
-    if key in _cache:
-        return _cache[key]
-    idx = spec.cuda_idx
-    keep_x = ('x' in spec.ref) or spec.has_2nd_grad
-    keep_y = 'y' in spec.ref
-    trivial = (act == 'linear' and gain == 1 and clamp < 0)
-
-    class BiasAct(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x, b):
-            ctx.memory_format = torch.channels_last if (x.ndim == 4 and x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format
-            x = x.contiguous(memory_format=ctx.memory_format)
-            nul = _null(x)
-            bb = b.contiguous() if b is not None else nul
-            y = x
-            if not trivial or b is not None:
-                y = _plugin.bias_act(x, bb, nul, nul, nul, 0, dim, idx, alpha, gain, clamp)
-            ctx.save_for_backward(x if keep_x else nul, bb if keep_x else nul, y if keep_y else nul)
-            return y
-
-        @staticmethod
-        def backward(ctx, dy):
-            dy = dy.contiguous(memory_format=ctx.memory_format)
-            x, b, y = ctx.saved_tensors
-            dx = db = None
-            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-                dx = dy if trivial else BiasActGrad.apply(dy, x, b, y)
-            if ctx.needs_input_grad[1]:
-                db = dx.sum([i for i in range(dx.ndim) if i != dim])
-            return dx, db
-
-    class BiasActGrad(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, dy, x, b, y):
-            ctx.memory_format = torch.channels_last if (dy.ndim == 4 and dy.stride(1) == 1 and dy.shape[1] > 1) else torch.contiguous_format
-            dx = _plugin.bias_act(dy, b, x, y, _null(dy), 1, dim, idx, alpha, gain, clamp)
-            ctx.save_for_backward(dy if spec.has_2nd_grad else _null(dy), x, b, y)
-            return dx
-
-        @staticmethod
-        def backward(ctx, d_dx):
-            d_dx = d_dx.contiguous(memory_format=ctx.memory_format)
-            dy, x, b, y = ctx.saved_tensors
-            d_dy = d_x = d_b = None
-            if ctx.needs_input_grad[0]:
-                d_dy = BiasActGrad.apply(d_dx, x, b, y)
-            if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
-                d_x = _plugin.bias_act(d_dx, b, x, y, dy, 2, dim, idx, alpha, gain, clamp)
-            if spec.has_2nd_grad and ctx.needs_input_grad[2]:
-                d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
-            return d_dy, d_x, d_b, None
-
-    _cache[key] = BiasAct
-    return BiasAct
+    e = activation_funcs[act]
+    return ActSpec(dim, act, float(e.def_alpha if alpha is None else alpha), float(e.def_gain if gain is None else gain), float(-1 if clamp is None else clamp))

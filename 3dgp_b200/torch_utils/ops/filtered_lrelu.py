@@ -8,6 +8,8 @@ memory); everything else takes the reference's own *generic* route -- upfirdn2d,
 for backward (0 positive, 1 negative, 2 clamped; filtered_lrelu.cu:1136-1145), and the backward is the same op with up/down swapped
 and the signs read back (filtered_lrelu.py:252-263).
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -36,68 +38,82 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np
                                 flip_filter=flip_filter).apply(x, fu, fd, b, None, 0, 0)
 
 
-_cache = dict()
+class LreluSpec(collections.namedtuple('LreluSpec', 'up down pad gain slope clamp flip')):
+    """Static half of one filtered_lrelu call (pad = (x0, x1, y0, y1) on the up-sampled lattice, clamp = inf when off).  The backward pass is the
+    same operator with the filters' roles exchanged, no clamp, and the stored sign codes read back at a shifted origin (`backward_spec`), so one
+    autograd node parameterised by the spec serves every order (the reference builds a class per parameter set, filtered_lrelu.py:178-272)."""
+    __slots__ = ()
+
+    def backward_spec(self, x_hw, y_hw, fu, fd):
+        """(spec, sign-origin shift) of the gradient call for an x_hw input that produced y_hw."""
+        (xh, xw), (yh, yw) = x_hw, y_hw
+        x0, _, y0, _ = self.pad
+        reach_x = (fu.shape[-1] - 1) + (fd.shape[-1] - 1)          # taps either filter hangs over an edge
+        reach_y = (fu.shape[0] - 1) + (fd.shape[0] - 1)
+        pad = (reach_x - x0, xw * self.up - yw * self.down + x0 - (self.up - 1),
+               reach_y - y0, xh * self.up - yh * self.down + y0 - (self.up - 1))
+        gain = self.gain * (self.up ** 2) / (self.down ** 2)
+        shift = (x0 - (fu.shape[-1] - 1), y0 - (fu.shape[0] - 1))
+        return LreluSpec(self.down, self.up, pad, gain, self.slope, float('inf'), not self.flip), shift
+
+    def run(self, x, fu, fd, b, signs, sx, sy, write_signs):
+        """(y, signs-out).  The fused kernel when the plugin has one for this case; else bias -> up FIR -> sign-coded lrelu in place -> down FIR."""
+        x0, x1, y0, y1 = self.pad
+        if x.dtype in (torch.float16, torch.float32):
+            y, so, rc = _plugin.filtered_lrelu(x, fu, fd, b, signs, self.up, self.down, x0, x1, y0, y1, sx, sy, self.gain, self.slope, self.clamp,
+                                               self.flip, write_signs)
+            if rc >= 0:
+                return y, so
+        t = x if b is None else x + b.reshape(1, -1, 1, 1)
+        t = upfirdn2d.upfirdn2d(x=t, f=fu, up=self.up, padding=[x0, x1, y0, y1], gain=self.up ** 2, flip_filter=self.flip).contiguous()
+        if t.data_ptr() == x.data_ptr():        # the activation kernel works in place: never on the caller's tensor
+            t = t.clone()
+        so = _plugin.filtered_lrelu_act_(t, signs, sx, sy, self.gain, self.slope, self.clamp, write_signs)
+        return upfirdn2d.upfirdn2d(x=t, f=fd, down=self.down, flip_filter=self.flip), so
+
+    def apply(self, x, fu, fd, b, si, sx, sy):
+        return _FilteredLreluNode.apply(x, fu, fd, b, si, sx, sy, self)
+
+
+def _unit_filter(f, factor, device):
+    """None -> 1x1 identity; a separable single tap with no resampling -> the 1x1 filter f*f."""
+    if f is None:
+        return torch.ones([1, 1], dtype=torch.float32, device=device)
+    assert 1 <= f.ndim <= 2
+    if factor == 1 and f.ndim == 1 and f.shape[0] == 1:
+        return f.square()[None]
+    return f
+
+
+class _FilteredLreluNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fu, fd, b, si, sx, sy, spec):
+        assert isinstance(x, torch.Tensor) and x.ndim == 4
+        fu, fd = _unit_filter(fu, spec.up, x.device), _unit_filter(fd, spec.down, x.device)
+        if si is None:
+            si = torch.empty([0], dtype=torch.uint8, device=x.device)
+        # sign codes are produced only by a first-order forward that will be differentiated; a gradient call reads the ones it was given
+        write_signs = (si.numel() == 0) and (x.requires_grad or (b is not None and b.requires_grad))
+        y, so = spec.run(x, fu, fd, b, si, sx, sy, write_signs)
+        ctx.save_for_backward(fu, fd, (si if si.numel() else so))
+        ctx.spec, ctx.x_hw, ctx.y_hw, ctx.s_ofs = spec, tuple(x.shape[2:]), tuple(y.shape[2:]), (sx, sy)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        fu, fd, si = ctx.saved_tensors
+        dx = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
+            spec, (shx, shy) = ctx.spec.backward_spec(ctx.x_hw, ctx.y_hw, fu, fd)
+            dx = spec.apply(dy, fd, fu, None, si, ctx.s_ofs[0] + shx, ctx.s_ofs[1] + shy)
+        if ctx.needs_input_grad[3]:
+            db = dx.sum([0, 2, 3])
+        return dx, None, None, db, None, None, None, None
 
 
 def _filtered_lrelu_cuda(up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None, flip_filter=False):
+    """Object with `.apply(x, fu, fd, b, si, sx, sy)` (the reference's private entry point of the same name, filtered_lrelu.py:159-272)."""
     assert isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1
-    px0, px1, py0, py1 = _parse_padding(padding)
-    gain = float(gain); slope = float(slope)
+    gain, slope = float(gain), float(slope)
     assert gain > 0 and slope >= 0 and (clamp is None or clamp >= 0)
-    clamp = float(clamp if clamp is not None else 'inf')
-    key = (up, down, px0, px1, py0, py1, gain, slope, clamp, flip_filter)
-    if key in _cache:
-        return _cache[key]
-
-    class FilteredLRelu(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x, fu, fd, b, si, sx, sy):
-            assert isinstance(x, torch.Tensor) and x.ndim == 4
-            one = lambda: torch.ones([1, 1], dtype=torch.float32, device=x.device)
-            fu = one() if fu is None else fu
-            fd = one() if fd is None else fd
-            assert 1 <= fu.ndim <= 2 and 1 <= fd.ndim <= 2
-            if up == 1 and fu.ndim == 1 and fu.shape[0] == 1:
-                fu = fu.square()[None]
-            if down == 1 and fd.ndim == 1 and fd.shape[0] == 1:
-                fd = fd.square()[None]
-            if si is None:
-                si = torch.empty([0], dtype=torch.uint8, device=x.device)
-            write_signs = (si.numel() == 0) and (x.requires_grad or (b is not None and b.requires_grad))
-            y = so = None
-            return_code = -1
-            if x.dtype in (torch.float16, torch.float32):
-                y, so, return_code = _plugin.filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filter, write_signs)
-            if return_code < 0:     # generic route (filtered_lrelu.py:223-229)
-                y = x if b is None else x + b.reshape(1, -1, 1, 1)
-                y = upfirdn2d.upfirdn2d(x=y, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-                y = y.contiguous()
-                if y.data_ptr() == x.data_ptr():
-                    y = y.clone()
-                so = _plugin.filtered_lrelu_act_(y, si, sx, sy, gain, slope, clamp, write_signs)   # in place on y
-                y = upfirdn2d.upfirdn2d(x=y, f=fd, down=down, flip_filter=flip_filter)
-            ctx.save_for_backward(fu, fd, (si if si.numel() else so))
-            ctx.x_shape, ctx.y_shape, ctx.s_ofs = x.shape, y.shape, (sx, sy)
-            return y
-
-        @staticmethod
-        def backward(ctx, dy):
-            fu, fd, si = ctx.saved_tensors
-            _, _, xh, xw = ctx.x_shape
-            _, _, yh, yw = ctx.y_shape
-            sx, sy = ctx.s_ofs
-            dx = db = None
-            if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
-                pp = [(fu.shape[-1] - 1) + (fd.shape[-1] - 1) - px0, xw * up - yw * down + px0 - (up - 1),
-                      (fu.shape[0] - 1) + (fd.shape[0] - 1) - py0, xh * up - yh * down + py0 - (up - 1)]
-                gg = gain * (up ** 2) / (down ** 2)
-                sx2 = sx - (fu.shape[-1] - 1) + px0
-                sy2 = sy - (fu.shape[0] - 1) + py0
-                dx = _filtered_lrelu_cuda(up=down, down=up, padding=pp, gain=gg, slope=slope, clamp=None,
-                                          flip_filter=(not flip_filter)).apply(dy, fd, fu, None, si, sx2, sy2)
-            if ctx.needs_input_grad[3]:
-                db = dx.sum([0, 2, 3])
-            return dx, None, None, db, None, None, None
-
-    _cache[key] = FilteredLRelu
-    return FilteredLRelu
+    return LreluSpec(up, down, tuple(_parse_padding(padding)), gain, slope, float('inf' if clamp is None else clamp), bool(flip_filter))
