@@ -15,7 +15,8 @@ What is different underneath (this is the B200 side of the data path, training_l
     side stream while batch i trains.  180 GB of HBM leave room to normalise on the device: `device_inputs` applies `/127.5 - 1` (and the depth
     scaling of :303) to the uint8 / int32 batch after the copy, so the PCIe transfer carries 1 byte per sample instead of 4.
 Embeddings (`cfg.use_embeddings`, a memmap of pre-extracted features used by the knowledge-distillation term) are read the reference's way when
-configured; depth maps are decoded with PIL (the reference needs pyspng, which is not installed here: that decode is restated, not pinned)."""
+configured; depth maps are decoded with PIL (the reference uses pyspng, which is not installed here; the items are pinned against the reference reader run
+with a specification-level PNG decoder in pyspng's place, tests/golden/dataset_depth_golden.npz)."""
 import json
 import os
 import threading

@@ -109,6 +109,37 @@ def test_depth_maps_8_and_16_bit_and_mirror(tmp_path):
     assert ds[0]['depth'].dtype == np.int32
 
 
+def test_depth_items_equal_the_reference_bit_for_bit():
+    """use_depth=True on the committed depth fixture (16-bit grey, 8-bit grey, 8-bit RGB depth maps, all five PNG scanline filters) against the items the
+    UNMODIFIED reference class returned for it; the reference's `pyspng.load` was stood in for by the specification decoder oracle/png_spec.py
+    (pyspng is absent from this image), the product decodes with PIL: two independent decoders, one reference logic (dataset.py:164-173, 310-323)."""
+    g = np.load(os.path.join(GOLD, 'dataset_depth_golden.npz'))
+    ds = dsmod.ImageFolderDataset(path=os.path.join(GOLD, 'tiny_dataset_depth.zip'), resolution=16, use_depth=True, cfg=_cfg(True, c_dim=2))
+    assert len(ds) == int(g['len']) == 12 and bool(ds.has_depth) == bool(g['has_depth'])
+    items = [ds[i] for i in range(len(ds))]
+    for k in ('image', 'label', 'depth'):
+        got = np.stack([it[k] for it in items])
+        assert got.dtype == g[k].dtype and got.shape == g[k].shape, k
+        np.testing.assert_array_equal(got, g[k], err_msg=k)
+    assert g['depth'].dtype == np.int32 and g['depth'].max() > 255 * 128      # the fixture really spans the 16-bit range
+    ds.close()
+
+
+def test_specification_png_decoder_agrees_with_pil_on_every_filter_type():
+    """The stand-in for pyspng (oracle/png_spec.py, written from the PNG specification) and PIL decode each other's files identically."""
+    import PIL.Image
+    from oracle import png_spec
+    rs = np.random.RandomState(5)
+    for shape, dt in (((16, 16, 3), np.uint8), ((16, 16), np.uint8), ((16, 16), np.uint16), ((5, 7, 4), np.uint8)):
+        a = (rs.randint(0, 65536, size=shape) if dt == np.uint16 else rs.randint(0, 256, size=shape)).astype(dt)
+        for ft in range(5):
+            data = png_spec.save(a, ft)
+            assert png_spec.load(data).dtype == dt and np.array_equal(png_spec.load(data), a)
+            assert np.array_equal(np.array(PIL.Image.open(io.BytesIO(data))).astype(dt), a), (shape, ft)
+        b = io.BytesIO(); PIL.Image.fromarray(a).save(b, format='png', compress_level=9)     # PIL chooses its own (adaptive) filters
+        assert np.array_equal(png_spec.load(b.getvalue()), a)
+
+
 def test_batch_stream_fills_pinned_style_buffers_in_sampler_order():
     ds = dsmod.ImageFolderDataset(path=ZIP, cfg=_cfg(True))
     stream = dsmod.BatchStream(ds, batch=5, rank=1, num_replicas=2, seed=4, workers=3, depth=3, pin=False)
