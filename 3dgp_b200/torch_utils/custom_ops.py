@@ -20,6 +20,12 @@ verbosity = 'brief'  # kept for train.py:49-50 (`custom_ops.verbosity = 'none'`)
 _cached_plugins = dict()
 
 
+def _x_on_cuda(x):
+    """The plugins' own device check (TORCH_CHECK(x.is_cuda(), ...) of bias_act.cpp:38, upfirdn2d.cpp:19, filtered_lrelu.cpp:22,218)."""
+    if not x.is_cuda:
+        raise RuntimeError('x must reside on CUDA device')
+
+
 def _dev(x):
     _lib.require_cuda(x, 'x')
     return torch.cuda.device(x.device)
@@ -31,8 +37,7 @@ class _BiasActPlugin:
     @staticmethod
     def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
         L = _lib.lib()
-        if not x.is_cuda:
-            raise RuntimeError('x must reside on CUDA device')
+        _x_on_cuda(x)
         for name, t in (('b', b), ('xref', xref), ('yref', yref), ('dy', dy)):
             if t.numel() > 0:
                 if t.dtype != x.dtype or t.device != x.device:
@@ -82,8 +87,7 @@ class _Upfirdn2dPlugin:
     @staticmethod
     def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
         L = _lib.lib()
-        if not x.is_cuda:
-            raise RuntimeError('x must reside on CUDA device')
+        _x_on_cuda(x)
         if f.device != x.device:
             raise RuntimeError('f must reside on the same device as x')
         if f.dtype != torch.float32:
@@ -133,8 +137,7 @@ class _FilteredLreluPlugin:
     def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns):
         L = _lib.lib()
         none = lambda: (torch.empty([0], device=x.device, dtype=x.dtype), torch.empty([0], device=x.device, dtype=torch.uint8), -1)
-        if not x.is_cuda:
-            raise RuntimeError('x must reside on CUDA device')
+        _x_on_cuda(x)
         if fu.dtype != torch.float32 or fd.dtype != torch.float32:
             raise RuntimeError('fu and fd must be float32')
         if x.dim() != 4:
@@ -195,8 +198,7 @@ class _FilteredLreluPlugin:
     @staticmethod
     def filtered_lrelu_act_(x, si, sx, sy, gain, slope, clamp, writeSigns):
         L = _lib.lib()
-        if not x.is_cuda:
-            raise RuntimeError('x must reside on CUDA device')
+        _x_on_cuda(x)
         if x.dim() != 4:
             raise RuntimeError('x must be rank 4')
         if not x.is_contiguous():

@@ -477,3 +477,85 @@ def _to_uint8(x, y, N, Cx, Cy, H, W, sN, sC, sH, sW, scale, shift, stream):
 
 
 FakeLib.gp3d_to_uint8 = staticmethod(_to_uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# LIBRARY-level stand-ins for the entry points behind the three reference plugins (gp3d_bias_act, gp3d_upfirdn2d(_out_size), gp3d_filtered_lrelu(_act)),
+# served from host pointers as include/gp3d_b200.h words them.  With these, the product's plugin OBJECTS (3dgp_b200/torch_utils/custom_ops.py: argument
+# checks, stride / size marshalling, output allocation) run on CPU tensors -- underneath the product's wrappers or, in tests/test_cpu_reference_wrappers.py,
+# underneath the UNMODIFIED reference wrappers (integration level A of INTEGRATION.md).
+_CT = {0: (ctypes.c_float, np.float32), 1: (ctypes.c_uint16, np.float16)}
+
+
+def _flat(ptr, code, n):
+    ct, npt = _CT[code]
+    return np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ct)), shape=(int(n),)).view(npt)
+
+
+def _strided(ptr, code, shape, strides):
+    extent = sum((d - 1) * s for d, s in zip(shape, strides)) + 1
+    base = _flat(ptr, code, extent)
+    return np.lib.stride_tricks.as_strided(base, shape=tuple(shape), strides=tuple(int(s) * base.itemsize for s in strides))
+
+
+def _lib_bias_act(x, b, xref, yref, dy, y, dtype, numel, sizeB, stepB, grad, act, alpha, gain, clamp, stream):
+    t = lambda p: torch.from_numpy(_flat(p, dtype, numel).copy()) if p else torch.empty([0], dtype=torch.float32 if dtype == 0 else torch.float16)
+    xt = t(x)
+    if b:       # the bias of element i is b[(i / stepB) % sizeB]
+        bb = torch.from_numpy(_flat(b, dtype, sizeB).copy())[(torch.arange(numel) // stepB) % sizeB]
+    else:
+        bb = torch.empty([0], dtype=xt.dtype)
+    out = BiasActPlugin.bias_act(xt, bb, t(xref), t(yref), t(dy), grad, 0, act, alpha, gain, clamp)
+    _flat(y, dtype, numel)[:] = out.numpy()
+    return 0
+
+
+def _lib_upfirdn2d_out_size(in_size, up, down, pad0, pad1, fsize):
+    from oracle import restated as R
+    return R.upfirdn2d_out_size(in_size, up, down, pad0, pad1, fsize)
+
+
+def _lib_upfirdn2d(x, f, y, dtype, N, C, inH, inW, xsN, xsC, xsH, xsW, fh, fw, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain,
+                   outH, outW, ysN, ysC, ysH, ysW, stream):
+    from oracle import restated as R
+    xv = _strided(x, dtype, (N, C, inH, inW), (xsN, xsC, xsH, xsW)).astype(np.float64)
+    fv = _flat(f, 0, fh * fw).reshape(fh, fw).copy()
+    out = R.upfirdn2d(xv, fv, up=[upx, upy], down=[downx, downy], padding=[padx0, padx1, pady0, pady1], flip_filter=bool(flip), gain=gain)
+    assert out.shape == (N, C, outH, outW), 'the caller-computed output extent disagrees with the operator'
+    yv = _strided(y, dtype, (N, C, outH, outW), (ysN, ysC, ysH, ysW))
+    yv[...] = out.astype(yv.dtype)
+    return 0
+
+
+def _lib_filtered_lrelu(*args):
+    return -2       # GP3D_E_UNSUPPORTED: no fused kernel in the emulation, the caller takes the generic route
+
+
+def _lib_filtered_lrelu_act(x, si, dtype, N, C, H, W, sH, sW4, sx, sy, gain, slope, clamp, write_signs, stream):
+    xv = _strided(x, dtype, (N, C, H, W), (C * H * W, H * W, W, 1))
+    xt = torch.from_numpy(xv.copy())
+    if write_signs:
+        assert sx == 0 and sy == 0 and sH == H and sW4 == ((W + 15) & ~15) >> 2
+        so = FilteredLreluPlugin.filtered_lrelu_act_(xt, torch.empty([0], dtype=torch.uint8), 0, 0, gain, slope, clamp, True)
+        np.ctypeslib.as_array(ctypes.cast(int(si), ctypes.POINTER(ctypes.c_uint8)), shape=(N, C, sH, sW4))[...] = so.numpy()
+    else:
+        st = torch.empty([0], dtype=torch.uint8)
+        if si:
+            st = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(int(si), ctypes.POINTER(ctypes.c_uint8)), shape=(N, C, sH, sW4)).copy())
+        FilteredLreluPlugin.filtered_lrelu_act_(xt, st, sx, sy, gain, slope, clamp, False)
+    xv[...] = xt.numpy()
+    return 0
+
+
+def install_plugin_library(monkeypatch):
+    """install() plus: the product's REAL plugin objects (custom_ops.get_plugin) on the library-level stand-ins above.  Returns the product's custom_ops."""
+    import importlib
+    install(monkeypatch)
+    co = importlib.import_module('3dgp_b200.torch_utils.custom_ops')
+    for name, fn in (('gp3d_bias_act', _lib_bias_act), ('gp3d_upfirdn2d_out_size', _lib_upfirdn2d_out_size), ('gp3d_upfirdn2d', _lib_upfirdn2d),
+                     ('gp3d_filtered_lrelu', _lib_filtered_lrelu), ('gp3d_filtered_lrelu_act', _lib_filtered_lrelu_act)):
+        monkeypatch.setattr(FakeLib, name, staticmethod(fn), raising=False)
+    monkeypatch.setattr(FakeLib, 'gp3d_last_error', staticmethod(lambda: b'emulated'), raising=False)
+    monkeypatch.setattr(co, '_x_on_cuda', lambda x: None)
+    monkeypatch.setattr(co, '_cached_plugins', dict())
+    return co
