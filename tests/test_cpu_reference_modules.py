@@ -1,0 +1,122 @@
+"""Op-level overlay of INTEGRATION.md (section B, first two rows), executed: the UNMODIFIED reference network code (src/training/{networks_epigraf,
+networks_stylegan2, networks_discriminator, networks_depth_adaptor, layers}.py, imported in place from /root/reference) with THIS repo's op modules
+(3dgp_b200/torch_utils/ops/{bias_act, upfirdn2d, conv2d_resample, conv2d_gradfix, fma}.py) bound under the names the reference imports
+(`from src.torch_utils.ops import ...`, networks_stylegan2.py:21-24, layers.py:9-11, networks_discriminator.py:7) -- i.e. every call site of the
+reference exercises the product ops' public surface: `conv2d_resample(x=, w=, f=, up=, down=, padding=, groups=, flip_weight=)`, `bias_act(x, b, act=,
+gain=, clamp=)`, `activation_funcs[...]`, `setup_filter`, `upsample2d`, `fma`, `conv2d_gradfix.no_weight_gradients()`.
+
+Results are held to the goldens the same reference code produced with its OWN ops (tests/golden/networks*.npz).  No GPU here: the product ops run on the
+emulated C ABI (tests/abi_emulator.py); skipped where /root/reference is absent."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator as emu
+from conftest import ROOT
+from oracle import cases, ref_harness as rh
+from util import l2rel, maxrel
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason='the unmodified reference is only present in the build container')
+OPS = ('bias_act', 'upfirdn2d', 'conv2d_resample', 'conv2d_gradfix', 'fma')
+
+
+@pytest.fixture()
+def overlay(monkeypatch):
+    tc = emu.install(monkeypatch)
+    ns = rh.load()
+    ours = {n: importlib.import_module('3dgp_b200.torch_utils.ops.' + n) for n in OPS}
+    import src.training.networks_depth_adaptor as ref_da
+    import src.training.networks_camera_adaptor as ref_ca
+    bound = 0
+    for mod in (ns.networks_epigraf, ns.networks_stylegan2, ns.networks_discriminator, ns.layers, ref_da, ref_ca):
+        for n, o in ours.items():
+            if hasattr(mod, n):
+                monkeypatch.setattr(mod, n, o); bound += 1
+    assert bound == 8          # networks_stylegan2.py:21-24 (4), layers.py:9-11 (3), networks_discriminator.py:7 (1)
+    return ns, tc, ours
+
+
+def _build(ns, variant):
+    kw = cases.net_kwargs(variant)
+    Gc, Dc, m = rh.make_cfg(**kw)
+    G = rh.build_reference_G(Gc, m['img_resolution'], seed=0)
+    D = rh.build_reference_D(Dc, m['patch_res'], use_depth=True, embedding_dim=m['embedding_dim'], seed=1, fp32=True)
+    G.load_state_dict(cases.fill_state_dict({k: tuple(v.shape) for k, v in G.state_dict().items()}, G.state_dict(), seed=100))
+    D.load_state_dict(cases.fill_state_dict({k: tuple(v.shape) for k, v in D.state_dict().items()}, D.state_dict(), seed=200))
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(kw).items()}
+    cam = ns.dnnlib.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+    return kw, G, D, t, cam, dict(scales=t['patch_scales'], offsets=t['patch_offsets'])
+
+
+def test_reference_networks_on_our_ops_small(overlay, monkeypatch):
+    ns, tc, ours = overlay
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'networks.npz'))
+    kw, G, D, t, cam, pp = _build(ns, 'small')
+    B, N, Rr = t['z'].shape[0], kw['num_ray_steps'], kw['patch_res'] ** 2
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    head = cases.depth_heads(B)
+    monkeypatch.setattr(np.random, 'choice', lambda *a, **k: head.copy())
+    s0 = dict(tc.stats)
+    G.train(); G.synthesis.nerf_noise_std = 0.0
+    with rh.injected_rng(randn=[n.clone() for n in noises], rand_like=[t['u_coarse'].reshape(B, Rr, N, 1)], rand=[t['u_fine'].reshape(B * Rr, N)]):
+        ws = G.mapping(t['z'], t['c'])
+        o = G.synthesis(ws, cam, patch_params=pp, render_opts=dict(concat_depth=True, return_depth=True))
+    assert tc.stats['aten'] > s0['aten'], 'the convolutions of the reference modules went through the product conv2d_gradfix'
+    assert maxrel(ws.detach().numpy(), gold['G/ws']) < 1e-5
+    assert maxrel(o.img.detach().numpy(), gold['G/train/img']) < 1e-4 and maxrel(o.depth.detach().numpy(), gold['G/train/depth']) < 1e-4
+    # Gmain gradients through D
+    D.train()
+    logits, _ = D(o.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    names = cases.probe_params('G'); pars = dict(G.named_parameters())
+    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
+        assert l2rel(gr.numpy(), gold['G/grad/' + n]) < 5e-4, n
+    # eval: the grouped-conv (fused_modconv) form of modulated_conv2d, const noise
+    G.eval()
+    ue = cases.eval_variates(kw, B); Re = kw['img_resolution'] ** 2
+    with torch.no_grad(), rh.injected_rng(rand_like=[torch.from_numpy(ue['u_coarse']).reshape(B, Re, N, 1)], rand=[torch.from_numpy(ue['u_fine']).reshape(B * Re, N)]):
+        oe = G.synthesis(ws.detach(), cam, noise_mode='const', render_opts=dict(concat_depth=True, return_depth=True))
+    assert maxrel(oe.img.numpy(), gold['G/eval/img']) < 1e-4
+    # D forward + the R1 double backward under the PRODUCT's no_weight_gradients (loss.py:238-253 uses conv2d_gradfix.no_weight_gradients)
+    img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    assert maxrel(logits.detach().numpy(), gold['D/logits']) < 1e-4 and maxrel(feats.detach().numpy(), gold['D/feats']) < 1e-4
+    with ours['conv2d_gradfix'].no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    assert l2rel(r1.detach().numpy(), gold['D/r1_grads']) < 1e-4
+    loss = torch.nn.functional.softplus(-logits).mean() + r1.square().sum([1, 2, 3]).mean() * 0.5
+    names = cases.probe_params('D'); pars = dict(D.named_parameters())
+    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
+        assert l2rel(gr.numpy(), gold['D/grad/' + n]) < 5e-4, n
+
+
+def test_reference_decoder_and_discriminator_on_our_tensor_core_route_wide(overlay):
+    """Same overlay at tensor-core-eligible widths: the reference modules' convolutions now take the product's tensor-core PRIMITIVES (conv2d_gradfix ->
+    ops/tc.py tap lists; the fused layer nodes belong to the module-level overlay and are not involved here)."""
+    ns, tc, ours = overlay
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'networks_wide.npz'))
+    kw, G, D, t, cam, pp = _build(ns, 'wide')
+    B = t['z'].shape[0]
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    ws = torch.from_numpy(gold['G/ws'])
+    G.train()
+    s0 = dict(tc.stats)
+    with torch.no_grad(), rh.injected_rng(randn=[n.clone() for n in noises]):
+        planes = G.synthesis.tri_plane_decoder(ws, noise_mode='random', fused_modconv=False)
+    assert tc.stats['tc'] - s0['tc'] >= 14 and tc.stats['fused'] == s0['fused']
+    assert maxrel(planes.flatten()[::31].numpy(), gold['G/train/planes_probe']) < 1e-4
+    stats = np.array([planes.double().sum().item(), planes.double().abs().sum().item()])
+    assert np.abs(stats - gold['G/train/planes_stats']).max() < 1e-4 * np.abs(gold['G/train/planes_stats']).max()
+    D.train()
+    s0 = dict(tc.stats)
+    img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
+    logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
+    assert tc.stats['tc'] - s0['tc'] >= 10
+    assert maxrel(logits.detach().numpy(), gold['D/logits']) < 1e-4 and maxrel(feats.detach().numpy(), gold['D/feats']) < 1e-4
+    with ours['conv2d_gradfix'].no_weight_gradients():
+        r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
+    assert l2rel(r1.detach().numpy(), gold['D/r1_grads']) < 5e-4
