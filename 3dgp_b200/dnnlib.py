@@ -53,8 +53,59 @@ class TensorGroup(EasyDict):
     def values(self):
         return [v for _, v in self.items()]
 
+    shape = property(lambda self: [len(self), None])
+
+    # -- member-wise maps: the group behaves like one tensor whose rows are the concatenated members (util.py:109-175) -------------------
+    def _map(self, fn):
+        return TensorGroup(**{n: fn(v) for n, v in self.items()})
+
+    def _zip(self, other, fn):
+        """fn(member, other's member of the same name) for a group, fn(member, other) for a scalar / tensor."""
+        if isinstance(other, TensorGroup):
+            return TensorGroup(**{n: fn(v, other[n]) for n, v in self.items()})
+        return self._map(lambda v: fn(v, other))
+
+    def __add__(self, other):
+        return self._zip(other, lambda a, b: a + b)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._zip(other, lambda a, b: a - b)
+
+    def __mul__(self, other):
+        return self._zip(other, lambda a, b: a * b)
+
+    __rmul__ = __mul__
+
+    def __pow__(self, other):
+        return self._zip(other, lambda a, b: a ** b)
+
+    def to(self, *a, **k):
+        return self._map(lambda v: v.to(*a, **k))
+
+    def float(self):
+        return self._map(lambda v: v.float())
+
+    def clone(self):
+        return self._map(lambda v: v.clone())
+
+    def repeat_interleave(self, *a, **k):
+        return self._map(lambda v: v.repeat_interleave(*a, **k))
+
+    def split(self, group_size):
+        """Consecutive row blocks of `group_size` (the last one may be short): how training_loop.py:306-319 cuts a batch into per-GPU micro-batches."""
+        return [self[i:i + group_size] for i in range(0, len(self), group_size)]
+
+    # -- whole-group reductions (used to tie every member into a loss term: `x + 0.0 * group.max()`, loss.py:171,204,228) ------------------
     def max(self):
         return torch.stack([v.max() for v in self.values()]).max()
 
-    def to(self, *a, **k):
-        return TensorGroup(**{n: v.to(*a, **k) for n, v in self.items()})
+    def sum(self):
+        return torch.stack([v.sum() for v in self.values()]).sum()
+
+    def numel(self):
+        return sum(v.numel() for v in self.values())
+
+    def reduce_mean(self):
+        return self.sum() / self.numel()
