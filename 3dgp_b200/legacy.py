@@ -157,13 +157,61 @@ def _build(node, device, init=None):
     return net.eval().requires_grad_(False).to(device)
 
 
+_OWN_FORMAT = '3dgp_b200.snapshot.v1'
+
+
+def _to_plain_config(v):
+    """EasyDict / TensorGroup-free copy of constructor arguments: nested dicts, lists and scalars only."""
+    if isinstance(v, dict):
+        return {k: _to_plain_config(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [_to_plain_config(x) for x in v]
+    return v
+
+
+def save_network_pkl(f, networks, init, **entries):
+    """The writing side of `training_loop.py:478-484` for THIS package's modules.  networks: {'G': module, 'D': ..., 'G_ema': ...}; init: {name: (args,
+    kwargs)} -- the constructor arguments (config.build_networks' call) -- ; entries: plain data stored alongside (training_set_kwargs, cur_nimg, ...).
+    A network is stored as {format, class_name, init, state_dict (CPU tensors)}: weights + configuration, no code and no module objects, so the file loads
+    through the same allow-listed unpickler as a reference snapshot.  A reference installation reads the weights with
+    `G.load_state_dict(pickle.load(f)['G']['state_dict'])` -- the parameter / buffer names are the reference's."""
+    data = dict(entries)
+    for name, net in networks.items():
+        args, kw = init[name]
+        data[name] = {'format': _OWN_FORMAT, 'class_name': type(net).__name__, 'init': (_to_plain_config(list(args)), _to_plain_config(dict(kw))),
+                      'state_dict': collections.OrderedDict((k, v.detach().cpu().clone()) for k, v in net.state_dict().items())}
+    if isinstance(f, (str, bytes)):
+        import gzip
+        opener = gzip.open if str(f).endswith('.gz') else open
+        with opener(f, 'wb') as fh:
+            pickle.dump(data, fh, protocol=4)
+    else:
+        pickle.dump(data, f, protocol=4)
+
+
+def _build_own(entry, device):
+    from .training.networks_epigraf import Generator
+    from .training.networks_discriminator import Discriminator
+    cls = {'Generator': Generator, 'Discriminator': Discriminator}.get(entry['class_name'])
+    if cls is None:
+        raise RuntimeError(f'snapshot holds a {entry["class_name"]}; only Generator / Discriminator of the 3dgp model are built here')
+    args, kw = entry['init']
+    net = cls(*args, **{k: (EasyDict.init_recursively(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+    net.load_state_dict(entry['state_dict'], strict=True)
+    return net.eval().requires_grad_(False).to(device)
+
+
 def load_network_pkl(f, device='cpu', names=('G', 'D', 'G_ema'), init=None):
     """The reference's `legacy.load_network_pkl` role: networks of a snapshot as THIS package's modules (eval mode, no grad), other entries as plain data.
-    init: optional {name: (args, kwargs)} constructor arguments for entries whose class keeps none."""
+    Reads the reference's snapshots and the ones `save_network_pkl` writes.  init: optional {name: (args, kwargs)} constructor arguments for entries
+    whose class keeps none."""
     data = read_snapshot(f)
     out = {}
     for k, v in data.items():
-        if _module_state(v) is not None:
+        if isinstance(v, dict) and v.get('format') == _OWN_FORMAT:
+            if k in names:
+                out[k] = _build_own(v, device)
+        elif _module_state(v) is not None:
             if k in names:
                 out[k] = _build(v, device, (init or {}).get(k))
         else:

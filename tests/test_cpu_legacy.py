@@ -65,3 +65,36 @@ def test_snapshot_reader_refuses_arbitrary_globals():
         assert isinstance(out['x'], type) and issubclass(out['x'], lg._Record), obj
     ok = lg._SnapshotUnpickler(io.BytesIO(pickle.dumps({'t': torch.arange(3.0), 'd': collections.OrderedDict(a=1), 's': {1, 2}}))).load()
     assert torch.equal(ok['t'], torch.arange(3.0)) and ok['d'] == {'a': 1} and ok['s'] == {1, 2}
+
+
+def test_own_snapshot_round_trip_and_reference_side_state_dict(tmp_path):
+    """save_network_pkl -> load_network_pkl: same constructor arguments, same weights, eval mode / no grad like the reference's snapshots; the file holds no
+    module objects (it loads through the allow-listed unpickler), and its `state_dict` entries carry the reference's parameter names (a reference
+    installation reads them with load_state_dict)."""
+    import json
+    import pickle
+    lg = importlib.import_module('3dgp_b200.legacy')
+    cfgm = importlib.import_module('3dgp_b200.config')
+    kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    cfg = cfgm.make_config(**kw, learn_camera_dist=True)
+    torch.manual_seed(3)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    g = cfg.model.generator
+    init = {'G': ([], dict(cfg=g, img_resolution=cfg.dataset.resolution, img_channels=3, mapping_kwargs=dict(camera_cond=False, camera_cond_drop_p=0.0, mean_camera_params=None),
+                           fused_modconv_default='inference_only', num_fp16_res=0, conv_clamp=None)),
+            'D': ([], dict(cfg=cfg.model.discriminator, input_resolution=cfg.training.patch.resolution, img_channels=4, block_kwargs=dict(freeze_layers=0), mapping_kwargs={},
+                           epilogue_kwargs=dict(mbstd_group_size=4, feat_predict_dim=cfg.dataset.embedding_dim), num_fp16_res=0, conv_clamp=None))}
+    init['G_ema'] = init['G']
+    path = str(tmp_path / 'network-snapshot-000000.pkl')
+    lg.save_network_pkl(path, dict(G=G, D=D, G_ema=G), init, training_set_kwargs=dict(path='x.zip', resolution=32), cur_nimg=12345)
+    back = lg.load_network_pkl(path)
+    assert back['cur_nimg'] == 12345 and back['training_set_kwargs'] == dict(path='x.zip', resolution=32)
+    for name, net in (('G', G), ('D', D), ('G_ema', G)):
+        sd, sb = net.state_dict(), back[name].state_dict()
+        assert list(sd) == list(sb) and all(torch.equal(sd[k], sb[k]) for k in sd)
+        assert not back[name].training and not any(p.requires_grad for p in back[name].parameters())
+    assert back['G'].synthesis.camera_adaptor is not None                     # learn_camera_dist=true survived through the stored configuration
+    raw = pickle.load(open(path, 'rb'))                                          # plain pickle: no class of this package is referenced by the file
+    assert raw['G']['class_name'] == 'Generator' and isinstance(raw['G']['init'][1]['cfg'], dict) and type(raw['G']['init'][1]['cfg']) is dict
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'networks_meta.json')))
+    assert set(meta['D_keys']) == set(raw['D']['state_dict'])                    # the reference Discriminator's own state-dict keys (golden meta was written by the reference)
