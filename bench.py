@@ -406,12 +406,14 @@ def run_train_step(args, rank, world, local):
     alg_tf = conv_flops / (conv_ms * 1e-3) / 1e12
     n_l = max(len(cev), 1)
     traffic = CONV_TRAFFIC_BYTES_PER_LAUNCH.get(f'B{mb}')
+    # The comparison legs below are reported next to the headline, never instead of it: a failure inside one of them (say, cuDNN running out of workspace
+    # on the unfused path) is recorded under its key and the measured line is still printed.
     gpu_base = None
     if world == 1 and not args.no_gpu_baseline and not args.small:
-        gpu_base = gpu_baseline_step(tr, host, dev, dn, args)
+        gpu_base = _side_leg('gpu_baseline', gpu_baseline_step, tr, host, dev, dn, args)
     ginfer = None
     if world == 1 and not args.no_ginfer and not args.small:      # replicas only: measured at N = 1 (use --workload ginfer under torchrun for N > 1)
-        ginfer = ginfer_leg(tr.G_ema, cfg, dev, dn, rank, world)
+        ginfer = _side_leg('ginfer', ginfer_leg, tr.G_ema, cfg, dev, dn, rank, world)
     res = dict(
         metric='G+D training-step images/s at 256x256', value=world * B / (ms * 1e-3), unit='images/s', ms_per_step=ms,
         dtype='f32 storage; G convs bf16x3 on tcgen05 (three bf16 MMAs per product, fp32 accumulate: fp32-grade), tri-plane MLP 3xTF32; '
@@ -440,6 +442,23 @@ def run_train_step(args, rank, world, local):
     if ginfer is not None:
         res['ginfer'] = ginfer
     return res
+
+
+def _side_leg(name, fn, *a, **k):
+    """Runs a comparison leg; on failure returns {'error': ...} (traceback on stderr) instead of taking the headline measurement down with it."""
+    try:
+        return fn(*a, **k)
+    except Exception as e:          # noqa: BLE001 -- any failure of a side leg is reported, not raised
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        print(f'bench.py: side leg {name} failed: {e!r}', file=sys.stderr)
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.empty_cache()
+        except Exception:
+            pass
+        return dict(error=f'{type(e).__name__}: {e}'[:300])
 
 
 D_LOW_PRECISION_NAME = 'fp16 x fp16 forward products (bf16 x bf16 for products with a gradient operand)'
@@ -725,9 +744,10 @@ def main():
                 line[k] = res[k]
         if world == 1 and not args.no_cpu_baseline:
             if args.workload == 'train_step':
-                line['cpu_baseline'] = cpu_train_step(small=args.small, steps=1, warmup=0, sample_batch=args.cpu_sample_batch)[0]
+                cb = _side_leg('cpu_baseline', cpu_train_step, small=args.small, steps=1, warmup=0, sample_batch=args.cpu_sample_batch)
+                line['cpu_baseline'] = cb if isinstance(cb, dict) else cb[0]
             elif args.workload == 'raymarch':
-                line['cpu_baseline'] = cpu_raymarch(sample_rays=4096, repeats=2)
+                line['cpu_baseline'] = _side_leg('cpu_baseline', cpu_raymarch, sample_rays=4096, repeats=2)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

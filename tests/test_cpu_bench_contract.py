@@ -38,3 +38,14 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run(['--steps', '1', '--warmup', '0'], timeout=300)
     assert r.returncode != 0
     assert 'no CUDA device' in (r.stderr + r.stdout)
+
+
+def test_a_failing_side_leg_is_reported_under_its_key_and_does_not_raise(capsys):
+    """gpu_baseline / ginfer / cpu_baseline are comparison legs: an exception inside one becomes {'error': ...} so the headline line is still printed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_under_test', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    assert bench._side_leg('ok', lambda a, b=0: a + b, 2, b=3) == 5
+    out = bench._side_leg('gpu_baseline', lambda: (_ for _ in ()).throw(RuntimeError('CUDNN_STATUS_ALLOC_FAILED')))
+    assert out == {'error': 'RuntimeError: CUDNN_STATUS_ALLOC_FAILED'}
+    assert 'side leg gpu_baseline failed' in capsys.readouterr().err
