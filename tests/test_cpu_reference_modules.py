@@ -120,3 +120,54 @@ def test_reference_decoder_and_discriminator_on_our_tensor_core_route_wide(overl
     with ours['conv2d_gradfix'].no_weight_gradients():
         r1 = torch.autograd.grad([logits.sum()], [img], create_graph=True)[0]
     assert l2rel(r1.detach().numpy(), gold['D/r1_grads']) < 5e-4
+
+
+def test_reference_synthesis_network_on_our_renderer(overlay, monkeypatch):
+    """`src/training/tri_plane_renderer.py` row of INTEGRATION.md: the unmodified reference SynthesisNetwork.forward (networks_epigraf.py:210-262) with THIS repo's
+    ImportanceRenderer in place of its own -- called positionally `(planes, decoder, ray_o, ray_d, rendering_options)` in training and, for frames above
+    `max_batch_res`, through `run_batchwise(fn=self.renderer, data=dict(ray_origins=, ray_directions=), dim=1, planes=, decoder=, rendering_options=)`
+    (:232-240) in ray chunks; the decoder it hands over is the reference's own TriPlaneMLP.  Held to the reference goldens (image, depth, Gmain gradients)."""
+    ns, tc, ours = overlay
+    tpr = importlib.import_module('3dgp_b200.training.tri_plane_renderer')
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'networks.npz'))
+    kw, G, D, t, cam, pp = _build(ns, 'small')
+    B, N = t['z'].shape[0], kw['num_ray_steps']
+
+    class Injecting(tpr.ImportanceRenderer):
+        """Supplies the goldens' sampling variates (the reference draws them with torch.rand inside its renderer; the product takes them as options or from its
+        counter-based stream) -- sliced along the ray axis when the caller renders in chunks."""
+        def arm(self, u_coarse, u_fine):
+            self.u, self.cursor, self.calls = (u_coarse, u_fine), 0, 0
+
+        def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
+            R = ray_origins.shape[1]
+            ro = dict(rendering_options, mlp_mode=0, u_coarse=self.u[0][:, self.cursor:self.cursor + R].contiguous(), u_fine=self.u[1][:, self.cursor:self.cursor + R].contiguous())
+            self.cursor += R; self.calls += 1
+            return super().forward(planes, decoder, ray_origins, ray_directions, ns.dnnlib.EasyDict(**ro))
+    G.synthesis.renderer = Injecting('classical')
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    head = cases.depth_heads(B)
+    monkeypatch.setattr(np.random, 'choice', lambda *a, **k: head.copy())
+    G.train(); G.synthesis.nerf_noise_std = 0.0
+    G.synthesis.renderer.arm(t['u_coarse'], t['u_fine'])
+    with rh.injected_rng(randn=[n.clone() for n in noises]):
+        ws = G.mapping(t['z'], t['c'])
+        o = G.synthesis(ws, cam, patch_params=pp, render_opts=dict(concat_depth=True, return_depth=True))
+    assert G.synthesis.renderer.calls == 1
+    assert maxrel(o.img.detach().numpy(), gold['G/train/img']) < 1e-4 and maxrel(o.depth.detach().numpy(), gold['G/train/depth']) < 1e-4
+    D.train()
+    logits, _ = D(o.img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    loss = torch.nn.functional.softplus(-logits).mean()
+    assert abs(loss.item() - float(gold['G/loss'][0])) < 1e-4
+    names = cases.probe_params('G'); pars = dict(G.named_parameters())
+    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
+        assert l2rel(gr.numpy(), gold['G/grad/' + n]) < 5e-4, n
+    # eval, full frame rendered in ray chunks through run_batchwise's keyword call
+    G.eval()
+    ue = cases.eval_variates(kw, B)
+    G.synthesis.renderer.arm(torch.from_numpy(ue['u_coarse']), torch.from_numpy(ue['u_fine']))
+    with torch.no_grad():
+        oe = G.synthesis(ws.detach(), cam, noise_mode='const', render_opts=dict(concat_depth=True, return_depth=True, max_batch_res=8))
+    R, chunk = kw['img_resolution'] ** 2, N * 8 * 8                 # run_batchwise cuts the ray axis into chunks of num_ray_steps * max_batch_res^2 (:236)
+    assert G.synthesis.renderer.calls == -(-R // chunk) > 1 and G.synthesis.renderer.cursor == R
+    assert maxrel(oe.img.numpy(), gold['G/eval/img']) < 1e-4 and maxrel(oe.depth.numpy(), gold['G/eval/depth']) < 1e-4
