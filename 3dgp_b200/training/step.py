@@ -38,12 +38,14 @@ class GradBuckets:
     """Bucketed all-reduce of a flat gradient buffer, overlapped with the backward pass that fills it (training_loop.py:335-344 issues ONE blocking
     all-reduce after backward; here the transfer hides behind the remaining backward kernels).
 
-    The buffer is cut into contiguous buckets of whole parameters, built from its END: autograd reaches the last layers first, so bucket 0 (the
-    tail of the buffer -- for G the 512^2 / 256^2 blocks) completes first.  `arm()` is called right before the phase's FINAL backward; every
-    parameter's post-accumulate hook then reports `ready(i)`, and a bucket whose parameters are all ready is all-reduced asynchronously on the
-    process group's own stream (NCCL: ordered after the work already enqueued on the compute stream).  Buckets are launched strictly in index
-    order, so every rank issues the same sequence of collectives whatever its hook order.  `finish()` reduces what never completed (parameters
-    without a gradient in this phase) and waits for all transfers."""
+    The buffer is cut into contiguous buckets of whole parameters (built from its END, so that a bucket holds layers that finish together).  `arm()` is
+    called right before the phase's FINAL backward; every parameter's post-accumulate hook then reports `ready(i)`, and a bucket whose parameters are all
+    ready is all-reduced asynchronously on the process group's own stream (NCCL: ordered after the work already enqueued on the compute stream).
+    Every rank must issue the same SEQUENCE of collectives, so buckets are launched strictly in a fixed `order`: by default their index order; in steady
+    state the order in which they COMPLETED in the previous final backward of the same phase (`completion_order()`, a function of the static graph and
+    therefore identical on every rank).  Storage order alone is not enough: G registers its mapping network after the synthesis network, so the tail of
+    G's buffer -- bucket 0 -- holds the parameters whose gradients arrive LAST, and an index-ordered launch would hold every other bucket back until the
+    backward is over.  `finish()` reduces what never completed (parameters without a gradient in this phase) and waits for all transfers."""
 
     def __init__(self, flat, offsets, numels, bucket_elems=16 << 20):
         self.flat = flat
@@ -57,37 +59,55 @@ class GradBuckets:
         self.bucket_of = {i: b for b, m in enumerate(self.members) for i in m}
         self.armed = False
         self.launched_async = 0                     # buckets whose transfer started during the backward (diagnostics / tests)
+        self.fire_sequence = []                     # parameter indices in the order their gradients arrived in the last armed backward
 
-    def arm(self, world_size, group=None, expected=None):
+    def arm(self, world_size, group=None, expected=None, order=None):
         """expected: indices of the parameters this backward will produce gradients for (None: all).  A phase's graph is static, so the caller
-        passes the set that `fired` in the previous final backward of the same phase; a bucket then does not wait for parameters that never fire."""
+        passes the set that `fired` in the previous final backward of the same phase; a bucket then does not wait for parameters that never fire.
+        order: launch sequence of the buckets (a permutation of their indices; None: index order) -- the previous pass's `completion_order()`."""
         self.armed, self.world, self.group = True, world_size, group
         self.pending = [set(m) if expected is None else set(m) & set(expected) for m in self.members]
-        self.next, self.handles, self.launched_async, self.fired = 0, [], 0, set()
+        self.order = list(range(len(self.bounds))) if order is None else list(order)
+        assert sorted(self.order) == list(range(len(self.bounds))), 'order must be a permutation of the bucket indices'
+        self.next, self.handles, self.launched_async, self.fired, self.fire_sequence, self.on_wire = 0, [], 0, set(), [], set()
+        self.launch_log = []                        # (bucket, gradients arrived so far) per launch: how early each transfer started (diagnostics / tests)
         self._launch_ready()
 
+    def _launch(self, b):
+        lo, hi = self.bounds[b]
+        self.handles.append(dist.all_reduce(self.flat[lo:hi], group=self.group, async_op=True))
+        self.on_wire.add(b)
+        self.launch_log.append((b, len(self.fire_sequence)))
+
     def _launch_ready(self):
-        while self.next < len(self.bounds) and not self.pending[self.next]:
-            a, b = self.bounds[self.next]
-            self.handles.append(dist.all_reduce(self.flat[a:b], group=self.group, async_op=True))
+        while self.next < len(self.order) and not self.pending[self.order[self.next]]:
+            self._launch(self.order[self.next])
             self.next += 1
             self.launched_async += 1
 
     def ready(self, i):
         if self.armed:
+            if i not in self.fired:
+                self.fire_sequence.append(i)
             self.fired.add(i)
             b = self.bucket_of[i]
-            if b < self.next:       # its bucket is already on the wire: the sum would miss this rank's contribution
+            if b in self.on_wire:   # its bucket is already on the wire: the sum would miss this rank's contribution
                 raise RuntimeError('GradBuckets: a parameter outside the expected set produced a gradient after its bucket was all-reduced '
                                    '(the phase graph changed between iterations); set Trainer.overlap_allreduce = False')
             self.pending[b].discard(i)
             self._launch_ready()
 
+    def completion_order(self):
+        """Bucket indices sorted by when their last gradient arrived in the armed backward that just ran (buckets nothing fired for: first, they are
+        complete from the start).  Deterministic for a static graph, hence the same on every rank."""
+        at = {i: k for k, i in enumerate(self.fire_sequence)}
+        done_at = [max((at[i] for i in m if i in at), default=-1) for m in self.members]
+        return sorted(range(len(self.members)), key=lambda b: (done_at[b], b))
+
     def finish(self):
         """After the backward: reduce the remaining buckets, wait for every transfer (the compute stream then sees the reduced buffer)."""
-        while self.next < len(self.bounds):
-            a, b = self.bounds[self.next]
-            self.handles.append(dist.all_reduce(self.flat[a:b], group=self.group, async_op=True))
+        while self.next < len(self.order):
+            self._launch(self.order[self.next])
             self.next += 1
         for h in self.handles:
             h.wait()
@@ -242,6 +262,7 @@ class Trainer:
         # of training_loop.py:335-344 is the shipped schedule.
         self.overlap_allreduce = False
         self._fired = {}         # phase -> parameters that produced gradients in its last final backward (GradBuckets.arm `expected`)
+        self._order = {}         # phase -> bucket launch sequence = completion order of that backward (GradBuckets.arm `order`)
         self.cur_nimg = 0
         self.it = 0
 
@@ -256,7 +277,7 @@ class Trainer:
         for j, (r_mb, g_mb) in enumerate(mbs):                 # gradient accumulation, training_loop.py:329-330
             # the last backward of the phase streams its gradient buckets into the all-reduce while it is still running
             # (never in the first two iterations: first-use kernel loading / allocator growth must not interleave with collectives already spinning on peers)
-            arm = (lambda: opt.buckets.arm(self.world_size, expected=self._fired.get(name))) if (self.flat and self.world_size > 1 and self.overlap_allreduce
+            arm = (lambda: opt.buckets.arm(self.world_size, expected=self._fired.get(name), order=self._order.get(name))) if (self.flat and self.world_size > 1 and self.overlap_allreduce
                                                                                                      and self.it >= 2 and j == len(mbs) - 1) else None
             stats = self.loss.accumulate_gradients(phase=name, real_data=r_mb, gen_data=g_mb, gain=gain, cur_nimg=self.cur_nimg, render_opts=render_opts,
                                                    final_backward=arm)
@@ -266,6 +287,7 @@ class Trainer:
             opt.step(self.world_size, ema_beta=ema_beta)
             if armed:
                 self._fired[name] = set(opt.buckets.fired)
+                self._order[name] = opt.buckets.completion_order()
         else:
             allreduce_gradients([p for p in module.parameters() if p.numel() > 0], self.world_size)
             opt.step()

@@ -117,6 +117,77 @@ def test_bucketed_gradient_allreduce_overlaps_and_matches_one_shot_gloo(world):
     assert torch.allclose(reduced[0].double(), want, rtol=1e-6, atol=1e-6)
 
 
+class _LateTail(torch.nn.Module):
+    """Like the Generator (networks_epigraf.py: `synthesis` registered before `mapping`): the parameters at the END of the flat buffer belong to the layer
+    that runs FIRST, so their gradients arrive last."""
+    def __init__(self):
+        super().__init__()
+        self.body = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+        self.first = torch.nn.Linear(6, 6)
+
+    def forward(self, x):
+        return self.body(self.first(x))
+
+
+def _late_tail_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    stepm = importlib.import_module('3dgp_b200.training.step')
+    torch.manual_seed(0)
+    net = _LateTail()
+    params = list(net.parameters())
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off); off += -(-p.numel() // 8) * 8
+    flat = torch.zeros(off)
+    for p, o in zip(params, offsets):
+        p.grad = flat[o:o + p.numel()].view(p.shape)
+    bk = stepm.GradBuckets(flat, offsets, [p.numel() for p in params], bucket_elems=64)
+    for i, p in enumerate(params):
+        p.register_post_accumulate_grad_hook(lambda _p, i=i: bk.ready(i))
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(20 + rank))
+    net(x).square().sum().backward()
+    local = flat.clone(); flat.zero_()
+    bk.arm(world)                                    # index order: bucket 0 (the tail = `first`) completes last and holds every other bucket back
+    net(x).square().sum().backward()
+    log_index = list(bk.launch_log)
+    bk.finish()
+    reduced_index = flat.clone(); flat.zero_()
+    order = bk.completion_order()
+    bk.arm(world, expected=set(bk.fired), order=order)   # previous completion order: transfers start as soon as the body's last layers are done
+    net(x).square().sum().backward()
+    log_order = list(bk.launch_log)
+    bk.finish()
+    q.put((rank, len(bk.bounds), order, log_index, log_order, local.numpy(), reduced_index.numpy(), flat.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_bucket_launch_order_follows_the_previous_completion_order_gloo_world2():
+    """With the first layer's parameters at the tail of the buffer (the Generator's layout), index-ordered launching starts every transfer only after the
+    LAST gradient; launching in the previous pass's completion order starts the first transfer after the first bucket's gradients -- same sums either way,
+    same sequence on both ranks."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_late_tail_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, nb, order, log_i, log_o, loc0, ri0, ro0), (_, nb1, order1, log_i1, log_o1, loc1, ri1, ro1) = res
+    n_params = 8
+    assert nb == nb1 >= 3 and order == order1 and log_i == log_i1 and log_o == log_o1          # identical collective sequence on both ranks
+    assert order[-1] == 0 and order != list(range(nb))                                          # the tail bucket completes last
+    assert [b for b, _ in log_i] == list(range(nb)) and all(k == n_params for _, k in log_i)    # index order: everything waits for the last gradient
+    assert [b for b, _ in log_o] == order and log_o[0][1] <= n_params // 2                      # completion order: the first transfer starts early
+    want = torch.from_numpy(loc0) + torch.from_numpy(loc1)
+    for r in (ri0, ri1, ro0, ro1):
+        assert torch.equal(torch.from_numpy(r), want)
+
+
 def _trainer_worker(rank, world, port, q):
     """One optimisation step of the REAL Generator / Discriminator / loss on each rank (CPU modules on the emulated C ABI, tests/abi_emulator.py), gloo
     carrying the per-phase gradient all-reduce: ranks start from different initialisations and see different data."""
