@@ -38,6 +38,43 @@ def sample_rays(c2w, fov, resolution: Tuple[int, int], patch_params: Dict = None
     return o_world, d_world
 
 
+def get_ray_limits_box(rays_o, rays_d, box_size):
+    """Entry / exit distance of each ray through the axis-aligned cube [-box_size/2, box_size/2]^3 (slab test), (-1, -2) where the ray misses it;
+    rays [..., 3] -> two [..., 1] tensors.  The launcher's geometry checks use it (tri_plane_renderer.py:409-461); the render kernel itself marches the
+    fixed [ray_start, ray_end] interval of configs/model/3dgp.yaml."""
+    o = rays_o.detach().reshape(-1, 3)
+    inv = 1 / rays_d.detach().reshape(-1, 3)
+    half = box_size / 2
+    t_a, t_b = (-half - o) * inv, (half - o) * inv                # per-axis crossings of the two faces
+    near, far = torch.minimum(t_a, t_b), torch.maximum(t_a, t_b)
+    # slabs are intersected in x, y, z order; a ray is rejected when an interval starts after the running one has ended (or the reverse) -- comparisons
+    # with NaN (a ray inside a face plane and parallel to it) are false, exactly like the sequential form
+    t0, t1 = near[:, 0], far[:, 0]
+    hit = torch.ones_like(t0, dtype=torch.bool)
+    for ax in (1, 2):
+        hit &= ~((t0 > far[:, ax]) | (near[:, ax] > t1))
+        t0, t1 = torch.max(t0, near[:, ax]), torch.min(t1, far[:, ax])
+    t0 = torch.where(hit, t0, torch.full_like(t0, -1))
+    t1 = torch.where(hit, t1, torch.full_like(t1, -2))
+    shape = tuple(rays_o.shape[:-1]) + (1,)
+    return t0.reshape(shape), t1.reshape(shape)
+
+
+def validate_image_plane(fov, radius, scale=1.0, step=1e-2, device='cpu'):
+    """True when, from every camera position on the sphere of `radius` (a yaw x pitch grid of pi/2/step angles each), the four corner rays of the image
+    plane pass through the scene cube of half-extent `scale` -- the configuration check of src/train.py:211-215 (tri_plane_renderer.py:531-556)."""
+    from ..dnnlib import TensorGroup
+    from .rendering_utils import compute_cam2world_matrix
+    n = int((np.pi / 2) / step)
+    yaw, pitch = torch.meshgrid(torch.linspace(0, np.pi * 2, steps=n, device=device), torch.linspace(0, np.pi, steps=n, device=device), indexing='ij')
+    angles = torch.stack([yaw.reshape(-1), pitch.clamp(1e-7, np.pi - 1e-7).reshape(-1), torch.zeros(n * n, device=device)], dim=1)
+    cams = TensorGroup(angles=angles, radius=torch.full([n * n], float(radius), device=device), fov=torch.full([n * n], float(fov), device=device),
+                       look_at=torch.zeros_like(angles))
+    ray_o, ray_d = sample_rays(compute_cam2world_matrix(cams), fov=cams.fov, resolution=(2, 2), patch_params=None, device=device)
+    t_in, t_out = get_ray_limits_box(ray_o, ray_d, box_size=scale * 2)
+    return bool((t_out > t_in).all().item())
+
+
 class ImportanceRenderer(torch.nn.Module):
     def __init__(self, ray_marcher_type: str):
         super().__init__()

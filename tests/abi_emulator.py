@@ -374,18 +374,18 @@ FakeLib.gp3d_generate_rays = staticmethod(_generate_rays)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------
-def install(monkeypatch):
+def install(monkeypatch, package='3dgp_b200'):
     """Swaps the whole emulation in: the ctypes library, the tensor-core launchers, the two plugins, and the CUDA-only guards of the public wrappers
     (each wrapper is entered right below its guard, at the autograd Function it dispatches to).  Eligibility predicates keep their shape rules and lose
     only the `is_cuda` clause, so the routing (fused node / tensor-core primitive / ATen) is the one a GPU run takes."""
     import contextlib
     import importlib
-    _lib = importlib.import_module('3dgp_b200._lib')
-    tc = importlib.import_module('3dgp_b200.torch_utils.ops.tc')
-    modconv = importlib.import_module('3dgp_b200.torch_utils.ops.modconv')
-    upf = importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d')
-    bact = importlib.import_module('3dgp_b200.torch_utils.ops.bias_act')
-    gradfix = importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix')
+    _lib = importlib.import_module(package + '._lib')
+    tc = importlib.import_module(package + '.torch_utils.ops.tc')
+    modconv = importlib.import_module(package + '.torch_utils.ops.modconv')
+    upf = importlib.import_module(package + '.torch_utils.ops.upfirdn2d')
+    bact = importlib.import_module(package + '.torch_utils.ops.bias_act')
+    gradfix = importlib.import_module(package + '.torch_utils.ops.conv2d_gradfix')
     from oracle import restated as R
     fake = FakeLib()
     monkeypatch.setattr(_lib, 'lib', lambda: fake)

@@ -109,3 +109,26 @@ def test_wrapper_rejects_malformed_inputs():
         rm.render_rays(t['planes'], t['w1'][:, :-1], t['b1'], t['w2'], t['b2'], t['ray_o'], t['ray_d'], u_coarse=t['u_coarse'], u_fine=t['u_fine'], **common)
     with pytest.raises(RuntimeError, match='float32 or float16'):
         rm.render_rays(t['planes'].double(), t['w1'], t['b1'], t['w2'], t['b2'], t['ray_o'], t['ray_d'], u_coarse=t['u_coarse'], u_fine=t['u_fine'], **common)
+
+
+def test_launcher_geometry_helpers_equal_the_reference():
+    """`get_ray_limits_box` / `validate_image_plane` (kept in the overlaid tri_plane_renderer.py because src/train.py:29,211 imports them): bit-identical
+    to the reference's slab test on random, missing and axis-parallel rays, same verdicts on camera configurations either side of the limit."""
+    import importlib
+    import pytest
+    import torch
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('the unmodified reference is only present in the build container')
+    ours = importlib.import_module('3dgp_b200.training.tri_plane_renderer')
+    ref = rh.load().tri_plane_renderer
+    g = torch.Generator().manual_seed(0)
+    o = torch.randn(3, 50, 3, generator=g) * 1.5
+    d = torch.nn.functional.normalize(torch.randn(3, 50, 3, generator=g), dim=-1)
+    d[0, 0] = torch.tensor([1.0, 0.0, 0.0]); d[0, 1] = torch.tensor([0.0, 0.0, -1.0]); o[0, 1] = torch.tensor([0.2, 0.3, 2.0])
+    for box in (1.0, 2.0, 4.0):
+        a, b = ref.get_ray_limits_box(o, d, box), ours.get_ray_limits_box(o, d, box)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and 0 < int((a[0] >= 0).sum()) < a[0].numel()
+    verdicts = [(fov, r, s, ours.validate_image_plane(fov, r, s, step=5e-2)) for fov, r, s in ((45.0, 1.0, 0.5), (10.0, 1.0, 0.5), (120.0, 3.0, 0.5), (30.0, 2.0, 0.5))]
+    assert [v[3] for v in verdicts] == [True, True, False, False]
+    assert all(v[3] == ref.validate_image_plane(v[0], v[1], v[2], step=5e-2) for v in verdicts)
