@@ -93,6 +93,41 @@ class TensorGroup(EasyDict):
     def repeat_interleave(self, *a, **k):
         return self._map(lambda v: v.repeat_interleave(*a, **k))
 
+    def detach(self):
+        return self._map(lambda v: v.detach())
+
+    def cpu(self):
+        return self._map(lambda v: v.cpu())
+
+    def clamp(self, *a, **k):
+        return self._map(lambda v: v.clamp(*a, **k))
+
+    def permute(self, *a, **k):
+        return self._map(lambda v: v.permute(*a, **k))
+
+    def mean(self, *a, **k):
+        """Member-wise mean (e.g. the mean camera of a sample, inference_utils.py:204); the scalar over everything is `reduce_mean()`."""
+        return self._map(lambda v: v.mean(*a, **k))
+
+    def reshape_each(self, new_shape_of):
+        """Each member reshaped to `new_shape_of(member)` (inference_utils.py:97)."""
+        return self._map(lambda v: v.reshape(new_shape_of(v)))
+
+    @property
+    def device(self):
+        return self.values()[0].device
+
+    @property
+    def shapes(self):
+        return [v.shape for v in self.values()]
+
+    @staticmethod
+    def cat(groups, dim=0):
+        """Groups with the same members joined member by member."""
+        names = groups[0].keys()
+        assert all(set(g.keys()) == set(names) for g in groups), [g.keys() for g in groups]
+        return TensorGroup(**{n: torch.cat([g[n] for g in groups], dim=dim) for n in names})
+
     def split(self, group_size):
         """Consecutive row blocks of `group_size` (the last one may be short): how training_loop.py:306-319 cuts a batch into per-GPU micro-batches."""
         return [self[i:i + group_size] for i in range(0, len(self), group_size)]

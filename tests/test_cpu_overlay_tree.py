@@ -90,6 +90,21 @@ with torch.no_grad():
     lg, ft = D(torch.from_numpy(gold['G/train/img']), t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
     assert maxrel(lg.numpy(), gold['D/logits']) < 1e-4 and maxrel(ft.numpy(), gold['D/feats']) < 1e-4
 
+# the reference's inference helpers and its metric loop's call pattern (src/training/inference_utils.py, metric_utils.py:303-319, 343-344) on this Generator
+import src.training.inference_utils as iu
+G.eval()
+with torch.no_grad():
+    z2, c2 = t['z'][:2], t['c'][:2]
+    cp = iu.sample_posterior_camera_params(G, z2, c2)
+    img = G(z=z2[:1], c=c2[:1], camera_params=cp[:1], camera_angles_cond=cp.angles[:1], noise_mode='const', render_opts=dict(cut_quantile=0.0))
+    assert torch.is_tensor(img) and tuple(img.shape) == (1, 3, kw['img_resolution'], kw['img_resolution']) and torch.isfinite(img).all()
+    frames = iu.generate(ED(batch_size=1), G, ws=G.mapping(z=z2, c=c2), camera_params=cp, verbose=False, render_opts=dict(return_depth=True, return_depth_adapted=True))
+    assert isinstance(frames, dnnlib.TensorGroup) and set(frames.keys()) == {'img', 'depth', 'depth_adapted'} and len(frames) == 2       # TensorGroup.cat of two batches
+    assert tuple(frames.depth.shape) == (2, 1, kw['img_resolution'], kw['img_resolution']) and float(frames.img.min()) >= 0.0 and float(frames.img.max()) <= 1.0
+    mean_cam = iu.approximate_mean_camera_params(G, num_samples=16)
+    assert tuple(mean_cam.angles.shape) == (1, 3)
+G.train()
+
 # the tree's own loss.py (reference file) runs its phases on these modules
 cfgm = importlib.import_module('3dgp_b200.config')      # only for the composed experiment configuration (a plain nested dict)
 cfg = ED.init_recursively(json.loads(json.dumps(cfgm.make_config(**{k: v for k, v in kw.items() if k != 'learn_camera_dist'}, kd_weight=1.0, batch_size=4))))

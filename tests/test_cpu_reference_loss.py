@@ -114,7 +114,7 @@ def test_tensor_group_has_the_reference_container_surface():
             for i, j in zip(x, y):
                 same(i, j)
         elif hasattr(x, 'items'):
-            fx, fy = flat(x), flat(y)
+            fx, fy = sorted(flat(x), key=lambda kv: kv[0]), sorted(flat(y), key=lambda kv: kv[0])      # the reference's `cat` walks a set of names: member order is not part of the contract
             assert [k for k, _ in fx] == [k for k, _ in fy]
             for (_, i), (_, j) in zip(fx, fy):
                 same(i, j)
@@ -122,10 +122,16 @@ def test_tensor_group_has_the_reference_container_surface():
             assert x == y
     ops = [lambda t: t + 1.5, lambda t: 2 + t, lambda t: t - 0.5, lambda t: t * 3, lambda t: 0.0 * t, lambda t: t ** 2, lambda t: t + t, lambda t: t * t, lambda t: t - t,
            lambda t: t.max(), lambda t: t.sum(), lambda t: t.numel(), lambda t: t.reduce_mean(), lambda t: t.clone(), lambda t: t.float(), lambda t: t.to(torch.float64),
-           lambda t: t.repeat_interleave(2, dim=0), lambda t: t.split(2), lambda t: t[1:3], lambda t: len(t), lambda t: t.shape, lambda t: t.keys()]
+           lambda t: t.repeat_interleave(2, dim=0), lambda t: t.split(2), lambda t: t[1:3], lambda t: len(t), lambda t: t.shape, lambda t: t.keys(),
+           lambda t: t.detach(), lambda t: t.cpu(), lambda t: t.clamp(-0.5, 0.5), lambda t: str(t.device)]
+    flat_ops = [lambda t: t.reshape_each(lambda v: [v.shape[0], 1, -1]).permute(0, 2, 1), lambda t: t.mean(dim=0, keepdim=True), lambda t: t.reshape_each(lambda v: [v.shape[0], -1]),
+                lambda t: [tuple(s) for s in t.shapes], lambda t: type(t).cat([t, t * 2], dim=0), lambda t: t.split(3)]
     a, b = mk(ns.dnnlib.TensorGroup), mk(dn.TensorGroup)
     for f in ops:
         same(f(a), f(b))
+    fa, fb = (T(angles=angles.clone(), fov=fov.clone()) for T in (ns.dnnlib.TensorGroup, dn.TensorGroup))      # member-wise tensor methods: flat groups (the reference's do not recurse)
+    for f in flat_ops:
+        same(f(fa), f(fb))
     t = mk(dn.TensorGroup)
     t.fov = t.fov * 2.0                                  # member assignment, as loss.py:172-175 does on the rolled regulariser groups
     assert torch.equal(t.fov, fov * 2.0) and len(t) == 5
