@@ -197,3 +197,58 @@ def test_embeddings_memmap_and_generator_side_batch(tmp_path):
     np.testing.assert_array_equal(g.c[0].numpy(), ds.get_label(pick[0]))
     np.testing.assert_allclose(g.camera_params.angles[0].numpy(), ds.get_camera_angles(pick[0]), rtol=0, atol=0)      # `custom`: cameras sit on dataset angles
     assert tuple(g.camera_params.look_at.shape) == (8, 3) and tuple(g.camera_angles_cond.shape) == (8, 3)
+
+
+def test_our_dataset_under_the_reference_loader_sampler_and_grid_setup():
+    """The reference's OWN data path around the dataset class (src/train.py:109-134 `init_dataset`, training_loop.py:96-100 InfiniteSampler + DataLoader,
+    inference_utils.py:20-39 `setup_snapshot_image_grid`) run once on the reference's ImageFolderDataset and once on this repo's, on the committed depth
+    fixture: constructor keywords as train.py passes them, `mean_camera_params`, `get_camera_angles`, collated batches (every key, dtype and value), the
+    snapshot grid -- identical; this repo's class also survives DataLoader worker processes."""
+    import copy
+    import types
+    from oracle import png_spec, ref_harness as rh
+    if not rh.available():
+        pytest.skip('the unmodified reference is only present in the build container')
+    ns = rh.load()
+    import src.training.dataset as ref_ds
+    import src.training.inference_utils as iu
+    from src.torch_utils import misc
+    ED = ns.dnnlib.EasyDict
+    dcfg = ED.init_recursively(json.loads(json.dumps(_cfg(True, dist='custom', c_dim=2))))
+    cam_cfg = copy.deepcopy(rh.make_cfg()[0]['camera']); cam_cfg['origin']['angles']['dist'] = 'custom'
+    cfg = ED.init_recursively(dict(training=dict(use_depth=True), camera=cam_cfg))
+    path = os.path.join(GOLD, 'tiny_dataset_depth.zip')
+
+    def sampler(ds):        # torch >= 2.2 dropped Sampler.__init__(data_source), which misc.py:118 still calls: set the fields, run the unmodified __iter__
+        s = misc.InfiniteSampler.__new__(misc.InfiniteSampler)
+        s.dataset, s.rank, s.num_replicas, s.shuffle, s.seed, s.window_size = ds, 0, 1, True, 0, 0.5
+        return s
+
+    def walk(cls):
+        ds = cls(path=path, max_size=None, use_depth=True, cfg=dcfg)                                                      # train.py:111-114
+        ds = cls(path=path, use_depth=True, cfg=dcfg, resolution=ds.resolution, max_size=len(ds), random_seed=0)            # train.py:115-116,180
+        out = dict(mean=torch.from_numpy(ds.mean_camera_params), angles=np.array([ds.get_camera_angles(i) for i in range(len(ds))]),
+                   flags=(ds.has_labels, ds.has_depth, list(ds.image_shape), list(ds.label_shape), ds.resolution, ds.num_channels))
+        it = iter(torch.utils.data.DataLoader(dataset=ds, sampler=sampler(ds), batch_size=4, num_workers=0))
+        out['batches'] = [next(it), next(it)]
+        np.random.seed(0); torch.manual_seed(0)
+        out['grid'] = iu.setup_snapshot_image_grid(training_set=ds, cfg=cfg)
+        return out, ds
+
+    old = ref_ds.pyspng
+    ref_ds.pyspng = types.SimpleNamespace(load=png_spec.load)      # pyspng is absent here: the specification decoder stands in (oracle/png_spec.py)
+    try:
+        a, _ = walk(ref_ds.ImageFolderDataset)
+    finally:
+        ref_ds.pyspng = old
+    b, ours = walk(dsmod.ImageFolderDataset)
+    assert torch.equal(a['mean'], b['mean']) and np.array_equal(a['angles'], b['angles']) and a['flags'] == b['flags']
+    for x, y in zip(a['batches'], b['batches']):
+        assert set(x) == set(y) == {'image', 'label', 'camera_angles', 'depth', 'embedding'}
+        assert all(x[k].dtype == y[k].dtype and torch.equal(x[k], y[k]) for k in x)
+    (ga, ia, da, la, ca), (gb, ib, db, lb, cb) = a['grid'], b['grid']
+    assert tuple(ga) == tuple(gb) and np.array_equal(ia, ib) and np.array_equal(da, db) and np.array_equal(la, lb) and all(torch.equal(ca[k], cb[k]) for k in ca.keys())
+    it = iter(torch.utils.data.DataLoader(dataset=ours, sampler=sampler(ours), batch_size=4, num_workers=2, prefetch_factor=2))      # training_loop.py:100, c.data_loader_kwargs
+    w = next(it)
+    assert all(torch.equal(w[k], b['batches'][0][k]) for k in w)
+    del it
