@@ -171,3 +171,30 @@ def test_reference_synthesis_network_on_our_renderer(overlay, monkeypatch):
     R, chunk = kw['img_resolution'] ** 2, N * 8 * 8                 # run_batchwise cuts the ray axis into chunks of num_ray_steps * max_batch_res^2 (:236)
     assert G.synthesis.renderer.calls == -(-R // chunk) > 1 and G.synthesis.renderer.cursor == R
     assert maxrel(oe.img.numpy(), gold['G/eval/img']) < 1e-4 and maxrel(oe.depth.numpy(), gold['G/eval/depth']) < 1e-4
+
+
+def test_reference_module_summary_walks_our_networks(monkeypatch, capsys):
+    """Start-up step of the reference loop (training_loop.py:140-160): `misc.print_module_summary` hooks every sub-module of G and D, runs one forward with the
+    loop's own arguments (z, c, camera_params from `sample_camera_params`; the patch-sized image, zero patch parameters and camera angles for D) and tabulates
+    parameters / buffers / output shapes -- on THIS repo's modules."""
+    emu.install(monkeypatch)
+    ns = rh.load()
+    from src.torch_utils import misc
+    from src.training.rendering_utils import sample_camera_params
+    cfgm = importlib.import_module('3dgp_b200.config')
+    kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    cfg = cfgm.make_config(**kw, kd_weight=1.0, batch_size=4)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    tb = 2
+    with torch.no_grad():
+        G.eval(); D.eval()
+        z, c, angles = torch.randn([tb, G.z_dim]), torch.zeros([tb, G.c_dim]), torch.zeros([tb, 3])
+        cam = sample_camera_params(ns.dnnlib.EasyDict.init_recursively(json.loads(json.dumps(G.cfg.camera))), tb, 'cpu', angles)
+        img = misc.print_module_summary(G, [z[[0]], c[[0]]], module_kwargs={'camera_params': cam[[0]]})
+        assert torch.is_tensor(img) and tuple(img.shape) == (1, 3, kw['img_resolution'], kw['img_resolution'])
+        img = img.repeat(tb, 1, 1, 1)[:, :, :cfg.training.patch.resolution, :cfg.training.patch.resolution][:, [0]].repeat(1, 4, 1, 1)
+        logits = misc.print_module_summary(D, [img, c], module_kwargs={'patch_params': {'scales': torch.zeros(tb, 2), 'offsets': torch.zeros(tb, 2)}, 'camera_angles': torch.zeros(tb, 3)})
+    text = capsys.readouterr().out
+    n_g, n_d = sum(p.numel() for p in G.parameters()), sum(p.numel() for p in D.parameters())
+    assert str(n_d) in text and 'synthesis.tri_plane_decoder.b32:0' in text and 'synthesis.depth_adaptor.head' in text and 'b4.mbstd' in text      # every visited sub-module is listed; D's total is its parameter count
+    assert n_g > 0 and tuple(logits[0].shape) == (tb,)                # D returns (logits, features)
