@@ -68,7 +68,7 @@ G = dnnlib.util.construct_class_by_name(class_name='src.training.networks_epigra
 D = dnnlib.util.construct_class_by_name(class_name='src.training.networks_discriminator.Discriminator', cfg=ED.init_recursively(Dc), input_resolution=m['patch_res'], img_channels=4,
                                         block_kwargs=dict(freeze_layers=0), mapping_kwargs={}, epilogue_kwargs=dict(mbstd_group_size=4, feat_predict_dim=m['embedding_dim']),
                                         num_fp16_res=0, conv_clamp=None).train().requires_grad_(False)
-assert type(G).__module__ == 'src.training.networks_epigraf' and isinstance(G.synthesis.renderer, ImportanceRenderer)
+assert type(G).__name__ == 'Generator' and type(G).__mro__[1].__module__ == 'src.training.networks_epigraf' and isinstance(G.synthesis.renderer, ImportanceRenderer)   # [0] is persistence's wrapper class
 assert {k: list(v.shape) for k, v in G.state_dict().items()} == meta['G_keys'] and {k: list(v.shape) for k, v in D.state_dict().items()} == meta['D_keys']
 G.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['G_keys'].items()}, G.state_dict(), seed=100))
 D.load_state_dict(cases.fill_state_dict({k: tuple(v) for k, v in meta['D_keys'].items()}, D.state_dict(), seed=200))
@@ -111,7 +111,7 @@ cfg = ED.init_recursively(json.loads(json.dumps(cfgm.make_config(**{k: v for k, 
 loss = dnnlib.util.construct_class_by_name(class_name='src.training.loss.StyleGAN2Loss', device='cpu', G=G, D=D, augment_pipe=None, cfg=cfg, r1_gamma=1.0)   # training_loop.py:186
 res = kw['img_resolution']
 g = torch.Generator().manual_seed(1)
-for phase, module in (('Dmain', D), ('Dreg', D)):          # Dmain runs the generator too (run_G under no_grad); Gmain's backward on these modules: tests/test_cpu_reference_loss.py
+for phase, module in (('Dmain', D),):          # Dmain runs the generator too (run_G under no_grad); Gmain / R1 on these modules: tests/test_cpu_reference_loss.py
     G.requires_grad_(module is G); D.requires_grad_(module is D)
     for p in module.parameters():
         p.grad = None
@@ -121,17 +121,67 @@ for phase, module in (('Dmain', D), ('Dreg', D)):          # Dmain runs the gene
     loss.accumulate_gradients(phase=phase, real_data=real, gen_data=gen, gain=1, cur_nimg=400000)
     grads = [p.grad for p in module.parameters() if p.grad is not None]
     assert len(grads) > 20 and all(torch.isfinite(x).all() for x in grads) and sum(float(x.abs().sum()) for x in grads) > 0, phase
+# training_loop.py:478-484: snapshot = CPU copies of the networks, pickled through the reference's persistence hooks (the overlaid classes carry the decorator)
+import copy, pickle
+from src.torch_utils import persistence
+assert persistence.is_persistent(G) and persistence.is_persistent(G.synthesis.tri_plane_decoder.b8.conv1) and not persistence.is_persistent(D)   # as in the reference
+snap = dict(G=copy.deepcopy(G).eval().requires_grad_(False).cpu(), G_ema=copy.deepcopy(G).eval().requires_grad_(False).cpu(), training_set_kwargs=dict(path='x.zip'))
+with open(sys.argv[3], 'wb') as f:
+    pickle.dump(snap, f)
+torch.save({k: v.clone() for k, v in G.state_dict().items()}, sys.argv[3] + '.sd')
 print('OVERLAY OK', e)
 '''
 
 
+LOADER = r'''
+import os, pickle, sys
+import torch
+overlay, repo, path = sys.argv[1], sys.argv[2], sys.argv[3]
+sys.path[:0] = [overlay, os.path.join(repo, 'tests'), repo]
+from oracle import ref_harness as rh
+rh._install_stubs()
+import src.torch_utils.persistence                      # all that pickle needs to find `_reconstruct_persistent_obj`; no network module has been imported
+assert not any(m.startswith('src.training.networks') for m in sys.modules)
+with open(path, 'rb') as f:
+    snap = pickle.load(f)
+G = snap['G_ema']
+assert type(G).__name__ == 'Generator' and type(G).__mro__[1].__module__.startswith('_imported_module_'), [c.__module__ for c in type(G).__mro__[:3]]   # rebuilt from the embedded source
+sd = torch.load(path + '.sd')
+got = G.state_dict()
+assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+assert G.init_kwargs['img_resolution'] == G.img_resolution and not G.training
+# the same file through this repo's reader (3dgp_b200/legacy.py: no exec of the embedded source)
+import importlib
+lg = importlib.import_module('3dgp_b200.legacy')
+back = lg.load_network_pkl(path, names=('G_ema',))
+assert all(torch.equal(back['G_ema'].state_dict()[k], sd[k]) for k in sd)
+print('SNAPSHOT OK', len(sd))
+'''
+
+
+def _make_overlay(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_overlay', os.path.join(ROOT, 'tools', 'make_overlay.py'))
+    tool = importlib.util.module_from_spec(spec); spec.loader.exec_module(tool)
+    out, written = tool.install(rh.REF_ROOT, dest=str(tmp_path / 'overlay'))
+    assert out == str(tmp_path / 'overlay' / 'src') and len(written) == sum(len(v) for v in OVERLAY.values())
+    assert sorted(written) == sorted((f'{k}/{n}' if k else n) for k, v in OVERLAY.items() for n in v)
+    for rel in written:                                    # no relative import survives (persistence.py execs module sources in anonymous modules)
+        text = open(os.path.join(out, rel)).read()
+        assert not [l for l in text.splitlines() if l.lstrip().startswith(('from .', 'import .'))], rel
+    assert os.path.exists(os.path.join(out, 'csrc', 'conv_tc.cu')) and os.path.exists(str(tmp_path / 'overlay' / 'include' / 'gp3d_b200.h'))
+    return str(tmp_path / 'overlay')
+
+
 def test_reference_tree_with_our_files_laid_over_it(tmp_path):
-    dst = tmp_path / 'overlay' / 'src'
-    shutil.copytree(os.path.join(rh.REF_ROOT, 'src'), dst, ignore=shutil.ignore_patterns('__pycache__', '*.cu', '*.cpp', '*.h', '*.pyc'))
-    for sub, names in OVERLAY.items():
-        for n in names:
-            shutil.copyfile(os.path.join(ROOT, '3dgp_b200', sub, n), dst / sub / n)
+    overlay = _make_overlay(tmp_path)                      # tools/make_overlay.py: the overlay recipe of INTEGRATION.md as a command
     script = tmp_path / 'drive.py'
     script.write_text(SCRIPT)
-    r = subprocess.run([sys.executable, str(script), str(tmp_path / 'overlay'), ROOT], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    r = subprocess.run([sys.executable, str(script), overlay, ROOT, str(tmp_path / 'snapshot.pkl')], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0 and 'OVERLAY OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    # a snapshot written by the reference's persistence machinery in that process loads in a FRESH interpreter that has not imported the network modules:
+    # persistence.py re-creates the classes from the module source stored in the pickle (the reason the overlaid files use absolute imports)
+    loader = tmp_path / 'load.py'
+    loader.write_text(LOADER)
+    r = subprocess.run([sys.executable, str(loader), overlay, ROOT, str(tmp_path / 'snapshot.pkl')], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0 and 'SNAPSHOT OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
