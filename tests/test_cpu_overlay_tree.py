@@ -98,9 +98,9 @@ with torch.no_grad():
     cp = iu.sample_posterior_camera_params(G, z2, c2)
     img = G(z=z2[:1], c=c2[:1], camera_params=cp[:1], camera_angles_cond=cp.angles[:1], noise_mode='const', render_opts=dict(cut_quantile=0.0))
     assert torch.is_tensor(img) and tuple(img.shape) == (1, 3, kw['img_resolution'], kw['img_resolution']) and torch.isfinite(img).all()
-    frames = iu.generate(ED(batch_size=1), G, ws=G.mapping(z=z2, c=c2), camera_params=cp, verbose=False, render_opts=dict(return_depth=True, return_depth_adapted=True))
-    assert isinstance(frames, dnnlib.TensorGroup) and set(frames.keys()) == {'img', 'depth', 'depth_adapted'} and len(frames) == 2       # TensorGroup.cat of two batches
-    assert tuple(frames.depth.shape) == (2, 1, kw['img_resolution'], kw['img_resolution']) and float(frames.img.min()) >= 0.0 and float(frames.img.max()) <= 1.0
+    frames = iu.generate(ED(batch_size=1), G, ws=G.mapping(z=z2, c=c2)[:1], camera_params=cp[:1], verbose=False, render_opts=dict(return_depth=True, return_depth_adapted=True))
+    assert isinstance(frames, dnnlib.TensorGroup) and set(frames.keys()) == {'img', 'depth', 'depth_adapted'} and len(frames) == 1
+    assert tuple(frames.depth.shape) == (1, 1, kw['img_resolution'], kw['img_resolution']) and float(frames.img.min()) >= 0.0 and float(frames.img.max()) <= 1.0
     mean_cam = iu.approximate_mean_camera_params(G, num_samples=16)
     assert tuple(mean_cam.angles.shape) == (1, 3)
 G.train()

@@ -61,26 +61,18 @@ def test_reference_networks_on_our_ops_small(overlay, monkeypatch):
     head = cases.depth_heads(B)
     monkeypatch.setattr(np.random, 'choice', lambda *a, **k: head.copy())
     s0 = dict(tc.stats)
-    G.train(); G.synthesis.nerf_noise_std = 0.0
-    with rh.injected_rng(randn=[n.clone() for n in noises], rand_like=[t['u_coarse'].reshape(B, Rr, N, 1)], rand=[t['u_fine'].reshape(B * Rr, N)]):
+    # (training forward and Gmain gradients of this overlay: test_reference_synthesis_network_on_our_renderer below)
+    with torch.no_grad():
         ws = G.mapping(t['z'], t['c'])
-        o = G.synthesis(ws, cam, patch_params=pp, render_opts=dict(concat_depth=True, return_depth=True))
-    assert tc.stats['aten'] > s0['aten'], 'the convolutions of the reference modules went through the product conv2d_gradfix'
-    assert maxrel(ws.detach().numpy(), gold['G/ws']) < 1e-5
-    assert maxrel(o.img.detach().numpy(), gold['G/train/img']) < 1e-4 and maxrel(o.depth.detach().numpy(), gold['G/train/depth']) < 1e-4
-    # Gmain gradients through D
+    assert maxrel(ws.numpy(), gold['G/ws']) < 1e-5
     D.train()
-    logits, _ = D(o.img, t['c'], patch_params=pp, camera_angles=t['angles'])
-    loss = torch.nn.functional.softplus(-logits).mean()
-    names = cases.probe_params('G'); pars = dict(G.named_parameters())
-    for n, gr in zip(names, torch.autograd.grad(loss, [pars[n] for n in names])):
-        assert l2rel(gr.numpy(), gold['G/grad/' + n]) < 5e-4, n
     # eval: the grouped-conv (fused_modconv) form of modulated_conv2d, const noise
     G.eval()
     ue = cases.eval_variates(kw, B); Re = kw['img_resolution'] ** 2
     with torch.no_grad(), rh.injected_rng(rand_like=[torch.from_numpy(ue['u_coarse']).reshape(B, Re, N, 1)], rand=[torch.from_numpy(ue['u_fine']).reshape(B * Re, N)]):
         oe = G.synthesis(ws.detach(), cam, noise_mode='const', render_opts=dict(concat_depth=True, return_depth=True))
     assert maxrel(oe.img.numpy(), gold['G/eval/img']) < 1e-4
+    assert tc.stats['aten'] > s0['aten'], 'the convolutions of the reference modules went through the product conv2d_gradfix'
     # D forward + the R1 double backward under the PRODUCT's no_weight_gradients (loss.py:238-253 uses conv2d_gradfix.no_weight_gradients)
     img = torch.from_numpy(gold['G/train/img']).requires_grad_(True)
     logits, feats = D(img, t['c'], patch_params=pp, camera_angles=t['angles'], predict_feat=True)
@@ -183,6 +175,7 @@ def test_reference_module_summary_walks_our_networks(monkeypatch, capsys):
     from src.training.rendering_utils import sample_camera_params
     cfgm = importlib.import_module('3dgp_b200.config')
     kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    kw.update(img_resolution=16, patch_res=8, tri_res=16, num_ray_steps=4)          # the walk is about module surfaces, not sizes
     cfg = cfgm.make_config(**kw, kd_weight=1.0, batch_size=4)
     G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
     tb = 2
@@ -196,5 +189,5 @@ def test_reference_module_summary_walks_our_networks(monkeypatch, capsys):
         logits = misc.print_module_summary(D, [img, c], module_kwargs={'patch_params': {'scales': torch.zeros(tb, 2), 'offsets': torch.zeros(tb, 2)}, 'camera_angles': torch.zeros(tb, 3)})
     text = capsys.readouterr().out
     n_g, n_d = sum(p.numel() for p in G.parameters()), sum(p.numel() for p in D.parameters())
-    assert str(n_d) in text and 'synthesis.tri_plane_decoder.b32:0' in text and 'synthesis.depth_adaptor.head' in text and 'b4.mbstd' in text      # every visited sub-module is listed; D's total is its parameter count
+    assert str(n_d) in text and 'synthesis.tri_plane_decoder.b16:0' in text and 'synthesis.depth_adaptor.head' in text and 'b4.mbstd' in text      # every visited sub-module is listed; D's total is its parameter count
     assert n_g > 0 and tuple(logits[0].shape) == (tb,)                # D returns (logits, features)
