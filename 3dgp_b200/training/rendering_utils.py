@@ -47,23 +47,35 @@ def _angles(cfg, B, device):
         yaw = (torch.rand((B, 1), device=device) - 0.5) * yr + yc
         v = (torch.rand((B, 1), device=device) - 0.5) * pr + pc
         pitch = torch.arccos(1 - 2 * torch.clamp(v / np.pi, 1e-5, 1 - 1e-5))
+    elif cfg.dist == 'truncnorm':       # configs/camera/base.yaml: centred on the middle of the allowed range, clipped to it
+        yaw = _truncnorm((cfg.yaw.max + cfg.yaw.min) * 0.5, cfg.yaw.std, cfg.yaw.min, cfg.yaw.max, B, device).unsqueeze(1)
+        pitch = _truncnorm((cfg.pitch.max + cfg.pitch.min) * 0.5, cfg.pitch.std, cfg.pitch.min, cfg.pitch.max, B, device).unsqueeze(1)
     else:
-        raise NotImplementedError(f'camera angle distribution `{cfg.dist}` (truncnorm needs scipy; use uniform/normal/spherical_uniform)')
+        raise NotImplementedError(f'camera angle distribution `{cfg.dist}` (built: uniform / normal / truncnorm / spherical_uniform)')
     pitch = torch.clamp(pitch, 1e-5, np.pi - 1e-5)
     return torch.cat([yaw, pitch, torch.zeros_like(yaw)], dim=1)
 
 
+def _truncnorm(mean, std, lo, hi, B, device):
+    """Normal(mean, std) restricted to [lo, hi], drawn as the reference draws it (rendering_utils.py:140-146: scipy's sampler on numpy's global stream)."""
+    from scipy.stats import truncnorm
+    x = truncnorm.rvs(a=(lo - mean) / std, b=(hi - mean) / std, loc=mean, scale=std, size=(B,))
+    return torch.from_numpy(x).float().to(device)
+
+
 def _scalar(cfg, B, device):
     if cfg.dist == 'normal':
-        assert cfg.std == 0.0
+        assert cfg.std == 0.0, 'Scalar must be bounded'
         return torch.full([B], float(cfg.mean), device=device)
+    if cfg.dist == 'truncnorm':
+        return _truncnorm(cfg.mean, cfg.std, cfg.min, cfg.max, B, device)
     if cfg.dist == 'uniform':
         return torch.rand(B, device=device) * (cfg.max - cfg.min) + cfg.min
     raise NotImplementedError(cfg.dist)
 
 
 def sample_camera_params(cfg, batch_size, device='cpu', origin_angles=None):
-    """Prior camera sampling (:150-156) for the uniform / normal / spherical_uniform distributions of configs/camera."""
+    """Prior camera sampling (:150-156) for the uniform / normal / truncnorm / spherical_uniform distributions of configs/camera (same draws from the same RNG state as the reference)."""
     angles = _angles(cfg.origin.angles, batch_size, device) if origin_angles is None else origin_angles
     fov = _scalar(cfg.fov, batch_size, device)
     radius = _scalar(cfg.origin.radius, batch_size, device)

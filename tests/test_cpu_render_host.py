@@ -132,3 +132,45 @@ def test_launcher_geometry_helpers_equal_the_reference():
     verdicts = [(fov, r, s, ours.validate_image_plane(fov, r, s, step=5e-2)) for fov, r, s in ((45.0, 1.0, 0.5), (10.0, 1.0, 0.5), (120.0, 3.0, 0.5), (30.0, 2.0, 0.5))]
     assert [v[3] for v in verdicts] == [True, True, False, False]
     assert all(v[3] == ref.validate_image_plane(v[0], v[1], v[2], step=5e-2) for v in verdicts)
+
+
+def test_camera_prior_sampling_equals_the_reference_draw_for_draw():
+    """`sample_camera_params` of the stand-alone rendering_utils.py vs the reference's (rendering_utils.py:72-156) from the same torch / numpy RNG state, for
+    every distribution the shipped camera configs use (configs/camera/{base, uniform, ...}.yaml): uniform, normal, truncnorm, spherical_uniform angles;
+    constant / uniform / truncnorm scalars; given origin angles."""
+    import copy
+    import importlib
+    import numpy as np
+    import pytest
+    import torch
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('the unmodified reference is only present in the build container')
+    ns = rh.load()
+    ref = ns.rendering_utils
+    ours = importlib.import_module('3dgp_b200.training.rendering_utils')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    base = rh.make_cfg()[0]['camera']
+
+    def variant(**edits):
+        c = copy.deepcopy(base)
+        for path, v in edits.items():
+            node = c
+            keys = path.split('__')
+            for k in keys[:-1]:
+                node = node[k]
+            node[keys[-1]] = v
+        return c
+    cases_ = {'uniform': variant(), 'normal': variant(origin__angles__dist='normal'), 'truncnorm': variant(origin__angles__dist='truncnorm'),
+              'spherical': variant(origin__angles__dist='spherical_uniform'), 'radius_uniform': variant(origin__radius=dict(dist='uniform', min=0.8, max=1.2)),
+              'fov_truncnorm': variant(fov=dict(dist='truncnorm', mean=20.0, std=3.0, min=10.0, max=45.0))}
+    for name, c in cases_.items():
+        for given in (None, torch.full([7, 3], 0.25)):
+            torch.manual_seed(3); np.random.seed(3)
+            a = ref.sample_camera_params(ns.dnnlib.EasyDict.init_recursively(copy.deepcopy(c)), 7, 'cpu', given)
+            torch.manual_seed(3); np.random.seed(3)
+            b = ours.sample_camera_params(dn.EasyDict.init_recursively(copy.deepcopy(c)), 7, 'cpu', given)
+            assert all(torch.equal(a[k], b[k]) for k in ('angles', 'fov', 'radius', 'look_at')), name
+    ang = base['origin']['angles']
+    assert ref.get_mean_angles_values(ns.dnnlib.EasyDict.init_recursively(ang)) == ours.get_mean_angles_values(dn.EasyDict.init_recursively(ang))
+    assert ref.get_mean_sampling_value(ns.dnnlib.EasyDict.init_recursively(base['fov'])) == ours.get_mean_sampling_value(dn.EasyDict.init_recursively(base['fov']))
