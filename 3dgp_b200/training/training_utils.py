@@ -40,13 +40,16 @@ def extract_patches(x, patch_params, resolution):
 
 
 def sample_patch_params(batch_size, patch_cfg, device='cpu'):
-    """Beta / uniform patch scales shared inside minibatch-std groups (training_utils.py:57-143)."""
+    """Beta / uniform / discrete-uniform patch scales shared inside minibatch-std groups (training_utils.py:57-143)."""
     g = patch_cfg.mbstd_group_size
     num_groups = batch_size // g
     if patch_cfg.distribution == 'beta':
         sx = np.random.beta(a=patch_cfg.alpha, b=patch_cfg.beta, size=num_groups) * (patch_cfg.max_scale - patch_cfg.min_scale) + patch_cfg.min_scale
     elif patch_cfg.distribution == 'uniform':
         sx = np.random.rand(num_groups) * (patch_cfg.max_scale - patch_cfg.min_scale) + patch_cfg.min_scale
+    elif patch_cfg.distribution == 'discrete_uniform':        # configs/training/patch_discrete_uniform.yaml: the listed scales that lie inside the current range
+        support = [v for v in patch_cfg.discrete_support if patch_cfg.min_scale <= v <= patch_cfg.max_scale]
+        sx = np.random.choice(support, size=num_groups, replace=True).astype(np.float32)
     else:
         raise NotImplementedError(patch_cfg.distribution)
     sx = torch.from_numpy(sx).float().to(device)

@@ -174,3 +174,35 @@ def test_camera_prior_sampling_equals_the_reference_draw_for_draw():
     ang = base['origin']['angles']
     assert ref.get_mean_angles_values(ns.dnnlib.EasyDict.init_recursively(ang)) == ours.get_mean_angles_values(dn.EasyDict.init_recursively(ang))
     assert ref.get_mean_sampling_value(ns.dnnlib.EasyDict.init_recursively(base['fov'])) == ours.get_mean_sampling_value(dn.EasyDict.init_recursively(base['fov']))
+
+
+def test_patch_sampling_and_schedules_equal_the_reference_draw_for_draw():
+    """Stand-alone training_utils.py vs the reference's (training_utils.py:8-214) from the same RNG state: patch parameters for the three shipped
+    distributions (configs/training/patch_{beta, uniform, discrete_uniform}.yaml), patch extraction, class sampling, the linear schedule."""
+    import importlib
+    import numpy as np
+    import pytest
+    import torch
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('the unmodified reference is only present in the build container')
+    ns = rh.load()
+    ref = ns.training_utils
+    ours = importlib.import_module('3dgp_b200.training.training_utils')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    common = dict(min_scale=0.25, max_scale=1.0, mbstd_group_size=4, alpha=1.0, beta=0.5, discrete_support=[0.125, 0.25, 0.5, 1.0])
+    for dist in ('beta', 'uniform', 'discrete_uniform'):
+        pc = dict(common, distribution=dist)
+        torch.manual_seed(5); np.random.seed(5)
+        a = ref.sample_patch_params(8, ns.dnnlib.EasyDict(**pc))
+        torch.manual_seed(5); np.random.seed(5)
+        b = ours.sample_patch_params(8, dn.EasyDict(**pc))
+        assert torch.equal(a['scales'], b['scales']) and torch.equal(a['offsets'], b['offsets']) and a['scales'].dtype == b['scales'].dtype, dist
+    x = torch.randn(8, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(ref.extract_patches(x, a, resolution=16), ours.extract_patches(x, b, resolution=16))
+    torch.manual_seed(6); ca = ref.sample_random_c(9, 5, 'cpu')
+    torch.manual_seed(6); cb = ours.sample_random_c(9, 5, 'cpu')
+    assert torch.equal(ca, cb)
+    for step in (-1, 0, 10, 250, 500, 501, 10_000):
+        assert ref.linear_schedule(step, 1.0, 0.25, 500) == ours.linear_schedule(step, 1.0, 0.25, 500)
+        assert ref.linear_schedule(step, 0.0, 1.0, 300, start_step=100) == ours.linear_schedule(step, 0.0, 1.0, 300, start_step=100)
