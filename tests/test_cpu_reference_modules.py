@@ -191,3 +191,43 @@ def test_reference_module_summary_walks_our_networks(monkeypatch, capsys):
     n_g, n_d = sum(p.numel() for p in G.parameters()), sum(p.numel() for p in D.parameters())
     assert str(n_d) in text and 'synthesis.tri_plane_decoder.b16:0' in text and 'synthesis.depth_adaptor.head' in text and 'b4.mbstd' in text      # every visited sub-module is listed; D's total is its parameter count
     assert n_g > 0 and tuple(logits[0].shape) == (tb,)                # D returns (logits, features)
+
+
+def test_epigraf_model_configuration_matches_the_reference_run_live(monkeypatch):
+    """The second 3-D model family of the reference, configs/model/epigraf.yaml (no depth adaptor, no depth channel into D, `discriminator.fmaps: 0.5`): the
+    UNMODIFIED reference networks run live on CPU next to this repo's modules (emulated ABI) with the same weights, layer noise and sampling variates --
+    training forward, Gmain loss through D, D logits."""
+    emu.install(monkeypatch)
+    ns = rh.load()
+    cfgm = importlib.import_module('3dgp_b200.config')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    kw.update(use_depth=False, d_fmaps=0.5)
+    Gc, Dc, m = rh.make_cfg(**kw)
+    Gr = rh.build_reference_G(Gc, m['img_resolution'], seed=0)
+    Dr = rh.build_reference_D(Dc, m['patch_res'], use_depth=False, embedding_dim=0, seed=1, fp32=True)
+    cfg = cfgm.make_config(**kw, kd_weight=0.0)
+    G, D = cfgm.build_networks(cfg, 'cpu', fp32_D=True)
+    assert G.synthesis.depth_adaptor is None and Gr.synthesis.depth_adaptor is None
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == {k: tuple(v.shape) for k, v in Gr.state_dict().items()}
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == {k: tuple(v.shape) for k, v in Dr.state_dict().items()}
+    sdG = cases.fill_state_dict({k: tuple(v.shape) for k, v in Gr.state_dict().items()}, Gr.state_dict(), seed=100)
+    sdD = cases.fill_state_dict({k: tuple(v.shape) for k, v in Dr.state_dict().items()}, Dr.state_dict(), seed=200)
+    for net, sd in ((Gr, sdG), (G, sdG), (Dr, sdD), (D, sdD)):
+        net.load_state_dict(sd); net.train()
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(kw).items()}
+    B, N, Rr = t['z'].shape[0], kw['num_ray_steps'], kw['patch_res'] ** 2
+    noises = [torch.from_numpy(n) for n in cases.layer_noises(kw, B)]
+    pp = dict(scales=t['patch_scales'], offsets=t['patch_offsets'])
+    Gr.synthesis.nerf_noise_std = G.synthesis.nerf_noise_std = 0.0
+    with torch.no_grad():
+        cam_r = ns.dnnlib.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+        with rh.injected_rng(randn=[n.clone() for n in noises], rand_like=[t['u_coarse'].reshape(B, Rr, N, 1)], rand=[t['u_fine'].reshape(B * Rr, N)]):
+            img_r = Gr.synthesis(Gr.mapping(t['z'], t['c']), cam_r, patch_params=pp)
+        logits_r, _ = Dr(img_r, t['c'], patch_params=pp, camera_angles=t['angles'])
+        cam = dn.TensorGroup(angles=t['angles'], fov=t['fov'], radius=t['radius'], look_at=t['look_at'])
+        img = G.synthesis(G.mapping(t['z'], t['c']), cam, patch_params=pp, noise_mode='random', layer_noises=noises,
+                          render_opts=dict(u_coarse=t['u_coarse'], u_fine=t['u_fine'], mlp_mode=0))
+        logits, _ = D(img, t['c'], patch_params=pp, camera_angles=t['angles'])
+    assert torch.is_tensor(img) and tuple(img.shape) == tuple(img_r.shape) == (B, 3, kw['patch_res'], kw['patch_res'])
+    assert maxrel(img.numpy(), img_r.numpy()) < 1e-4 and maxrel(logits.numpy(), logits_r.numpy()) < 1e-4
