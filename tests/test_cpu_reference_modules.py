@@ -231,3 +231,28 @@ def test_epigraf_model_configuration_matches_the_reference_run_live(monkeypatch)
         logits, _ = D(img, t['c'], patch_params=pp, camera_angles=t['angles'])
     assert torch.is_tensor(img) and tuple(img.shape) == tuple(img_r.shape) == (B, 3, kw['patch_res'], kw['patch_res'])
     assert maxrel(img.numpy(), img_r.numpy()) < 1e-4 and maxrel(logits.numpy(), logits_r.numpy()) < 1e-4
+
+
+def test_reference_augment_pipe_on_our_ops(monkeypatch):
+    """src/training/augment.py (ADA, off in the 3dgp configuration but part of the reference loop) imports `upfirdn2d` and `conv2d_gradfix` from the overlaid
+    package (:19-21) and calls forms nothing else on the path uses: `upsample2d` / `downsample2d` with a 12-tap separable wavelet filter, negative padding
+    and `flip_filter=True` (:294, :305), and `conv2d` with `groups = batch * channels` (:413-414).  All fifteen augmentations on, same RNG state: output and
+    input gradient with this repo's op modules bound equal the reference's own."""
+    ns = rh.load()
+    import src.training.augment as aug
+    pipe = aug.AugmentPipe(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1,
+                           imgfilter=1, noise=1, cutout=1).train()
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+
+    def run():
+        torch.manual_seed(1); np.random.seed(1)
+        xi = x.clone().requires_grad_(True)
+        y = pipe(xi, num_color_channels=3)
+        g, = torch.autograd.grad(y.square().sum(), xi)
+        return y.detach(), g
+    y_ref, g_ref = run()                                  # the reference's own ops (their CPU implementations)
+    emu.install(monkeypatch)
+    monkeypatch.setattr(aug, 'upfirdn2d', importlib.import_module('3dgp_b200.torch_utils.ops.upfirdn2d'))
+    monkeypatch.setattr(aug, 'conv2d_gradfix', importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix'))
+    y, g = run()
+    assert maxrel(y.numpy(), y_ref.numpy()) < 1e-5 and maxrel(g.numpy(), g_ref.numpy()) < 1e-5
