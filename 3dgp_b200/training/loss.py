@@ -37,8 +37,15 @@ def emd2_1d(a, b):
 
 
 class StyleGAN2Loss:
-    def __init__(self, cfg, device, G, D, r1_gamma=10):
-        self.cfg, self.device, self.G, self.D, self.r1_gamma = cfg, device, G, D, r1_gamma
+    def __init__(self, cfg, device, G, D, augment_pipe=None, r1_gamma=10, style_mixing_prob=0, pl_batch_shrink=2, pl_decay=0.01):
+        """Same constructor keywords as the reference class (loss.py:34), so `training_loop.py:186` can build either one.  `augment_pipe` (ADA, augment.py) is
+        applied to the discriminator's input as in loss.py:98-99; style mixing and path-length regularisation are off in configs/model/{3dgp,epigraf}.yaml
+        (`style_mixing_prob` is only set for model=stylegan2, train.py:200; `pl_weight: 0`) and are not built."""
+        if style_mixing_prob > 0:
+            raise NotImplementedError('style mixing (model=stylegan2 only, train.py:200) is not on the 3dgp path')
+        if cfg.model.loss_kwargs.get('pl_weight', 0) > 0:
+            raise NotImplementedError('path-length regularisation (pl_weight > 0) is not on the 3dgp path')
+        self.cfg, self.device, self.G, self.D, self.r1_gamma, self.augment_pipe = cfg, device, G, D, r1_gamma, augment_pipe
         lk = cfg.model.loss_kwargs
         self.blur_init_sigma = lk.get('blur_init_sigma', 0)
         self.blur_fade_kimg = lk.get('blur_fade_kimg', 0)
@@ -115,6 +122,8 @@ class StyleGAN2Loss:
             bs = np.floor(blur_sigma * 3)
             f = torch.arange(-bs, bs + 1, device=img.device).div(30.0).square().neg().exp2()   # loss.py:93-94
             img = torch.cat([img[:, :3], upfirdn2d.filter2d(img[:, [3]], f / f.sum()), img[:, 4:]], dim=1)
+        if self.augment_pipe is not None:
+            img = self.augment_pipe(img, num_color_channels=self.G.img_channels)
         return self.D(img, c, update_emas=update_emas, **kwargs)
 
     def compute_sample_weights(self, patch_params, scale_pow=1):
@@ -125,6 +134,7 @@ class StyleGAN2Loss:
         """real_data: {img [B,3,H,W], depth [B,1,H,W], c, embs, camera_angles}; gen_data: {z, c, camera_params}.
         final_backward: optional callable invoked right before the LAST backward() of the phase (training/step.py arms the bucketed all-reduce there)."""
         arm = final_backward if final_backward is not None else (lambda: None)
+        phase = {'Gall': 'Gmain'}.get(phase, phase)      # without lazy G regularisation the reference loop names G's only phase 'Gall' (training_loop.py:195); pl_weight is 0 here
         assert phase in ['Gmain', 'Dmain', 'Dreg', 'Dall']
         if self.r1_gamma == 0:
             phase = {'Dreg': 'none', 'Dall': 'Dmain'}.get(phase, phase)
