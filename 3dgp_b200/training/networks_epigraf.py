@@ -104,6 +104,24 @@ class SynthesisNetwork(torch.nn.Module):
         if self.depth_adaptor is not None:
             self.depth_adaptor.progressive_update(cur_kimg)
 
+    @torch.no_grad()
+    def compute_densities(self, ws, coords, max_batch_res=32, **block_kwargs):
+        """sigma of the radiance field at world points `coords` [B, M, 3] -> [B, M, 1] (networks_epigraf.py:196-208; scripts/extract_geometry.py samples a
+        volume with it).  Not a rendering: no rays, no compositing -- each point reads its three bilinear plane taps (points outside the cube read zeros),
+        the taps are averaged and go through the tri-plane MLP; evaluated in chunks of max_batch_res^3 points."""
+        F_, P = self.cfg.tri_plane.feat_dim, self.cfg.tri_plane.res
+        dec = self.tri_plane_decoder(ws[:, :self.tri_plane_decoder.num_ws], **block_kwargs)
+        B = dec.shape[0]
+        planes = dec[:, :3 * F_].reshape(B * 3, F_, P, P)                   # plane-major channel groups: xy, xz, yz
+        out = []
+        for pts in coords.split(max_batch_res ** 3, dim=1):
+            q = pts / self.cfg.camera.cube_scale
+            uv = torch.stack([q[..., [0, 1]], q[..., [0, 2]], q[..., [1, 2]]], dim=1).reshape(B * 3, 1, -1, 2)
+            taps = torch.nn.functional.grid_sample(planes, uv, mode='bilinear', align_corners=True)       # [B*3, F, 1, m]
+            feats = taps.reshape(B, 3, F_, -1).permute(0, 1, 3, 2)                                         # [B, 3, m, F]
+            out.append(self.tri_plane_mlp(feats)['sigma'])
+        return torch.cat(out, dim=1)
+
     def forward(self, ws, camera_params, patch_params=None, render_opts={}, **block_kwargs):
         """ws [B,num_ws,w_dim]; camera_params {angles [B,3], fov [B], radius [B], look_at [B,3]}; patch_params {scales, offsets}.
         render_opts may carry `u_coarse`, `u_fine`, `sn_coarse`, `sn_fine`, `depth_head_idx` (parity runs)."""

@@ -256,3 +256,26 @@ def test_reference_augment_pipe_on_our_ops(monkeypatch):
     monkeypatch.setattr(aug, 'conv2d_gradfix', importlib.import_module('3dgp_b200.torch_utils.ops.conv2d_gradfix'))
     y, g = run()
     assert maxrel(y.numpy(), y_ref.numpy()) < 1e-5 and maxrel(g.numpy(), g_ref.numpy()) < 1e-5
+
+
+def test_compute_densities_matches_the_reference_run_live(monkeypatch):
+    """`SynthesisNetwork.compute_densities` (networks_epigraf.py:196-208, the call scripts/extract_geometry.py:30 makes): this repo's method next to the
+    reference's on the same weights and query points (inside and outside the scene cube), evaluated in several chunks."""
+    emu.install(monkeypatch)
+    ns = rh.load()
+    cfgm = importlib.import_module('3dgp_b200.config')
+    kw = {k: v for k, v in cases.net_kwargs('small').items() if k != 'learn_camera_dist'}
+    Gc, _, m = rh.make_cfg(**kw)
+    Gr = rh.build_reference_G(Gc, m['img_resolution'], seed=0).eval()
+    G, _ = cfgm.build_networks(cfgm.make_config(**kw), 'cpu', fp32_D=True)
+    sd = cases.fill_state_dict({k: tuple(v.shape) for k, v in Gr.state_dict().items()}, Gr.state_dict(), seed=100)
+    Gr.load_state_dict(sd); G.load_state_dict(sd); G.eval()
+    t = {k: torch.from_numpy(v) for k, v in cases.net_inputs(kw).items()}
+    g = torch.Generator().manual_seed(4)
+    coords = (torch.rand(t['z'].shape[0], 700, 3, generator=g) * 2 - 1) * 0.6            # cube half-extent is 0.5: some points fall outside
+    with torch.no_grad():
+        ws = Gr.mapping(t['z'], t['c'])
+        want = Gr.synthesis.compute_densities(ws, coords, max_batch_res=6, noise_mode='const')
+        got = G.synthesis.compute_densities(ws, coords, max_batch_res=6, noise_mode='const')
+    assert tuple(got.shape) == tuple(want.shape) == (t['z'].shape[0], 700, 1)
+    assert maxrel(got.numpy(), want.numpy()) < 1e-4
