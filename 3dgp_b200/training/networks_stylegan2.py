@@ -177,3 +177,68 @@ class SynthesisBlock(torch.nn.Module):
             else:
                 img = img.add_(y)
         return x, img
+
+
+class SynthesisNetwork(torch.nn.Module):
+    """The 2-D StyleGAN2 image synthesis network (`model=stylegan2`, reference networks_stylegan2.py:281-340): the same SynthesisBlocks from 4^2 up to the image
+    resolution, no volume rendering.  Kept so that the file can replace the reference's for every model it serves; the tri-plane decoder of the 3-D models is
+    `networks_epigraf.SynthesisBlocksSequence` over the same blocks."""
+
+    def __init__(self, cfg, img_resolution, img_channels, num_fp16_res=4, **block_kwargs):
+        assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.cfg, self.img_resolution, self.img_channels, self.num_fp16_res = cfg, img_resolution, img_channels, num_fp16_res
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
+        width = lambda res: min(int(cfg.cbase * cfg.fmaps) // res, cfg.cmax)
+        first_fp16 = max(2 ** (self.img_resolution_log2 + 1 - num_fp16_res), 8)
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            last = (res == img_resolution)
+            block = SynthesisBlock(width(res // 2) if res > 4 else 0, width(res), w_dim=cfg.w_dim, resolution=res, img_channels=img_channels, is_last=last,
+                                   use_fp16=(res >= first_fp16), architecture=cfg.get('architecture', 'skip'), **block_kwargs)
+            self.num_ws += block.num_conv + (block.num_torgb if last else 0)
+            setattr(self, f'b{res}', block)
+
+    def forward(self, ws, camera_params=None, patch_params=None, render_opts={}, layer_noises=None, **block_kwargs):
+        """camera_params / render_opts are accepted for call compatibility with the 3-D generators (the loss passes them to either);
+        layer_noises: optional list of [B,1,r,r] noise images, one per noisy layer in execution order (parity runs)."""
+        assert not render_opts.get('concat_depth', False), 'a 2-D generator has no depth to concatenate'
+        assert tuple(ws.shape[1:]) == (self.num_ws, self.cfg.w_dim), tuple(ws.shape)
+        ws = ws.to(torch.float32)
+        x = img = None
+        first = 0
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            given = None if layer_noises is None else layer_noises[first:first + block.num_conv]
+            x, img = block(x, img, ws.narrow(1, first, block.num_conv + block.num_torgb), layer_noises=given, **block_kwargs)
+            first += block.num_conv
+        if self.training and patch_params is not None:
+            from .training_utils import extract_patches
+            img = extract_patches(img, patch_params, resolution=self.cfg.patch.resolution)
+        if render_opts.get('return_depth', False):
+            from ..dnnlib import TensorGroup
+            return TensorGroup(img=img, depth=torch.zeros_like(img))
+        return img
+
+
+class Generator(torch.nn.Module):
+    """2-D StyleGAN2 generator (networks_stylegan2.py:346-375): mapping network + SynthesisNetwork."""
+
+    def __init__(self, cfg, img_resolution, img_channels, mapping_kwargs={}, **synthesis_kwargs):
+        super().__init__()
+        from .layers import MappingNetwork
+        self.cfg, self.z_dim, self.c_dim, self.w_dim = cfg, cfg.z_dim, cfg.c_dim, cfg.w_dim
+        self.img_resolution, self.img_channels = img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(cfg=cfg, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=self.z_dim, c_dim=self.c_dim, w_dim=self.w_dim, num_ws=self.num_ws, num_layers=cfg.map_depth, **mapping_kwargs)
+        self.params_to_freeze = None
+
+    def forward(self, z, c, camera_angles_cond=None, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)
+
+    def progressive_update(self, cur_kimg):
+        pass
+

@@ -279,3 +279,34 @@ def test_compute_densities_matches_the_reference_run_live(monkeypatch):
         got = G.synthesis.compute_densities(ws, coords, max_batch_res=6, noise_mode='const')
     assert tuple(got.shape) == tuple(want.shape) == (t['z'].shape[0], 700, 1)
     assert maxrel(got.numpy(), want.numpy()) < 1e-4
+
+
+def test_stylegan2_2d_generator_matches_the_reference_run_live(monkeypatch):
+    """`model=stylegan2` (the 2-D generator of networks_stylegan2.py:281-375, kept so the overlaid file serves every model): this repo's classes next to the
+    reference's, same weights and layer noise, fp32 blocks; training forward with patch extraction and the eval (grouped-conv) form."""
+    emu.install(monkeypatch)
+    ns = rh.load()
+    sg = importlib.import_module('3dgp_b200.training.networks_stylegan2')
+    dn = importlib.import_module('3dgp_b200.dnnlib')
+    g_cfg = dict(cbase=512, cmax=32, fmaps=1.0, w_dim=32, z_dim=32, c_dim=4, map_depth=2, architecture='skip',
+                 patch=dict(enabled=True, resolution=16), camera_cond=False)
+    kwargs = dict(img_resolution=32, img_channels=3, mapping_kwargs=dict(camera_cond=False, camera_cond_drop_p=0.0, mean_camera_params=None),
+                  fused_modconv_default='inference_only', num_fp16_res=0, conv_clamp=None)
+    torch.manual_seed(0)
+    Gr = ns.networks_stylegan2.Generator(cfg=ns.dnnlib.EasyDict.init_recursively(g_cfg), **kwargs)
+    G = sg.Generator(cfg=dn.EasyDict.init_recursively(g_cfg), **kwargs)
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == {k: tuple(v.shape) for k, v in Gr.state_dict().items()} and G.num_ws == Gr.num_ws
+    sd = cases.fill_state_dict({k: tuple(v.shape) for k, v in Gr.state_dict().items()}, Gr.state_dict(), seed=300)
+    Gr.load_state_dict(sd); G.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(2)
+    z, c = torch.randn(4, 32, generator=gen), torch.eye(4)
+    pp = dict(scales=torch.full([4, 2], 0.5), offsets=torch.rand(4, 2, generator=gen) * 0.5)
+    noises = [torch.randn(4, 1, r, r, generator=gen) for r in (4, 8, 8, 16, 16, 32, 32)]
+    Gr.train(); G.train()
+    with torch.no_grad():
+        with rh.injected_rng(randn=[n.clone() for n in noises]):
+            want = Gr(z, c, patch_params=pp, render_opts=dict(return_depth=True))
+        got = G(z, c, patch_params=pp, render_opts=dict(return_depth=True), noise_mode='random', layer_noises=noises)
+        assert tuple(got.img.shape) == tuple(want.img.shape) == (4, 3, 16, 16) and maxrel(got.img.numpy(), want.img.numpy()) < 1e-4 and float(got.depth.abs().max()) == 0.0
+        Gr.eval(); G.eval()
+        assert maxrel(G(z, c, noise_mode='const').numpy(), Gr(z, c, noise_mode='const').numpy()) < 1e-4

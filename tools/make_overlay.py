@@ -36,7 +36,7 @@ FILES = {
 PERSISTENT = {
     'training/layers.py': ['FullyConnectedLayer', 'MappingNetwork', 'Conv2dLayer', 'ScalarEncoder1d', 'FourierEncoder1d'],
     'training/networks_epigraf.py': ['TriPlaneMLP', 'SynthesisBlocksSequence', 'SynthesisNetwork', 'Generator'],
-    'training/networks_stylegan2.py': ['SynthesisLayer', 'ToRGBLayer', 'SynthesisBlock'],
+    'training/networks_stylegan2.py': ['SynthesisLayer', 'ToRGBLayer', 'SynthesisBlock', 'SynthesisNetwork', 'Generator'],
     'training/networks_discriminator.py': ['DiscriminatorBlock', 'MinibatchStdLayer', 'DiscriminatorEpilogue'],
     'training/networks_depth_adaptor.py': ['DepthAdaptor'],
     'training/networks_camera_adaptor.py': ['ParamsAdaptor', 'CameraAdaptor'],
