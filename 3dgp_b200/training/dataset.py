@@ -53,7 +53,7 @@ def _strip_root(fname, root):
 
 
 class _Archive:
-    """File listing + byte access for a directory or a zip.  Zip handles are per thread: `zipfile.ZipFile` serialises concurrent reads on one handle."""
+    """File listing + byte access for a directory or a zip.  Zip handles are per thread (`zipfile.ZipFile` serialises concurrent reads on one handle) and per process (never shared across fork)."""
 
     def __init__(self, path):
         self.path = path
@@ -73,8 +73,11 @@ class _Archive:
             with open(os.path.join(self.path, name), 'rb') as f:
                 return f.read()
         z = getattr(self._local, 'zip', None)
-        if z is None:
+        if z is None or getattr(self._local, 'pid', None) != os.getpid():
+            # first use in this thread -- or in this PROCESS: a handle inherited through fork() (DataLoader workers) shares its file offset with the
+            # parent and with every sibling, and concurrent seeks corrupt each other's reads
             z = self._local.zip = zipfile.ZipFile(self.path)
+            self._local.pid = os.getpid()
         return z.read(name)
 
     def close(self):
